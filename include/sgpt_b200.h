@@ -1,0 +1,183 @@
+/*
+ * sgpt_b200 — C ABI of the B200-native SGPT bi-encoder hot path.
+ *
+ * The reference (Muennighoff/sgpt @ 37c8bf09) is pure Python and has no FFI layer; its plug-in boundary is the pair
+ * of duck-typed protocols in biencoder/beir/custommodels/exact_search.py:22-32 (embedder: encode_queries /
+ * encode_corpus; retriever: search).  This header is the C boundary that sits *underneath* those protocols: every
+ * entry point replaces the PyTorch/HF library call(s) cited next to it.  All pointers are DEVICE pointers owned by
+ * the caller unless stated otherwise; no torch types cross this boundary.  Every function returns SGPT_OK (0) or an
+ * error code; sgpt_last_error() returns a thread-local message.  Nothing throws.  A handle is bound to the device
+ * that was current when it was created, is not thread-safe, and may be used on any stream of that device as long
+ * as calls are externally ordered.
+ *
+ * Abbreviations in citations:  BDR = biencoder/beir/beir_dense_retriever.py, XS = .../custommodels/exact_search.py,
+ * ST/ = biencoder/nli_msmarco/sentence-transformers/sentence_transformers/, HF: = transformers/models/ (third-party
+ * dependency of the reference, pinned >=4.6,<5 by ST's setup.py:21).
+ */
+#ifndef SGPT_B200_H_
+#define SGPT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGPT_ABI_VERSION 1
+
+#define SGPT_OK 0
+#define SGPT_ERR_INVALID 1     /* bad argument / unsupported shape */
+#define SGPT_ERR_CUDA 2        /* a CUDA runtime/driver call failed */
+#define SGPT_ERR_UNSUPPORTED 3 /* valid request this build does not implement */
+
+typedef void* sgpt_stream_t; /* cudaStream_t */
+
+int sgpt_abi_version(void);
+const char* sgpt_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Encoder building blocks (rows F1–F7 of SURVEY.md §8a).  Token-major, *ragged* layout: the B sequences of a batch
+ * are packed back to back into T = sum(len_b) rows ("tokens"); padding never exists on the device.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* F1. resid[t,:] = wte[ids[t],:] (+ wpe[pos[t],:] if wpe != NULL)       HF:gpt_neo/modeling_gpt_neo.py:462-463
+ *     ids,pos int32[T]; wte bf16[vocab,d]; wpe bf16[max_pos,d] or NULL (GPT-J / BLOOM); resid fp32[T,d]. */
+int sgpt_embed_tokens(const int32_t* ids, const int32_t* pos, const void* wte, const void* wpe, float* resid,
+                      int T, int d, int vocab, int max_pos, sgpt_stream_t stream);
+
+/* F2/F7. y = LayerNorm(x; gamma, beta, eps) row-wise, fp32 statistics, bf16 output.   HF:gpt_neo/...:332,345,492
+ *     x fp32[T,d]; gamma,beta fp32[d]; y bf16[T,d]. */
+int sgpt_layernorm(const float* x, const float* gamma, const float* beta, void* y, int T, int d, float eps,
+                   sgpt_stream_t stream);
+
+/* F3/F5/F6. y = epilogue(x @ w^T + bias).   torch.nn.Linear call sites HF:gpt_neo/...:84-87,153,295-309
+ *     x bf16[M,K] (row pitch ldx), w bf16[N,K] (nn.Linear weight layout, row pitch ldw), bias fp32[N] or NULL.
+ *     epilogue: SGPT_EPI_BF16       out bf16[M,N]  = acc + bias
+ *               SGPT_EPI_GELU_BF16  out bf16[M,N]  = gelu_new(acc + bias)       (HF activations.py NewGELUActivation)
+ *               SGPT_EPI_RESID_F32  out fp32[M,N]  = resid + acc + bias         (resid fp32[M,N], may alias out)
+ *     Runs on the tcgen05 tensor cores (TMA-staged tiles, TMEM accumulators). */
+#define SGPT_EPI_BF16 0
+#define SGPT_EPI_GELU_BF16 1
+#define SGPT_EPI_RESID_F32 2
+int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out, int64_t ldo,
+                const float* resid, int M, int N, int K, int epilogue, sgpt_stream_t stream);
+
+/* F4. Causal self-attention over a ragged batch.    HF:gpt_neo/modeling_gpt_neo.py:105-130 (_attn)
+ *     qkv bf16[T, 3*H*hd]: per token [q(H*hd) | k(H*hd) | v(H*hd)];  out bf16[T, H*hd].
+ *     cu_seqlens int32[B+1] (row offsets of each sequence; cu[B] == T).
+ *     scale: multiplies q.k before softmax (GPT-Neo: 1.0 — unscaled, :110; GPT-J: 1/sqrt(hd)).
+ *     window: 0 = plain causal; w > 0 = GPT-Neo local attention (key j visible to query i iff i-w < j <= i, :63-66).
+ *     impl: 0 = tcgen05 tensor-core kernel, 1 = SIMT cross-check kernel (test infrastructure). */
+int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seqlens, int B, int T, int H, int hd, float scale,
+                   int window, int max_seqlen, int impl, sgpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * P1/P2. Pooling over the ragged sequence dimension, fp32 accumulate.
+ *     BDR:258-270 == ST/models/Pooling.py:99-125 (weightedmean), BDR:238-242 (mean), BDR:271-282 (lasttoken)
+ *     x fp32[T,d] (residual stream or hidden state); pos int32[T] = index of the token in its *padded* row
+ *     (weight of token t is pos[t]+1 for weightedmean); out fp32[B,d].
+ *     If gamma != NULL the final LayerNorm (ln_f, F7) is applied to every row on the fly before it is pooled.
+ *     clamp_denominator != 0 reproduces ST's clamp(min=1e-9) (Pooling.py:122); 0 reproduces the script (no clamp).
+ *     normalize != 0 additionally L2-normalises each output row (ST/models/Normalize.py:13-14).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define SGPT_POOL_MEAN 0
+#define SGPT_POOL_WEIGHTEDMEAN 1
+#define SGPT_POOL_LASTTOKEN 2
+int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma, const float* beta,
+              float eps, float* out, float* row_stats_ws /* fp32[2*T] scratch */, int B, int T, int d, int mode,
+              int clamp_denominator, int normalize, sgpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Whole-encoder handle (F1..F7 + P1 in one call).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define SGPT_ARCH_GPT_NEO 0
+#define SGPT_ARCH_GPTJ 1
+#define SGPT_ARCH_BLOOM 2
+
+typedef struct sgpt_model_config {
+  int32_t arch;
+  int32_t n_layer, d_model, n_head, d_ff, vocab, max_pos;
+  int32_t window;     /* GPT-Neo local-attention window (256) */
+  int32_t rotary_dim; /* GPT-J */
+  float ln_eps;
+  int32_t max_tokens; /* workspace capacity: largest T a single sgpt_encode call may carry */
+  int32_t max_batch;  /* largest B */
+} sgpt_model_config;
+
+/* Per-layer device pointers.  Linear weights are bf16 in nn.Linear layout [out,in]; biases and LayerNorm
+ * parameters are fp32.  Unused entries (arch-dependent) are NULL. */
+typedef struct sgpt_layer_weights {
+  const float *ln1_g, *ln1_b;
+  const void* w_qkv;   /* bf16[3d, d]: rows [q | k | v] */
+  const float* b_qkv;  /* fp32[3d] or NULL (GPT-Neo / GPT-J have no q,k,v bias) */
+  const void* w_o;     /* bf16[d, d] */
+  const float* b_o;    /* fp32[d] or NULL */
+  const float *ln2_g, *ln2_b;
+  const void* w_fc;    /* bf16[ff, d] */
+  const float* b_fc;   /* fp32[ff] */
+  const void* w_proj;  /* bf16[d, ff] */
+  const float* b_proj; /* fp32[d] */
+  int32_t local_attention; /* GPT-Neo: 1 for "local" layers */
+  int32_t _pad;
+} sgpt_layer_weights;
+
+typedef struct sgpt_model_weights {
+  const void* wte; /* bf16[vocab, d] */
+  const void* wpe; /* bf16[max_pos, d] or NULL */
+  const float *lnf_g, *lnf_b;
+  const sgpt_layer_weights* layers; /* HOST array of n_layer entries (copied at create) */
+} sgpt_model_weights;
+
+typedef struct sgpt_model* sgpt_model_t;
+
+/* Replaces AutoModel.from_pretrained(...).to(device) at BDR:123 / ST/models/Transformer.py:38 (weights are handed
+ * over already on the device; the handle borrows them and owns only its activation workspace). */
+int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_weights* w, sgpt_model_t* out);
+void sgpt_model_destroy(sgpt_model_t m);
+
+/* Replaces self.model(**batch_tokens, output_hidden_states=True) + pooling, BDR:205 + BDR:233-304
+ * (ST path: ST/models/Transformer.py:72 + ST/models/Pooling.py:85-168).
+ *     ids,pos int32[T]; cu_seqlens int32[B+1]; out fp32[B,d].
+ *     layer_idx: which entry of HF hidden_states to pool: -1 / n_layer = after ln_f (the reference default, BDR:44);
+ *                0..n_layer-1 = input of block i (no final LayerNorm). */
+int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const int32_t* cu_seqlens, int B, int T,
+                int max_seqlen, int layer_idx, int pool_mode, int clamp_denominator, int normalize, float* out,
+                sgpt_stream_t stream);
+
+/* Debug/parity tap: copy of the fp32 residual stream (hidden_states[layer] before ln_f) of the LAST sgpt_encode. */
+int sgpt_model_residual(sgpt_model_t m, const float** resid, int* T, int* d);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * S1–S3. Exact dense retrieval over one corpus shard.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* inv_norm[i] = 1 / max(||x_i||_2, 1e-12) for bf16 rows (F.normalize semantics, ST/util.py:41-42).  x bf16[n,D]. */
+int sgpt_row_inv_norms(const void* x, float* inv_norm, int64_t n, int D, sgpt_stream_t stream);
+
+/* fp32 -> bf16 row conversion (round-to-nearest-even) used to store embeddings in a shard. */
+int sgpt_f32_to_bf16(const float* x, void* y, int64_t count, sgpt_stream_t stream);
+
+/* S1. scores[q,j] = fixnan( <Q[q,:], C[j,:]> * q_scale[q] * c_scale[j] )      ST/util.py:24-63, XS:96-99
+ *     Q bf16[nq,D], C bf16[n,D], q_scale fp32[nq]|NULL, c_scale fp32[n]|NULL (NULL = 1: dot_score),
+ *     scores fp32[nq, lds]; NaN -> -1 as XS:99.  tcgen05 GEMM, corpus streamed once from HBM. */
+int sgpt_scores(const void* Q, const void* C, const float* q_scale, const float* c_scale, float* scores, int64_t lds,
+                int nq, int64_t n, int D, sgpt_stream_t stream);
+
+/* S2. Row-wise exact top-k of a score matrix (torch.topk(..., largest=True, sorted=False), XS:102-108), with the
+ *     winners returned in DESCENDING score order (ties: ascending id).  ids are offset by id_base (global doc ids of a
+ *     shard).  scores fp32[nq, lds] (n valid columns); out_scores fp32[nq,k]; out_ids int64[nq,k].
+ *     If n < k the tail is filled with (-inf, -1).  ws: scratch of sgpt_topk_workspace_bytes(nq,n,k) bytes. */
+int64_t sgpt_topk_workspace_bytes(int nq, int64_t n, int k);
+int sgpt_topk(const float* scores, int64_t lds, int nq, int64_t n, int k, int64_t id_base, float* out_scores,
+              int64_t* out_ids, void* ws, sgpt_stream_t stream);
+
+/* S3. Merge G candidate lists per query (cross-chunk heapq.nlargest merge XS:121-132; cross-shard merge after the
+ *     all-gather): in_scores fp32[G,nq,k], in_ids int64[G,nq,k] -> out fp32/int64[nq,k], descending; entries with
+ *     id < 0 are ignored. */
+int sgpt_topk_merge(const float* in_scores, const int64_t* in_ids, int G, int nq, int k, float* out_scores,
+                    int64_t* out_ids, void* ws, sgpt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGPT_B200_H_ */

@@ -1,0 +1,373 @@
+// F4: causal (optionally sliding-window) self-attention over a ragged batch, HF:gpt_neo/modeling_gpt_neo.py:105-130.
+//
+// tcgen05 kernel (impl 0).  One CTA = one (sequence, head, 128-query tile); 128 threads, thread r owns query row r
+// (TMEM lane r), so the softmax needs no cross-thread reduction.
+//   smem : Q[128,hd] K[128,hd] V[128,hd] (TMA, SWIZZLE_128B, 64-column sub-tiles) + P[128,128] bf16
+//   TMEM : S = Q K^T (128 fp32 columns) | O (hd fp32 columns)
+//   loop over 128-key tiles j (only tiles the causal/window mask can reach):
+//       S  = Q K_j^T                    tcgen05.mma, A = Q (K-major), B = K_j (K-major)
+//       online softmax in fp32 (exp2, running max m and sum l per row), P -> bf16 -> swizzled smem
+//       O  = alpha * O                  tcgen05.ld / tcgen05.st  (skipped on the first tile)
+//       O += P V_j                      tcgen05.mma, A = P (K-major), B = V_j (MN-major: V is [key, hd] row-major)
+//   epilogue: O / l -> bf16 -> out[token, head*hd : (head+1)*hd]
+// K_{j+1} is fetched by TMA while tile j's softmax runs; V_{j+1} while tile j+1's QK^T and softmax run.
+// hd=64 uses 81 KB smem and 256 TMEM columns so two CTAs share an SM and overlap each other's MMA/softmax phases.
+//
+// SIMT kernel (impl 1): one warp per (token, head), fp32 everywhere — test cross-check only.
+#include <math.h>
+
+#include "../../include/sgpt_b200.h"
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace sgpt {
+
+constexpr int kAttnTile = 128;
+constexpr int kSubBytes = kAttnTile * 128;  // one [128 rows x 64 bf16] sub-tile
+
+template <int HD>
+struct AttnCfg {
+  static constexpr int kSub = HD / 64;
+  static constexpr int kQBytes = kSub * kSubBytes;
+  static constexpr int kPBytes = 2 * kSubBytes;
+  static constexpr int kSmemBytes = 1024 + 3 * kQBytes + kPBytes + 64;
+  static constexpr int kTmemCols = (128 + HD <= 256) ? 256 : 512;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv,
+                                                           __nv_bfloat16* __restrict__ out,
+                                                           const int32_t* __restrict__ cu, int H, float sl2,
+                                                           int window) {
+  using Cfg = AttnCfg<HD>;
+  const int qt = blockIdx.x, b = blockIdx.y, h = blockIdx.z;
+  const int seq0 = __ldg(cu + b);
+  const int len = __ldg(cu + b + 1) - seq0;
+  const int qp0 = qt * kAttnTile;
+  if (qp0 >= len) return;  // whole CTA exits together, before any barrier/TMEM state exists
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kQBytes;
+  uint8_t* sV = sK + Cfg::kQBytes;
+  uint8_t* sP = sV + Cfg::kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int d = H * HD;
+
+  const int lo_pos = (window > 0) ? max(0, qp0 - window + 1) : 0;
+  const int j_lo = lo_pos / kAttnTile;
+  const int j_hi = qt;  // len > qp0, so the diagonal tile always exists
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tS = tmem_base;
+  const uint32_t tO = tmem_base + 128;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, Cfg::kQBytes);
+    for (int s = 0; s < Cfg::kSub; ++s) tma_load_2d(sQ + s * kSubBytes, &tma_qkv, bar_q, h * HD + 64 * s, seq0 + qp0);
+    mbar_expect_tx(bar_k, Cfg::kQBytes);
+    for (int s = 0; s < Cfg::kSub; ++s)
+      tma_load_2d(sK + s * kSubBytes, &tma_qkv, bar_k, d + h * HD + 64 * s, seq0 + j_lo * kAttnTile);
+    mbar_expect_tx(bar_v, Cfg::kQBytes);
+    for (int s = 0; s < Cfg::kSub; ++s)
+      tma_load_2d(sV + s * kSubBytes, &tma_qkv, bar_v, 2 * d + h * HD + 64 * s, seq0 + j_lo * kAttnTile);
+  }
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, true);
+
+  const int qpos = qp0 + tid;
+  const int vis_hi = min(qpos, len - 1);
+  const int vis_lo = (window > 0) ? (qpos - window + 1) : 0;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int j = j_lo; j <= j_hi; ++j) {
+    const uint32_t ph = static_cast<uint32_t>(j - j_lo) & 1u;
+    // ---- S = Q K_j^T ----
+    if (tid == 0) {
+      if (j == j_lo) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, ph);
+      tc_fence_after();
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * kSubBytes + (kk & 3) * 32;
+        umma_bf16_ss(tS, make_smem_desc_sw128(aq + off, 16, 1024), make_smem_desc_sw128(ak + off, 16, 1024), idesc_s,
+                     kk != 0);
+      }
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    // K buffer is free again: prefetch K_{j+1} under the softmax
+    if (tid == 0 && j < j_hi) {
+      mbar_expect_tx(bar_k, Cfg::kQBytes);
+      for (int s = 0; s < Cfg::kSub; ++s)
+        tma_load_2d(sK + s * kSubBytes, &tma_qkv, bar_k, d + h * HD + 64 * s, seq0 + (j + 1) * kAttnTile);
+    }
+    __syncwarp();
+
+    // ---- online softmax over this row's 128 scores ----
+    const int kv0 = j * kAttnTile;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tS + lane_off + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int kp = kv0 + c * 32 + i;
+        const float s = __uint_as_float(v[i]);
+        if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, s);
+      }
+    }
+    const float m_new = fmaxf(m_run, mx * sl2);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = exp2f(m_run - m_use);
+    float lsum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tS + lane_off + c * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int kp = kv0 + c * 32 + 2 * i;
+        float p0 = exp2f(__uint_as_float(v[2 * i]) * sl2 - m_use);
+        float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * sl2 - m_use);
+        if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
+        if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
+        lsum += p0 + p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+      // P[row, kv 32c .. 32c+31] -> sub-tile (c >> 1), 16-B chunks 4*(c&1) .. +3, XOR-swizzled with (row & 7)
+      uint8_t* prow = sP + (c >> 1) * kSubBytes + tid * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int chunk = ((c & 1) * 4 + q4) ^ (tid & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) =
+            make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      }
+    }
+    l_run = l_run * alpha + lsum;
+    m_run = m_new;
+
+    // ---- O = alpha * O (needs the previous P V MMA to have landed) ----
+    if (j > j_lo) {
+      mbar_wait(bar_o, ph ^ 1u);
+      tc_fence_after();
+      __syncwarp();
+#pragma unroll 1
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st_32x32(tO + lane_off + c * 32, v);
+      }
+      tmem_st_wait();
+      // V buffer is free (previous P V done): fetch V_j now (it could not be prefetched earlier)
+    }
+    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    // ---- O += P V_j ----
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+#pragma unroll
+      for (int kk = 0; kk < kAttnTile / 16; ++kk) {
+        const uint64_t da = make_smem_desc_sw128(ap + (kk >> 2) * kSubBytes + (kk & 3) * 32, 16, 1024);
+        const uint64_t db = make_smem_desc_sw128(av + kk * 2048, kSubBytes, 1024);
+        umma_bf16_ss(tO, da, db, idesc_o, (j > j_lo) || (kk != 0));
+      }
+      umma_commit(bar_o);
+      if (j < j_hi) {
+        // V buffer is reusable once this P V completes; wait for it, then prefetch V_{j+1} (lands during the next
+        // tile's QK^T + softmax)
+        mbar_wait(bar_o, ph);
+        mbar_expect_tx(bar_v, Cfg::kQBytes);
+        for (int s = 0; s < Cfg::kSub; ++s)
+          tma_load_2d(sV + s * kSubBytes, &tma_qkv, bar_v, 2 * d + h * HD + 64 * s, seq0 + (j + 1) * kAttnTile);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue ----
+  {
+    const uint32_t ph = static_cast<uint32_t>(j_hi - j_lo) & 1u;
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    __syncwarp();
+    const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+    const bool row_ok = qpos < len;
+    __nv_bfloat16* dst = out + static_cast<size_t>(seq0 + qpos) * d + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tO + lane_off + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = pack_bf16(__uint_as_float(v[8 * q4 + 2 * i]) * inv_l, __uint_as_float(v[8 * q4 + 2 * i + 1]) * inv_l);
+          d4[q4] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SIMT cross-check: one warp per (token, head); lanes split the head dimension; fp32 online softmax.
+// ---------------------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256) attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                             __nv_bfloat16* __restrict__ out,
+                                                             const int32_t* __restrict__ cu, int B, int T, int H,
+                                                             float scale, int window) {
+  constexpr int E = HD / 32;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int h = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  // sequence containing token t: largest b with cu[b] <= t
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cu + mid) <= t) lo = mid; else hi = mid;
+  }
+  const int seq0 = __ldg(cu + lo);
+  const int d = H * HD;
+  const size_t ld = 3 * static_cast<size_t>(d);
+  float q[E], o[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    q[e] = __bfloat162float(qkv[t * ld + h * HD + lane * E + e]);
+    o[e] = 0.f;
+  }
+  int k_lo = seq0;
+  if (window > 0) k_lo = max(seq0, t - window + 1);
+  float m = -INFINITY, l = 0.f;
+  for (int kt = k_lo; kt <= t; ++kt) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s += q[e] * __bfloat162float(qkv[kt * ld + d + h * HD + lane * E + e]);
+    s = warp_sum(s) * scale;
+    const float mn = fmaxf(m, s);
+    const float a = expf(m - mn), p = expf(s - mn);
+    l = l * a + p;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      o[e] = o[e] * a + p * __bfloat162float(qkv[kt * ld + 2 * d + h * HD + lane * E + e]);
+    m = mn;
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    out[static_cast<size_t>(t) * d + h * HD + lane * E + e] = __float2bfloat16_rn(o[e] / l);
+}
+
+template <int HD>
+static int launch_attention_tc(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale,
+                               int window, int max_seqlen, cudaStream_t stream) {
+  using Cfg = AttnCfg<HD>;
+  CUtensorMap map;
+  int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
+  if (rc != SGPT_OK) return rc;
+  auto kern = attention_tc_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((max_seqlen + kAttnTile - 1) / kAttnTile, B, H);
+  const float sl2 = scale * 1.4426950408889634f;
+  kern<<<grid, 128, Cfg::kSmemBytes, stream>>>(map, static_cast<__nv_bfloat16*>(out), cu, H, sl2, window);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
+template <int HD>
+static int launch_attention_simt(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale,
+                                 int window, cudaStream_t stream) {
+  dim3 grid((T + 7) / 8, H);
+  attention_simt_kernel<HD><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                      static_cast<__nv_bfloat16*>(out), cu, B, T, H, scale, window);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
+}  // namespace sgpt
+
+using namespace sgpt;
+
+extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seqlens, int B, int T, int H, int hd,
+                              float scale, int window, int max_seqlen, int impl, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(B >= 0 && T >= 0 && H > 0, "sgpt_attention: bad sizes B=%d T=%d H=%d", B, T, H);
+  SGPT_REQUIRE(hd == 64 || hd == 128 || hd == 256, "sgpt_attention: head_dim %d not in {64,128,256}", hd);
+  SGPT_REQUIRE(scale > 0.f, "sgpt_attention: scale must be positive");
+  SGPT_REQUIRE(window >= 0, "sgpt_attention: window must be >= 0");
+  SGPT_REQUIRE(max_seqlen > 0 || T == 0, "sgpt_attention: max_seqlen must be positive");
+  if (B == 0 || T == 0) return SGPT_OK;
+  if (impl == 0) {
+    SGPT_REQUIRE(H <= 65535 && B <= 65535, "sgpt_attention: grid limits exceeded (B=%d H=%d)", B, H);
+    switch (hd) {
+      case 64: return launch_attention_tc<64>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, stream);
+      case 128: return launch_attention_tc<128>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, stream);
+      default: return launch_attention_tc<256>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, stream);
+    }
+  } else if (impl == 1) {
+    switch (hd) {
+      case 64: return launch_attention_simt<64>(qkv, out, cu_seqlens, B, T, H, scale, window, stream);
+      case 128: return launch_attention_simt<128>(qkv, out, cu_seqlens, B, T, H, scale, window, stream);
+      default: return launch_attention_simt<256>(qkv, out, cu_seqlens, B, T, H, scale, window, stream);
+    }
+  }
+  set_error("sgpt_attention: unknown impl %d", impl);
+  return SGPT_ERR_INVALID;
+}

@@ -1,0 +1,365 @@
+// HBM-bound row kernels of the encoder: token(+position) embedding gather (F1), LayerNorm (F2/F7), and the
+// position-weighted masked pooling with ln_f fused in (P1/P2).  All reductions accumulate in fp32; all global
+// accesses are 16-byte vectorised and coalesced along d.
+#include <math.h>
+
+#include "../../include/sgpt_b200.h"
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace sgpt {
+
+// ---------------------------------------------------------------------------------------------------------------
+// F1: resid[t, :] = wte[ids[t], :] (+ wpe[pos[t], :])        one warp-wide 16-B vector per thread-iteration
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos,
+                                                    const uint4* __restrict__ wte, const uint4* __restrict__ wpe,
+                                                    float4* __restrict__ resid, int T, int d8, int vocab,
+                                                    int max_pos) {
+  // d8 = d / 8: number of 16-B bf16 vectors per row.  Grid-stride over (token, vector).
+  const long long total = static_cast<long long>(T) * d8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / d8);
+    const int v = static_cast<int>(i - static_cast<long long>(t) * d8);
+    int id = __ldg(ids + t);
+    id = min(max(id, 0), vocab - 1);
+    uint4 e = __ldg(wte + static_cast<size_t>(id) * d8 + v);
+    float f[8] = {bf16_lo(e.x), bf16_hi(e.x), bf16_lo(e.y), bf16_hi(e.y),
+                  bf16_lo(e.z), bf16_hi(e.z), bf16_lo(e.w), bf16_hi(e.w)};
+    if (wpe != nullptr) {
+      int p = __ldg(pos + t);
+      p = min(max(p, 0), max_pos - 1);
+      uint4 q = __ldg(wpe + static_cast<size_t>(p) * d8 + v);
+      f[0] += bf16_lo(q.x); f[1] += bf16_hi(q.x); f[2] += bf16_lo(q.y); f[3] += bf16_hi(q.y);
+      f[4] += bf16_lo(q.z); f[5] += bf16_hi(q.z); f[6] += bf16_lo(q.w); f[7] += bf16_hi(q.w);
+    }
+    float4* dst = resid + (static_cast<size_t>(t) * d8 + v) * 2;
+    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// F2/F7: LayerNorm, fp32 in, bf16 out.  TPR threads cooperate on one row; each holds V float4 (row in registers,
+// exact two-pass mean/variance like torch's CPU kernel).
+// ---------------------------------------------------------------------------------------------------------------
+template <int TPR>
+__device__ __forceinline__ float group_sum(float v, float* scratch /* [rows_per_cta][TPR/32] */, int row_in_cta,
+                                           int lane_in_row) {
+  v = warp_sum(v);
+  if (TPR == 32) return v;
+  constexpr int W = TPR / 32;
+  __syncthreads();  // protect scratch reuse between consecutive reductions
+  if ((lane_in_row & 31) == 0) scratch[row_in_cta * W + (lane_in_row >> 5)] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < W; ++i) s += scratch[row_in_cta * W + i];
+  return s;
+}
+
+template <int TPR, int V>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ g,
+                                                        const float4* __restrict__ b, uint2* __restrict__ y, int T,
+                                                        int d4, float eps) {
+  constexpr int ROWS = 256 / TPR;
+  __shared__ float scratch[ROWS * (TPR / 32) + 1];
+  const int row_in_cta = threadIdx.x / TPR;
+  const int l = threadIdx.x % TPR;
+  const int row = blockIdx.x * ROWS + row_in_cta;
+  const bool active = row < T;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = l + i * TPR;
+    v[i] = (active && c < d4) ? x[static_cast<size_t>(row) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float inv_d = 1.0f / static_cast<float>(d4 * 4);
+  const float mean = group_sum<TPR>(s, scratch, row_in_cta, l) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = l + i * TPR;
+    if (c < d4) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+      q += (a * a + bb * bb) + (cc * cc + dd * dd);
+    }
+  }
+  const float var = group_sum<TPR>(q, scratch, row_in_cta, l) * inv_d;
+  const float rstd = rsqrtf(var + eps);
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = l + i * TPR;
+    if (c < d4) {
+      const float4 gg = __ldg(g + c), bb = __ldg(b + c);
+      const float o0 = (v[i].x - mean) * rstd * gg.x + bb.x;
+      const float o1 = (v[i].y - mean) * rstd * gg.y + bb.y;
+      const float o2 = (v[i].z - mean) * rstd * gg.z + bb.z;
+      const float o3 = (v[i].w - mean) * rstd * gg.w + bb.w;
+      y[static_cast<size_t>(row) * d4 + c] = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+    }
+  }
+}
+
+// Row statistics only (mean, rstd) -> stats[2*t], used by the pooling kernel to apply ln_f on the fly.
+template <int TPR, int V>
+__global__ void __launch_bounds__(256) row_stats_kernel(const float4* __restrict__ x, float2* __restrict__ stats,
+                                                        int T, int d4, float eps) {
+  constexpr int ROWS = 256 / TPR;
+  __shared__ float scratch[ROWS * (TPR / 32) + 1];
+  const int row_in_cta = threadIdx.x / TPR;
+  const int l = threadIdx.x % TPR;
+  const int row = blockIdx.x * ROWS + row_in_cta;
+  const bool active = row < T;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = l + i * TPR;
+    v[i] = (active && c < d4) ? x[static_cast<size_t>(row) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float inv_d = 1.0f / static_cast<float>(d4 * 4);
+  const float mean = group_sum<TPR>(s, scratch, row_in_cta, l) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = l + i * TPR;
+    if (c < d4) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+      q += (a * a + bb * bb) + (cc * cc + dd * dd);
+    }
+  }
+  const float var = group_sum<TPR>(q, scratch, row_in_cta, l) * inv_d;
+  if (active && l == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
+}
+
+// Choose (threads-per-row, float4-per-thread) so the row lives in registers: d <= 1024 -> one warp per row.
+#define SGPT_ROW_DISPATCH(KERNEL, d4, T, stream, ...)                                               \
+  do {                                                                                              \
+    if (d4 <= 32 * 8) {                                                                             \
+      const int rows = 8;                                                                           \
+      KERNEL<32, 8><<<(T + rows - 1) / rows, 256, 0, stream>>>(__VA_ARGS__);                        \
+    } else if (d4 <= 128 * 8) {                                                                     \
+      const int rows = 2;                                                                           \
+      KERNEL<128, 8><<<(T + rows - 1) / rows, 256, 0, stream>>>(__VA_ARGS__);                       \
+    } else if (d4 <= 256 * 16) {                                                                    \
+      KERNEL<256, 16><<<T, 256, 0, stream>>>(__VA_ARGS__);                                          \
+    } else {                                                                                        \
+      set_error("hidden size %d too large for the row kernels", d4 * 4);                            \
+      return SGPT_ERR_UNSUPPORTED;                                                                  \
+    }                                                                                               \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// P1/P2: out[b, :] = sum_t w_t * LN(x_t) / sum_t w_t   over the tokens of sequence b.
+//   grid = (B, d / 128); 128 threads = 4 warps; each warp strides over the tokens of the sequence, each lane owns one
+//   float4 column group (coalesced 512-B row segments); fp32 accumulators; cross-warp combine through smem.
+//   With ln_f:  sum_t w_t ((x_t - mu_t) r_t g + b) = g * sum_t w_t r_t (x_t - mu_t) + b * W.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x, const int32_t* __restrict__ pos,
+                                                   const int32_t* __restrict__ cu, const float2* __restrict__ stats,
+                                                   const float4* __restrict__ g, const float4* __restrict__ bta,
+                                                   float4* __restrict__ out, float* __restrict__ sumsq, int d4,
+                                                   int mode, int clamp_den) {
+  __shared__ float4 part[4][32];
+  __shared__ float wpart[4];
+  const int b = blockIdx.x;
+  const int col = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int warp = threadIdx.x >> 5;
+  const int t0 = __ldg(cu + b), t1 = __ldg(cu + b + 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float wsum = 0.f;
+  const bool col_ok = col < d4;
+  for (int t = t0 + warp; t < t1; t += 4) {
+    float w;
+    if (mode == SGPT_POOL_WEIGHTEDMEAN) w = static_cast<float>(__ldg(pos + t) + 1);
+    else if (mode == SGPT_POOL_LASTTOKEN) w = (t == t1 - 1) ? 1.f : 0.f;
+    else w = 1.f;
+    wsum += w;
+    if (w != 0.f && col_ok) {
+      float4 v = x[static_cast<size_t>(t) * d4 + col];
+      if (stats != nullptr) {
+        const float2 s = __ldg(stats + t);
+        const float wr = w * s.y;
+        acc.x += wr * (v.x - s.x); acc.y += wr * (v.y - s.x); acc.z += wr * (v.z - s.x); acc.w += wr * (v.w - s.x);
+      } else {
+        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+      }
+    }
+  }
+  part[warp][threadIdx.x & 31] = acc;
+  if ((threadIdx.x & 31) == 0) wpart[warp] = wsum;
+  __syncthreads();
+  if (warp == 0) {
+    float4 a = part[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+      const float4 p = part[i][threadIdx.x];
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    float W = (wpart[0] + wpart[1]) + (wpart[2] + wpart[3]);
+    float den = W;
+    if (clamp_den) den = fmaxf(den, 1e-9f);
+    float4 o;
+    if (stats != nullptr && col_ok) {
+      const float4 gg = __ldg(g + col), bb = __ldg(bta + col);
+      o.x = (gg.x * a.x + bb.x * W) / den; o.y = (gg.y * a.y + bb.y * W) / den;
+      o.z = (gg.z * a.z + bb.z * W) / den; o.w = (gg.w * a.w + bb.w * W) / den;
+    } else {
+      o.x = a.x / den; o.y = a.y / den; o.z = a.z / den; o.w = a.w / den;
+    }
+    if (col_ok) out[static_cast<size_t>(b) * d4 + col] = o;
+    if (sumsq != nullptr) {
+      float ss = col_ok ? (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w) : 0.f;
+      ss = warp_sum(ss);
+      if (threadIdx.x == 0) atomicAdd(sumsq + b, ss);
+    }
+  }
+}
+
+// P2: x[b,:] /= max(sqrt(sumsq[b]), 1e-12)      (F.normalize(p=2, dim=1))
+__global__ void __launch_bounds__(256) l2_scale_rows_kernel(float4* __restrict__ x, const float* __restrict__ sumsq,
+                                                            int B, int d4) {
+  const long long total = static_cast<long long>(B) * d4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / d4);
+    const float inv = 1.0f / fmaxf(sqrtf(__ldg(sumsq + b)), 1e-12f);
+    float4 v = x[i];
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    x[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shard maintenance: fp32 -> bf16 rows, and 1 / max(||row||, 1e-12) of the *stored* bf16 rows.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y,
+                                                          long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// one warp per row; D % 8 == 0
+__global__ void __launch_bounds__(256) row_inv_norm_kernel(const uint4* __restrict__ x, float* __restrict__ inv,
+                                                           long long n, int d8) {
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < d8; c += 32) {
+    const uint4 e = __ldg(x + row * d8 + c);
+    const float f0 = bf16_lo(e.x), f1 = bf16_hi(e.x), f2 = bf16_lo(e.y), f3 = bf16_hi(e.y);
+    const float f4 = bf16_lo(e.z), f5 = bf16_hi(e.z), f6 = bf16_lo(e.w), f7 = bf16_hi(e.w);
+    s += ((f0 * f0 + f1 * f1) + (f2 * f2 + f3 * f3)) + ((f4 * f4 + f5 * f5) + (f6 * f6 + f7 * f7));
+  }
+  s = warp_sum(s);
+  if (lane == 0) inv[row] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+}
+
+static inline int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace sgpt
+
+using namespace sgpt;
+
+extern "C" int sgpt_embed_tokens(const int32_t* ids, const int32_t* pos, const void* wte, const void* wpe,
+                                 float* resid, int T, int d, int vocab, int max_pos, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(T >= 0 && d > 0 && d % 8 == 0, "sgpt_embed_tokens: d=%d must be a positive multiple of 8", d);
+  SGPT_REQUIRE(wpe == nullptr || pos != nullptr, "sgpt_embed_tokens: pos required when wpe is given");
+  if (T == 0) return SGPT_OK;
+  const int d8 = d / 8;
+  embed_kernel<<<grid_for(static_cast<long long>(T) * d8, 256), 256, 0, stream>>>(
+      ids, pos, static_cast<const uint4*>(wte), static_cast<const uint4*>(wpe), reinterpret_cast<float4*>(resid), T,
+      d8, vocab, max_pos);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_layernorm(const float* x, const float* gamma, const float* beta, void* y, int T, int d,
+                              float eps, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(T >= 0 && d > 0 && d % 4 == 0, "sgpt_layernorm: d=%d must be a positive multiple of 4", d);
+  if (T == 0) return SGPT_OK;
+  const int d4 = d / 4;
+  SGPT_ROW_DISPATCH(layernorm_kernel, d4, T, stream, reinterpret_cast<const float4*>(x),
+                    reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
+                    static_cast<uint2*>(y), T, d4, eps);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                         const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d, int mode,
+                         int clamp_denominator, int normalize, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(d > 0 && d % 4 == 0, "sgpt_pool: d=%d must be a positive multiple of 4", d);
+  SGPT_REQUIRE(mode >= 0 && mode <= 2, "sgpt_pool: unknown mode %d", mode);
+  SGPT_REQUIRE(mode != SGPT_POOL_WEIGHTEDMEAN || pos != nullptr, "sgpt_pool: weightedmean needs pos");
+  SGPT_REQUIRE((gamma == nullptr) == (beta == nullptr), "sgpt_pool: gamma and beta must be given together");
+  SGPT_REQUIRE(gamma == nullptr || row_stats_ws != nullptr, "sgpt_pool: ln_f fusion needs row_stats_ws");
+  if (B == 0) return SGPT_OK;
+  const int d4 = d / 4;
+  const float2* stats = nullptr;
+  if (gamma != nullptr && T > 0) {
+    SGPT_ROW_DISPATCH(row_stats_kernel, d4, T, stream, reinterpret_cast<const float4*>(x),
+                      reinterpret_cast<float2*>(row_stats_ws), T, d4, eps);
+    SGPT_CHECK_CUDA(cudaGetLastError());
+    stats = reinterpret_cast<const float2*>(row_stats_ws);
+  }
+  float* sumsq = nullptr;
+  if (normalize) {
+    // the tail of the stats scratch is not available (size 2T); keep a tiny dedicated buffer per call instead
+    SGPT_REQUIRE(row_stats_ws != nullptr, "sgpt_pool: normalize needs row_stats_ws (>= 2*T + B floats)");
+    sumsq = row_stats_ws + 2 * static_cast<size_t>(T);
+    SGPT_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * B, stream));
+  }
+  dim3 grid(B, (d4 + 31) / 32);
+  pool_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float4*>(x), pos, cu_seqlens, stats,
+                                        reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
+                                        reinterpret_cast<float4*>(out), sumsq, d4, mode, clamp_denominator);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  if (normalize) {
+    l2_scale_rows_kernel<<<grid_for(static_cast<long long>(B) * d4, 256), 256, 0, stream>>>(
+        reinterpret_cast<float4*>(out), sumsq, B, d4);
+    SGPT_CHECK_CUDA(cudaGetLastError());
+  }
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_row_inv_norms(const void* x, float* inv_norm, int64_t n, int D, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(D > 0 && D % 8 == 0, "sgpt_row_inv_norms: D=%d must be a positive multiple of 8", D);
+  if (n == 0) return SGPT_OK;
+  const long long blocks = (n + 7) / 8;
+  SGPT_REQUIRE(blocks < (1ll << 31), "sgpt_row_inv_norms: too many rows");
+  row_inv_norm_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint4*>(x), inv_norm, n,
+                                                                          D / 8);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_f32_to_bf16(const float* x, void* y, int64_t count, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(count >= 0 && count % 4 == 0, "sgpt_f32_to_bf16: count must be a multiple of 4");
+  if (count == 0) return SGPT_OK;
+  f32_to_bf16_kernel<<<grid_for(count / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                                    static_cast<uint2*>(y), count / 4);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}

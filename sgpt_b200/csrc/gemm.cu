@@ -1,0 +1,101 @@
+// Host launchers for the tcgen05 GEMM (gemm.cuh): nn.Linear with fused epilogues (F3/F5/F6) and the
+// query x corpus similarity (S1).
+#include "gemm.cuh"
+
+#include "../../include/sgpt_b200.h"
+#include "host_utils.h"
+
+namespace sgpt {
+
+template <int BN, class Epi>
+static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K,
+                       const typename Epi::Params& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  int rc = make_tma_2d_bf16(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
+                            kGemmBM, kGemmBK);
+  if (rc != SGPT_OK) return rc;
+  rc = make_tma_2d_bf16(&tb, b, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), BN,
+                        kGemmBK);
+  if (rc != SGPT_OK) return rc;
+  auto kern = gemm_bf16_tn_kernel<BN, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  int grid = sm_count();
+  if (tiles < grid) grid = static_cast<int>(tiles);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
+// Tile-width heuristic: BN=256 halves the smem bytes the tensor core must read per FLOP, but with few tiles the
+// last wave is emptier; take the width with the better wave efficiency, preferring 256 on ties.
+static int pick_bn(int M, int N) {
+  if (N <= 128) return 128;
+  const int sms = sm_count();
+  auto eff = [&](int bn) {
+    const long long tiles = static_cast<long long>((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double useful = static_cast<double>(M) * N;
+    return useful / (static_cast<double>(waves) * sms * kGemmBM * bn);
+  };
+  return (eff(256) * 1.08 >= eff(128)) ? 256 : 128;
+}
+
+}  // namespace sgpt
+
+using namespace sgpt;
+
+extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out,
+                           int64_t ldo, const float* resid, int M, int N, int K, int epilogue,
+                           sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(M >= 0 && N > 0 && K > 0, "sgpt_linear: bad sizes M=%d N=%d K=%d", M, N, K);
+  SGPT_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "sgpt_linear: K, ldx, ldw must be multiples of 8");
+  SGPT_REQUIRE(ldx >= K && ldw >= K && ldo >= N, "sgpt_linear: row pitch smaller than the row");
+  if (M == 0) return SGPT_OK;
+  const int bn = pick_bn(M, N);
+  switch (epilogue) {
+    case SGPT_EPI_BF16: {
+      SGPT_REQUIRE(ldo % 8 == 0, "sgpt_linear: ldo must be a multiple of 8 for bf16 output");
+      EpiBiasActBF16<false>::Params p{static_cast<__nv_bfloat16*>(out), bias, static_cast<int>(ldo)};
+      return bn == 256 ? launch_gemm<256, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream)
+                       : launch_gemm<128, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream);
+    }
+    case SGPT_EPI_GELU_BF16: {
+      SGPT_REQUIRE(ldo % 8 == 0, "sgpt_linear: ldo must be a multiple of 8 for bf16 output");
+      EpiBiasActBF16<true>::Params p{static_cast<__nv_bfloat16*>(out), bias, static_cast<int>(ldo)};
+      return bn == 256 ? launch_gemm<256, EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, stream)
+                       : launch_gemm<128, EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, stream);
+    }
+    case SGPT_EPI_RESID_F32: {
+      SGPT_REQUIRE(resid != nullptr, "sgpt_linear: SGPT_EPI_RESID_F32 needs resid");
+      SGPT_REQUIRE(ldo % 4 == 0, "sgpt_linear: ldo must be a multiple of 4 for fp32 output");
+      EpiResidualF32::Params p{static_cast<float*>(out), resid, bias, static_cast<int>(ldo)};
+      return bn == 256 ? launch_gemm<256, EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, stream)
+                       : launch_gemm<128, EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, stream);
+    }
+    default:
+      set_error("sgpt_linear: unknown epilogue %d", epilogue);
+      return SGPT_ERR_INVALID;
+  }
+}
+
+extern "C" int sgpt_scores(const void* Q, const void* C, const float* q_scale, const float* c_scale, float* scores,
+                           int64_t lds, int nq, int64_t n, int D, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(nq >= 0 && n >= 0 && D > 0 && D % 8 == 0, "sgpt_scores: bad sizes nq=%d n=%lld D=%d", nq,
+               (long long)n, D);
+  SGPT_REQUIRE(n < (1ll << 31), "sgpt_scores: shard too large for one launch (n=%lld)", (long long)n);
+  SGPT_REQUIRE(lds >= n, "sgpt_scores: lds < n");
+  if (nq == 0 || n == 0) return SGPT_OK;
+  EpiScoresF32::Params p{scores, q_scale, c_scale, static_cast<long long>(lds)};
+  // lanes = queries (A operand), columns = corpus rows (B operand, streamed once from HBM)
+  return launch_gemm<256, EpiScoresF32>(Q, D, C, D, nq, static_cast<int>(n), D, p, stream);
+}

@@ -1,0 +1,38 @@
+// Host-side helpers: error plumbing for the C ABI and TMA tensor-map construction (driver entry point resolved
+// at run time through the CUDA runtime, so the library never links libcuda directly).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgpt {
+
+// thread-local last-error message, returned by sgpt_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SGPT_CHECK_CUDA(expr)                                                               \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::sgpt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SGPT_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+#define SGPT_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::sgpt::set_error(__VA_ARGS__);  \
+      return SGPT_ERR_INVALID;         \
+    }                                  \
+  } while (0)
+
+// 2-D bf16 row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols] with the
+// 128-byte swizzle (box_cols must be 64 bf16 = 128 B).  Returns 0 on success.
+int make_tma_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows, uint32_t box_cols);
+
+int sm_count();
+
+}  // namespace sgpt

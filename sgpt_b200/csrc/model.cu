@@ -1,0 +1,141 @@
+// Whole-encoder handle: token ids -> GPT forward (F1..F7) -> pooled embeddings (P1/P2) in one C call.
+// Replaces `self.model(**batch_tokens, output_hidden_states=True)` + the pooling block of the reference
+// (biencoder/beir/beir_dense_retriever.py:205, :233-304).  The handle borrows the caller's weight buffers and owns
+// only its activation workspace, laid out for a ragged batch of at most cfg.max_tokens rows:
+//     resid fp32[T,d] | xn bf16[T,d] | qkv bf16[T,3d] | attn bf16[T,d] | ffn bf16[T,ff] | stats fp32[2T+B]
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/sgpt_b200.h"
+#include "host_utils.h"
+
+struct sgpt_model {
+  sgpt_model_config cfg;
+  sgpt_model_weights w;
+  std::vector<sgpt_layer_weights> layers;
+  int device = 0;
+  float* resid = nullptr;
+  void* xn = nullptr;
+  void* qkv = nullptr;
+  void* attn = nullptr;
+  void* ffn = nullptr;
+  float* stats = nullptr;
+  int last_T = 0;
+};
+
+using namespace sgpt;
+
+extern "C" int sgpt_abi_version(void) { return SGPT_ABI_VERSION; }
+
+extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_weights* w, sgpt_model_t* out) {
+  SGPT_REQUIRE(cfg != nullptr && w != nullptr && out != nullptr, "sgpt_model_create: null argument");
+  *out = nullptr;
+  SGPT_REQUIRE(cfg->arch == SGPT_ARCH_GPT_NEO || cfg->arch == SGPT_ARCH_GPTJ || cfg->arch == SGPT_ARCH_BLOOM,
+               "sgpt_model_create: unknown arch %d", cfg->arch);
+  if (cfg->arch != SGPT_ARCH_GPT_NEO) {
+    set_error("sgpt_model_create: arch %d (GPT-J / BLOOM) is not built yet", cfg->arch);
+    return SGPT_ERR_UNSUPPORTED;
+  }
+  SGPT_REQUIRE(cfg->n_layer > 0 && cfg->d_model > 0 && cfg->n_head > 0 && cfg->d_ff > 0, "sgpt_model_create: bad dims");
+  SGPT_REQUIRE(cfg->d_model % cfg->n_head == 0, "sgpt_model_create: d_model %% n_head != 0");
+  const int hd = cfg->d_model / cfg->n_head;
+  SGPT_REQUIRE(hd == 64 || hd == 128 || hd == 256, "sgpt_model_create: head_dim %d not in {64,128,256}", hd);
+  SGPT_REQUIRE(cfg->d_model % 64 == 0 && cfg->d_ff % 64 == 0, "sgpt_model_create: d_model and d_ff must be multiples of 64");
+  SGPT_REQUIRE(cfg->max_tokens > 0 && cfg->max_batch > 0, "sgpt_model_create: max_tokens/max_batch must be positive");
+  SGPT_REQUIRE(w->wte != nullptr && w->lnf_g != nullptr && w->lnf_b != nullptr && w->layers != nullptr,
+               "sgpt_model_create: missing weights");
+  SGPT_REQUIRE(w->wpe != nullptr, "sgpt_model_create: GPT-Neo needs wpe");
+
+  sgpt_model* m = new sgpt_model();
+  m->cfg = *cfg;
+  m->w = *w;
+  m->layers.assign(w->layers, w->layers + cfg->n_layer);
+  m->w.layers = m->layers.data();
+  for (int l = 0; l < cfg->n_layer; ++l) {
+    const sgpt_layer_weights& lw = m->layers[l];
+    if (!lw.ln1_g || !lw.ln1_b || !lw.w_qkv || !lw.w_o || !lw.ln2_g || !lw.ln2_b || !lw.w_fc || !lw.w_proj) {
+      delete m;
+      set_error("sgpt_model_create: layer %d has missing weights", l);
+      return SGPT_ERR_INVALID;
+    }
+  }
+  cudaError_t e = cudaGetDevice(&m->device);
+  const size_t T = static_cast<size_t>(cfg->max_tokens), d = static_cast<size_t>(cfg->d_model);
+  if (e == cudaSuccess) e = cudaMalloc(&m->resid, T * d * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&m->xn, T * d * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&m->qkv, T * d * 3 * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&m->attn, T * d * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&m->ffn, T * static_cast<size_t>(cfg->d_ff) * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&m->stats, (2 * T + static_cast<size_t>(cfg->max_batch)) * 4);
+  if (e != cudaSuccess) {
+    set_error("sgpt_model_create: workspace allocation failed: %s", cudaGetErrorString(e));
+    sgpt_model_destroy(m);
+    return SGPT_ERR_CUDA;
+  }
+  *out = m;
+  return SGPT_OK;
+}
+
+extern "C" void sgpt_model_destroy(sgpt_model_t m) {
+  if (!m) return;
+  cudaFree(m->resid);
+  cudaFree(m->xn);
+  cudaFree(m->qkv);
+  cudaFree(m->attn);
+  cudaFree(m->ffn);
+  cudaFree(m->stats);
+  delete m;
+}
+
+#define SGPT_TRY(call)            \
+  do {                            \
+    int _rc = (call);             \
+    if (_rc != SGPT_OK) return _rc; \
+  } while (0)
+
+extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const int32_t* cu_seqlens, int B,
+                           int T, int max_seqlen, int layer_idx, int pool_mode, int clamp_denominator, int normalize,
+                           float* out, sgpt_stream_t stream) {
+  SGPT_REQUIRE(m != nullptr, "sgpt_encode: null model");
+  const sgpt_model_config& c = m->cfg;
+  SGPT_REQUIRE(B >= 0 && T >= 0, "sgpt_encode: negative sizes");
+  SGPT_REQUIRE(T <= c.max_tokens && B <= c.max_batch, "sgpt_encode: batch (B=%d, T=%d) exceeds workspace (B<=%d, T<=%d)",
+               B, T, c.max_batch, c.max_tokens);
+  SGPT_REQUIRE(max_seqlen <= c.max_pos, "sgpt_encode: max_seqlen %d exceeds max_position_embeddings %d", max_seqlen,
+               c.max_pos);
+  if (layer_idx < 0) layer_idx += c.n_layer + 1;
+  SGPT_REQUIRE(layer_idx >= 0 && layer_idx <= c.n_layer, "sgpt_encode: layer index out of range for %d hidden states",
+               c.n_layer + 1);
+  if (B == 0) return SGPT_OK;
+  const int d = c.d_model, H = c.n_head, hd = d / H;
+  m->last_T = T;
+
+  SGPT_TRY(sgpt_embed_tokens(ids, pos, m->w.wte, m->w.wpe, m->resid, T, d, c.vocab, c.max_pos, stream));
+  const int n_run = layer_idx;  // hidden_states[i] is the input of block i; hidden_states[L] is ln_f(output of block L-1)
+  for (int l = 0; l < n_run && l < c.n_layer; ++l) {
+    const sgpt_layer_weights& lw = m->layers[l];
+    SGPT_TRY(sgpt_layernorm(m->resid, lw.ln1_g, lw.ln1_b, m->xn, T, d, c.ln_eps, stream));
+    SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
+    const int window = (lw.local_attention && c.window > 0 && max_seqlen > c.window) ? c.window : 0;
+    SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, /*scale=*/1.0f, window, max_seqlen, 0, stream));
+    SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
+    SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
+    SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, c.d_ff, nullptr, T, c.d_ff, d, SGPT_EPI_GELU_BF16, stream));
+    SGPT_TRY(sgpt_linear(m->ffn, c.d_ff, lw.w_proj, c.d_ff, lw.b_proj, m->resid, d, m->resid, T, d, c.d_ff,
+                         SGPT_EPI_RESID_F32, stream));
+  }
+  const bool final_ln = (layer_idx == c.n_layer);
+  SGPT_TRY(sgpt_pool(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr,
+                     c.ln_eps, out, m->stats, B, T, d, pool_mode, clamp_denominator, normalize, stream));
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_model_residual(sgpt_model_t m, const float** resid, int* T, int* d) {
+  SGPT_REQUIRE(m != nullptr && resid != nullptr && T != nullptr && d != nullptr, "sgpt_model_residual: null argument");
+  *resid = m->resid;
+  *T = m->last_T;
+  *d = m->cfg.d_model;
+  return SGPT_OK;
+}

@@ -1,0 +1,22 @@
+// Source descriptor for the top-k selection kernel (topk.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgpt {
+
+struct TopkSrc {
+  const float* scores = nullptr;     // dense scores or gathered list scores
+  const long long* ids = nullptr;    // explicit ids (id < 0 = empty slot); null -> id = id_base + position
+  const uint2* packed = nullptr;     // (score bits, local index) pairs; overrides scores/ids when set
+  const int32_t* counts = nullptr;   // per-(list, query) valid length (clamped to L); null -> L
+  long long id_base = 0;
+  int G = 1;                         // lists per query
+  int nq = 0;
+  long long L = 0;                   // capacity / length of each list
+  long long stride_g = 0, stride_q = 0;
+};
+
+int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream);
+
+}  // namespace sgpt
