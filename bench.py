@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline hot path on B200: SGPT-125M bi-encoder, batch 256 x seq_len 128 encode
+(GPT-Neo forward + weighted-mean pool) and exact top-1001 cosine retrieval of 128 queries over a 1M-doc corpus shard.
+
+One "step" = encode one batch of 256 synthetic documents  +  search 128 synthetic queries against the resident
+1M x 768 shard (N>1: every rank encodes its own batch and scans its own 1M-doc shard — weak scaling — then one NCCL
+all-gather of the per-shard top-1001 and a merge).  Prints ONE JSON line (rank 0).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+  python bench.py --impl reference ...      # the reference's CPU path (HF GPTNeoModel fp32 + pooling + cos_sim/topk)
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "embeddings/sec (SGPT-125M, batch 256, seq 128) + queries/sec@top-1000 (1M-doc corpus)"
+B, S, NQ, NDOCS, TOPK = 256, 128, 128, 1_000_000, 1000
+CFG = dict(n_layer=12, d_model=768, n_head=12, d_ff=3072, vocab=50257, max_pos=2048)
+
+
+def synthetic_weights(seed=0):
+    """Random-init SGPT-125M (GPT-Neo-125M architecture) weights, HF state_dict keys, bf16-representable values."""
+    g = torch.Generator().manual_seed(seed)
+    d, ff, L = CFG["d_model"], CFG["d_ff"], CFG["n_layer"]
+
+    def rnd(*shape, sd=0.02, mean=0.0):
+        return (torch.randn(*shape, generator=g) * sd + mean).to(torch.bfloat16).float()
+
+    w = {"wte.weight": rnd(CFG["vocab"], d), "wpe.weight": rnd(CFG["max_pos"], d, sd=0.01)}
+    for i in range(L):
+        p = f"h.{i}."
+        w[p + "ln_1.weight"], w[p + "ln_1.bias"] = rnd(d, sd=0.1, mean=1.0), rnd(d, sd=0.05)
+        for n in ("q_proj", "k_proj", "v_proj"):
+            w[p + f"attn.attention.{n}.weight"] = rnd(d, d)
+        w[p + "attn.attention.out_proj.weight"], w[p + "attn.attention.out_proj.bias"] = rnd(d, d), rnd(d)
+        w[p + "ln_2.weight"], w[p + "ln_2.bias"] = rnd(d, sd=0.1, mean=1.0), rnd(d, sd=0.05)
+        w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"] = rnd(ff, d), rnd(ff)
+        w[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"] = rnd(d, ff), rnd(d)
+    w["ln_f.weight"], w["ln_f.bias"] = rnd(d, sd=0.1, mean=1.0), rnd(d, sd=0.05)
+    return w
+
+
+def token_batches(n_batches, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randint(0, CFG["vocab"], (B, S), generator=g, dtype=torch.int64) for _ in range(n_batches)]
+
+
+def encoder_flops_per_seq(S_):
+    """S*2*L*(4d^2 + 2*d*ff) linear FLOPs + L*2*S*(S+1)*d causal attention FLOPs."""
+    L, d, ff = CFG["n_layer"], CFG["d_model"], CFG["d_ff"]
+    return S_ * 2 * L * (4 * d * d + 2 * d * ff), L * 2 * S_ * (S_ + 1) * d
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return dict(hbm=z["hbm_gbs"], tf_burst=z["bf16_tflops"], tf_sustained=z["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_cpu_model(weights):
+    """The reference's encoder on CPU: HF GPTNeoModel fp32 (what AutoModel.from_pretrained resolves to at
+    beir_dense_retriever.py:123); falls back to the oracle's restatement if transformers is unavailable."""
+    try:
+        from transformers import GPTNeoConfig, GPTNeoModel
+
+        cfg = GPTNeoConfig(vocab_size=CFG["vocab"], max_position_embeddings=CFG["max_pos"], hidden_size=CFG["d_model"],
+                           num_layers=CFG["n_layer"], num_heads=CFG["n_head"], intermediate_size=CFG["d_ff"],
+                           window_size=256, attention_types=[[["global", "local"], CFG["n_layer"] // 2]],
+                           embed_dropout=0.0, attention_dropout=0.0, resid_dropout=0.0)
+        m = GPTNeoModel(cfg)
+        m.load_state_dict(weights, strict=False)
+        m = m.float().eval()
+
+        def fwd(ids, mask):
+            with torch.no_grad():
+                return m(input_ids=ids, attention_mask=mask, output_hidden_states=True).hidden_states[-1]
+        return fwd, "HF GPTNeoModel fp32 + oracle.pooling/oracle.search (ports of Pooling.py / exact_search.py)"
+    except Exception:
+        from oracle import gpt_neo
+
+        spec = gpt_neo.NeoSpec()
+
+        def fwd(ids, mask):
+            with torch.no_grad():
+                return gpt_neo.forward(spec, weights, ids, mask)[-1]
+        return fwd, "oracle.gpt_neo restatement + oracle.pooling/oracle.search"
+
+
+_REF_MODEL = {}
+
+
+def cpu_reference_times(weights, enc_batch=32, n_enc=2, search_docs=100_000):
+    """Bounded sample of the reference CPU path: encode `n_enc` batches of `enc_batch` x 128 tokens (+1 warm-up of 8),
+    and cos_sim + topk(1001) of 128 queries over `search_docs` docs in 50k chunks with the heapq merge (XS:80-132)."""
+    from oracle import pooling, search
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    if "m" not in _REF_MODEL:
+        _REF_MODEL["m"] = reference_cpu_model(weights)  # built once per process
+    fwd, how = _REF_MODEL["m"]
+    ids = token_batches(1, seed=77)[0]
+    mask = torch.ones_like(ids)
+    pooling.weighted_mean(fwd(ids[:8], mask[:8]), mask[:8])
+    t0 = time.perf_counter()
+    for i in range(n_enc):
+        sl = slice(i * enc_batch, (i + 1) * enc_batch)
+        pooling.weighted_mean(fwd(ids[sl], mask[sl]), mask[sl])
+    t_enc = time.perf_counter() - t0
+    g = torch.Generator().manual_seed(4321)
+    q, c = torch.randn(NQ, CFG["d_model"], generator=g), torch.randn(search_docs, CFG["d_model"], generator=g)
+    qids, cids = [f"q{i}" for i in range(NQ)], [f"d{i}" for i in range(search_docs)]
+    t0 = time.perf_counter()
+    search.search_embeddings(qids, q, cids, c, TOPK, "cos_sim", corpus_chunk_size=50000)
+    t_search = time.perf_counter() - t0
+    emb_s = n_enc * enc_batch / t_enc
+    qps_1m = NQ / (t_search * (NDOCS / search_docs))
+    return dict(emb_s=emb_s, qps_1m=qps_1m, how=how, t_enc=t_enc, t_search=t_search,
+                sample=f"encode {n_enc}x{enc_batch} seqs of {S} tokens (+8-seq warm-up); search {NQ} queries over "
+                       f"{search_docs} docs in 50k chunks incl. python heapq merge, scaled x{NDOCS // search_docs} to 1M docs")
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    w = synthetic_weights(0)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_times(w, enc_batch=8, n_enc=1, search_docs=50_000)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = cpu_reference_times(w, enc_batch=32, n_enc=1, search_docs=100_000)
+        vals.append(r)
+    wall = time.perf_counter() - t0
+    emb_s = float(np.mean([v["emb_s"] for v in vals]))
+    qps = float(np.mean([v["qps_1m"] for v in vals]))
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": emb_s, "unit": "embeddings/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(args.gpus), "search": {"value": qps, "unit": "queries/s"},
+            "cpu_baseline": {"value": emb_s, "unit": "embeddings/s", "cores": cores, "kind": "port",
+                             "sample": vals[-1]["sample"], "how": vals[-1]["how"], "search_qps_1m": qps},
+            "e2e": {"value": emb_s, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "SGPT-125M (GPT-Neo-125M arch, random-init bf16) bi-encoder: encode batch 256 x seq_len 128 "
+                        "(full-length rows) + weighted-mean pool; cos_sim top-1001 of 128 queries over a 1M x 768 bf16 "
+                        "corpus shard per GPU", "batch": B, "seq_len": S, "queries": NQ, "docs_per_gpu": NDOCS,
+            "top_k": TOPK, "parallelism": f"dp{n} (corpus row-sharded, per-shard top-k all-gather)",
+            "l2": "inputs larger than L2 (activations 0.55 GB, shard 1.5 GB)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from sgpt_b200 import CorpusShard, Encoder, _lib, preset
+    from sgpt_b200.dist import all_gather_topk
+    from sgpt_b200.encoder import pack_ragged
+    from sgpt_b200.index import merge_topk
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    lib = _lib.lib()
+    weights = synthetic_weights(0)
+    enc = Encoder(preset("sgpt-125m"), weights, device=dev, max_tokens=B * S, max_batch=B)
+    batches = token_batches(4, seed=1234 + 1 + rank)
+    mask = np.ones((B, S), dtype=np.int8)
+    # HBM-resident ragged inputs for the device-timed loop
+    resident = []
+    for ids in batches:
+        p, pos, cu, mx = pack_ragged(ids.numpy(), mask)
+        resident.append((torch.from_numpy(p).to(dev), torch.from_numpy(pos).to(dev), torch.from_numpy(cu).to(dev)))
+    # corpus shard: generated on the device in slabs (1% planted near-duplicates of the queries)
+    D = CFG["d_model"]
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    queries = torch.randn(NQ, D, generator=g, device=dev)
+    shard = CorpusShard(D, NDOCS, device=dev, id_base=rank * NDOCS)
+    slab = 100_000
+    for s0 in range(0, NDOCS, slab):
+        c = torch.randn(slab, D, generator=g, device=dev)
+        idx = torch.arange(0, slab, 100, device=dev)
+        c[idx] = queries[(idx // 100) % NQ] + 0.5 * c[idx]
+        shard.add(c)
+    del c
+    q_host = queries.cpu().pin_memory()
+    kk = TOPK + 1
+
+    def search_step(q_dev):
+        s, i = shard.search(q_dev, kk, "cos_sim")
+        if world > 1:
+            gs, gi = all_gather_topk(s, i)
+            s, i = merge_topk(gs, gi)
+        return s, i
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -----------------------------------------------------------------------------------------------
+    for w_ in range(max(args.warmup, 1)):
+        r = resident[w_ % len(resident)]
+        enc.encode_packed(r[0], r[1], r[2], B, B * S, S)
+        search_step(queries)
+        enc.encode_tokens(batches[w_ % 4].numpy(), mask).cpu()
+    barrier()
+
+    # ---- device-timed loop (inputs resident in HBM) -------------------------------------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    prof_ms = (ctypes.c_double * 8)()
+    prof_n = (ctypes.c_int64 * 8)()
+    tot_n0 = (ctypes.c_int64 * 8)()
+    tot_n1 = (ctypes.c_int64 * 8)()
+    lib.sgpt_profile_read(None, None, tot_n0)
+    lib.sgpt_profile_enable(1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        r = resident[k % len(resident)]
+        ev[k][0].record()
+        enc.encode_packed(r[0], r[1], r[2], B, B * S, S)
+        ev[k][1].record()
+        search_step(queries)
+        ev[k][2].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    lib.sgpt_profile_enable(0)
+    lib.sgpt_profile_read(prof_ms, prof_n, tot_n1)
+    enc_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
+    sea_ms = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps))
+    tot_ms = ev[0][0].elapsed_time(ev[-1][2])
+    launches = sum(int(tot_n1[c] - tot_n0[c]) for c in range(8))
+
+    # ---- end-to-end loop: public API, HOST buffers in, HOST results out -------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    d2h = h2d = 0
+    for k in range(args.steps):
+        emb = enc.encode_tokens(batches[k % 4].numpy(), mask)
+        h2d += enc.h2d_bytes_last
+        emb_host = emb.cpu()
+        d2h += emb_host.numel() * 4
+        qd = q_host.to(dev, non_blocking=True)
+        h2d += q_host.numel() * 4
+        s, i = search_step(qd)
+        s_host, i_host = s.cpu(), i.cpu()
+        d2h += s_host.numel() * 4 + i_host.numel() * 8
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    # separate e2e encode-only timing for the headline emb/s
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        enc.encode_tokens(batches[k % 4].numpy(), mask).cpu()
+    barrier()
+    e2e_enc_s = time.perf_counter() - t0
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    enc_ms, sea_ms, tot_ms, e2e_s, e2e_enc_s = maxr(enc_ms), maxr(sea_ms), maxr(tot_ms), maxr(e2e_s), maxr(e2e_enc_s)
+    if rank != 0:
+        return
+    K = args.steps
+    pk = peaks()
+    lin_flops, att_flops = encoder_flops_per_seq(S)
+    emb_per_s = world * B * K / (enc_ms / 1e3)
+    qps = NQ * K / (sea_ms / 1e3)
+    gemm_ms, gemm_n = prof_ms[2], int(prof_n[2])
+    gemm_tflops = (lin_flops * B * K) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    sim_ms, sim_n = prof_ms[5], int(prof_n[5])
+    sim_bytes = NDOCS * D * 2 + NDOCS * 4 + NQ * D * 2  # corpus shard + inv norms + queries
+    sim_gbs = sim_bytes * sim_n / (sim_ms / 1e3) / 1e9 if sim_ms > 0 else None
+    cats = ["embed", "layernorm", "linear_gemm", "attention", "pool", "similarity_gemm", "topk", "misc"]
+    line = {
+        "metric": METRIC, "value": emb_per_s, "unit": "embeddings/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(world),
+        "encode_ms_per_step": enc_ms / K, "search_ms_per_step": sea_ms / K,
+        "search": {"value": qps, "unit": "queries/s", "corpus_docs": NDOCS * world, "top_k": TOPK,
+                   "pairs_per_s": qps * NDOCS * world},
+        "encoder_model_tflops": (lin_flops + att_flops) * B * world * K / (enc_ms / 1e3) / 1e12,
+        "roofline": {"kernel": "gemm_bf16_tn_kernel (tcgen05 linear layers)", "bound": "tensor", "achieved": gemm_tflops,
+                     "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": (gemm_tflops / pk["tf_sustained"]) if gemm_tflops else None, "traffic": None,
+                     "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
+                     "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(1, gemm_n),
+                     "algorithmic_flops_per_launch": lin_flops * B / 48},
+        "roofline_similarity": {"kernel": "gemm_bf16_tn_kernel<EpiScoresF32> (query x corpus)", "bound": "hbm",
+                                "achieved": sim_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": (sim_gbs / pk["hbm"]) if sim_gbs else None, "traffic": None,
+                                "algorithmic_bytes_per_launch": sim_bytes, "avg_launch_ms": sim_ms / max(1, sim_n)},
+        "kernel_ms_per_step": {c: prof_ms[i] / K for i, c in enumerate(cats)},
+        "gpu_launches": launches,
+        "e2e": {"value": world * B * K / e2e_enc_s, "unit": "embeddings/s", "h2d_bytes_per_step": h2d // K,
+                "d2h_bytes_per_step": d2h // K, "full_step_ms": 1000 * e2e_s / K,
+                "search_queries_per_s": None, "note": "public API: Encoder.encode_tokens(host ids) -> .cpu(); "
+                "full_step_ms also includes host->device queries, CorpusShard.search and device->host top-k"},
+        "clocks": clocks, "wall_s_timed_loop": t_wall,
+    }
+    e2e_search_ms = 1000 * e2e_s / K - 1000 * e2e_enc_s / K
+    line["e2e"]["search_queries_per_s"] = NQ / (e2e_search_ms / 1e3) if e2e_search_ms > 0 else None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_times(weights)
+        line["cpu_baseline"] = {"value": r["emb_s"], "unit": "embeddings/s", "cores": os.cpu_count() or 1,
+                                "kind": "port", "sample": r["sample"], "how": r["how"], "search_qps_1m": r["qps_1m"]}
+    print(json.dumps(line), flush=True)
+    enc.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,8 +144,9 @@ int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const in
                 int max_seqlen, int layer_idx, int pool_mode, int clamp_denominator, int normalize, float* out,
                 sgpt_stream_t stream);
 
-/* Debug/parity tap: copy of the fp32 residual stream (hidden_states[layer] before ln_f) of the LAST sgpt_encode. */
-int sgpt_model_residual(sgpt_model_t m, const float** resid, int* T, int* d);
+/* Debug/parity tap: copies the fp32 residual stream (hidden_states[layer] before ln_f) left by the LAST sgpt_encode
+ * into dst (device, capacity_elems floats) and reports its shape. */
+int sgpt_model_read_residual(sgpt_model_t m, float* dst, int64_t capacity_elems, int* T, int* d, sgpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * S1–S3. Exact dense retrieval over one corpus shard.
@@ -173,9 +174,28 @@ int sgpt_topk(const float* scores, int64_t lds, int nq, int64_t n, int k, int64_
 
 /* S3. Merge G candidate lists per query (cross-chunk heapq.nlargest merge XS:121-132; cross-shard merge after the
  *     all-gather): in_scores fp32[G,nq,k], in_ids int64[G,nq,k] -> out fp32/int64[nq,k], descending; entries with
- *     id < 0 are ignored. */
+ *     id < 0 are ignored, and so are entries whose id equals exclude_ids[q] (the `corpus_id != query_id` self-match
+ *     rule of XS:118; exclude_ids int64[nq] or NULL). */
 int sgpt_topk_merge(const float* in_scores, const int64_t* in_ids, int G, int nq, int k, float* out_scores,
-                    int64_t* out_ids, void* ws, sgpt_stream_t stream);
+                    int64_t* out_ids, const int64_t* exclude_ids, void* ws, sgpt_stream_t stream);
+
+/* S1+S2 in one call: exact top-k of one corpus shard for a batch of queries (XS:96-108 for one chunk).
+ *     Q bf16[nq,D], C bf16[n,D], q_scale/c_scale as sgpt_scores; out_scores fp32[nq,k], out_ids int64[nq,k]
+ *     (descending, ids offset by id_base, tail (-inf,-1) when n < k).  ws: sgpt_search_workspace_bytes(nq,n,k). */
+int64_t sgpt_search_workspace_bytes(int nq, int64_t n, int k);
+int sgpt_search(const void* Q, const void* C, const float* q_scale, const float* c_scale, int nq, int64_t n, int D,
+                int k, int64_t id_base, float* out_scores, int64_t* out_ids, void* ws, int64_t ws_bytes,
+                sgpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): launch counters are always on; with profiling enabled every kernel launch issued
+ * through this library is bracketed by CUDA events on its stream.  sgpt_profile_read waits for them, returns the
+ * summed device milliseconds and launch counts per category since the previous read, and resets the timed set.
+ * Categories: 0 embed, 1 layernorm, 2 linear GEMM, 3 attention, 4 pool, 5 similarity GEMM, 6 top-k, 7 misc.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define SGPT_NUM_LAUNCH_CATEGORIES 8
+int sgpt_profile_enable(int on);
+int sgpt_profile_read(double* ms_by_cat, int64_t* timed_launches_by_cat, int64_t* total_launches_by_cat);
 
 #ifdef __cplusplus
 }

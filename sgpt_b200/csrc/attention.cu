@@ -326,6 +326,7 @@ static int launch_attention_tc(const void* qkv, void* out, const int32_t* cu, in
   }
   dim3 grid((max_seqlen + kAttnTile - 1) / kAttnTile, B, H);
   const float sl2 = scale * 1.4426950408889634f;
+  LaunchScope _ls(kCatAttention, stream);
   kern<<<grid, 128, Cfg::kSmemBytes, stream>>>(map, static_cast<__nv_bfloat16*>(out), cu, H, sl2, window);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
@@ -335,6 +336,7 @@ template <int HD>
 static int launch_attention_simt(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale,
                                  int window, cudaStream_t stream) {
   dim3 grid((T + 7) / 8, H);
+  LaunchScope _ls(kCatAttention, stream);
   attention_simt_kernel<HD><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                       static_cast<__nv_bfloat16*>(out), cu, B, T, H, scale, window);
   SGPT_CHECK_CUDA(cudaGetLastError());

@@ -284,6 +284,7 @@ extern "C" int sgpt_embed_tokens(const int32_t* ids, const int32_t* pos, const v
   SGPT_REQUIRE(wpe == nullptr || pos != nullptr, "sgpt_embed_tokens: pos required when wpe is given");
   if (T == 0) return SGPT_OK;
   const int d8 = d / 8;
+  LaunchScope _ls(kCatEmbed, stream);
   embed_kernel<<<grid_for(static_cast<long long>(T) * d8, 256), 256, 0, stream>>>(
       ids, pos, static_cast<const uint4*>(wte), static_cast<const uint4*>(wpe), reinterpret_cast<float4*>(resid), T,
       d8, vocab, max_pos);
@@ -297,6 +298,7 @@ extern "C" int sgpt_layernorm(const float* x, const float* gamma, const float* b
   SGPT_REQUIRE(T >= 0 && d > 0 && d % 4 == 0, "sgpt_layernorm: d=%d must be a positive multiple of 4", d);
   if (T == 0) return SGPT_OK;
   const int d4 = d / 4;
+  LaunchScope _ls(kCatLayerNorm, stream);
   SGPT_ROW_DISPATCH(layernorm_kernel, d4, T, stream, reinterpret_cast<const float4*>(x),
                     reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
                     static_cast<uint2*>(y), T, d4, eps);
@@ -314,6 +316,7 @@ extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_s
   SGPT_REQUIRE((gamma == nullptr) == (beta == nullptr), "sgpt_pool: gamma and beta must be given together");
   SGPT_REQUIRE(gamma == nullptr || row_stats_ws != nullptr, "sgpt_pool: ln_f fusion needs row_stats_ws");
   if (B == 0) return SGPT_OK;
+  LaunchScope _ls(kCatPool, stream);
   const int d4 = d / 4;
   const float2* stats = nullptr;
   if (gamma != nullptr && T > 0) {
@@ -348,6 +351,7 @@ extern "C" int sgpt_row_inv_norms(const void* x, float* inv_norm, int64_t n, int
   if (n == 0) return SGPT_OK;
   const long long blocks = (n + 7) / 8;
   SGPT_REQUIRE(blocks < (1ll << 31), "sgpt_row_inv_norms: too many rows");
+  LaunchScope _ls(kCatMisc, stream);
   row_inv_norm_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint4*>(x), inv_norm, n,
                                                                           D / 8);
   SGPT_CHECK_CUDA(cudaGetLastError());
@@ -358,6 +362,7 @@ extern "C" int sgpt_f32_to_bf16(const float* x, void* y, int64_t count, sgpt_str
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(count >= 0 && count % 4 == 0, "sgpt_f32_to_bf16: count must be a multiple of 4");
   if (count == 0) return SGPT_OK;
+  LaunchScope _ls(kCatMisc, stream);
   f32_to_bf16_kernel<<<grid_for(count / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
                                                                     static_cast<uint2*>(y), count / 4);
   SGPT_CHECK_CUDA(cudaGetLastError());

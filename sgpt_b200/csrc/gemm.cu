@@ -9,7 +9,7 @@ namespace sgpt {
 
 template <int BN, class Epi>
 static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K,
-                       const typename Epi::Params& ep, cudaStream_t stream) {
+                       const typename Epi::Params& ep, cudaStream_t stream, int cat = kCatGemm) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
   int rc = make_tma_2d_bf16(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
@@ -29,6 +29,7 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
   int grid = sm_count();
   if (tiles < grid) grid = static_cast<int>(tiles);
+  LaunchScope _ls(cat, stream);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
@@ -97,5 +98,5 @@ extern "C" int sgpt_scores(const void* Q, const void* C, const float* q_scale, c
   if (nq == 0 || n == 0) return SGPT_OK;
   EpiScoresF32::Params p{scores, q_scale, c_scale, static_cast<long long>(lds)};
   // lanes = queries (A operand), columns = corpus rows (B operand, streamed once from HBM)
-  return launch_gemm<256, EpiScoresF32>(Q, D, C, D, nq, static_cast<int>(n), D, p, stream);
+  return launch_gemm<256, EpiScoresF32>(Q, D, C, D, nq, static_cast<int>(n), D, p, stream, kCatScores);
 }

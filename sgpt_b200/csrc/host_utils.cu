@@ -71,3 +71,72 @@ int sm_count() {
 }  // namespace sgpt
 
 extern "C" const char* sgpt_last_error(void) { return sgpt::get_error(); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ---------------------------------------------------------------------------------------------------------------
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+namespace sgpt {
+
+static std::atomic<long long> g_launches[kNumCats];
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+struct ProfRec { cudaEvent_t a, b; int cat; };
+static std::vector<ProfRec> g_recs;       // recorded scopes since the last read
+static std::vector<ProfRec> g_free;       // recycled event pairs
+
+LaunchScope::LaunchScope(int cat, cudaStream_t stream) : cat_(cat), stream_(stream), slot_(-1) {
+  g_launches[cat].fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  if (!g_free.empty()) {
+    r = g_free.back();
+    g_free.pop_back();
+  } else {
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  }
+  r.cat = cat;
+  cudaEventRecord(r.a, stream);
+  g_recs.push_back(r);
+  slot_ = static_cast<int>(g_recs.size()) - 1;
+}
+
+LaunchScope::~LaunchScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot_ < static_cast<int>(g_recs.size())) cudaEventRecord(g_recs[slot_].b, stream_);
+}
+
+}  // namespace sgpt
+
+extern "C" int sgpt_profile_enable(int on) {
+  sgpt::g_prof_on.store(on != 0);
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_profile_read(double* ms_by_cat, int64_t* timed_launches_by_cat, int64_t* total_launches_by_cat) {
+  using namespace sgpt;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int c = 0; c < kNumCats; ++c) {
+    if (ms_by_cat) ms_by_cat[c] = 0.0;
+    if (timed_launches_by_cat) timed_launches_by_cat[c] = 0;
+    if (total_launches_by_cat) total_launches_by_cat[c] = g_launches[c].load();
+  }
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.b) == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+        if (ms_by_cat) ms_by_cat[r.cat] += ms;
+        if (timed_launches_by_cat) timed_launches_by_cat[r.cat] += 1;
+      }
+    }
+    g_free.push_back(r);
+  }
+  g_recs.clear();
+  cudaGetLastError();
+  return SGPT_OK;
+}

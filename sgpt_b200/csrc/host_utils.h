@@ -36,3 +36,18 @@ int make_tma_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 int sm_count();
 
 }  // namespace sgpt
+
+// ---------------------------------------------------------------------------------------------------------------
+// Launch accounting (always on) and optional per-category CUDA-event timing (sgpt_profile_*).
+// ---------------------------------------------------------------------------------------------------------------
+namespace sgpt {
+enum LaunchCat { kCatEmbed = 0, kCatLayerNorm, kCatGemm, kCatAttention, kCatPool, kCatScores, kCatTopk, kCatMisc, kNumCats };
+
+struct LaunchScope {
+  LaunchScope(int cat, cudaStream_t stream);
+  ~LaunchScope();
+  int cat_;
+  cudaStream_t stream_;
+  int slot_;
+};
+}  // namespace sgpt

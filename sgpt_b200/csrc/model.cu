@@ -132,10 +132,14 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
   return SGPT_OK;
 }
 
-extern "C" int sgpt_model_residual(sgpt_model_t m, const float** resid, int* T, int* d) {
-  SGPT_REQUIRE(m != nullptr && resid != nullptr && T != nullptr && d != nullptr, "sgpt_model_residual: null argument");
-  *resid = m->resid;
+extern "C" int sgpt_model_read_residual(sgpt_model_t m, float* dst, int64_t capacity_elems, int* T, int* d,
+                                        sgpt_stream_t stream) {
+  SGPT_REQUIRE(m != nullptr && dst != nullptr && T != nullptr && d != nullptr, "sgpt_model_read_residual: null argument");
   *T = m->last_T;
   *d = m->cfg.d_model;
+  const int64_t n = static_cast<int64_t>(m->last_T) * m->cfg.d_model;
+  SGPT_REQUIRE(capacity_elems >= n, "sgpt_model_read_residual: destination too small");
+  SGPT_CHECK_CUDA(cudaMemcpyAsync(dst, m->resid, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice,
+                                  static_cast<cudaStream_t>(stream)));
   return SGPT_OK;
 }

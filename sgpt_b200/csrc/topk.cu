@@ -39,7 +39,7 @@ __device__ __forceinline__ Elem load_elem(const TopkSrc& s, int q, int g, long l
     e.key = score_key(s.scores[off]);
     if (s.ids != nullptr) {
       e.id = s.ids[off];
-      if (e.id < 0) e.key = 0;
+      if (e.id < 0 || (s.exclude != nullptr && e.id == s.exclude[q])) e.key = 0;
     } else {
       e.id = s.id_base + i;
     }
@@ -213,6 +213,7 @@ int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));
     attr_set = true;
   }
+  LaunchScope _ls(kCatTopk, stream);
   topk_select_kernel<<<nq, kTopkThreads, dsm, stream>>>(src, k, KP, out_scores, reinterpret_cast<long long*>(out_ids));
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
@@ -245,7 +246,8 @@ extern "C" int sgpt_topk(const float* scores, int64_t lds, int nq, int64_t n, in
 }
 
 extern "C" int sgpt_topk_merge(const float* in_scores, const int64_t* in_ids, int G, int nq, int k,
-                               float* out_scores, int64_t* out_ids, void* ws, sgpt_stream_t stream_) {
+                               float* out_scores, int64_t* out_ids, const int64_t* exclude_ids, void* ws,
+                               sgpt_stream_t stream_) {
   (void)ws;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(G >= 1 && nq >= 0, "sgpt_topk_merge: bad sizes G=%d nq=%d", G, nq);
@@ -253,6 +255,7 @@ extern "C" int sgpt_topk_merge(const float* in_scores, const int64_t* in_ids, in
   TopkSrc src{};
   src.scores = in_scores;
   src.ids = reinterpret_cast<const long long*>(in_ids);
+  src.exclude = reinterpret_cast<const long long*>(exclude_ids);
   src.G = G;
   src.nq = nq;
   src.L = k;

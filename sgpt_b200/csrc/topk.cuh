@@ -8,6 +8,7 @@ namespace sgpt {
 struct TopkSrc {
   const float* scores = nullptr;     // dense scores or gathered list scores
   const long long* ids = nullptr;    // explicit ids (id < 0 = empty slot); null -> id = id_base + position
+  const long long* exclude = nullptr;  // per-query id to drop (self match, XS:118); only with explicit ids
   const uint2* packed = nullptr;     // (score bits, local index) pairs; overrides scores/ids when set
   const int32_t* counts = nullptr;   // per-(list, query) valid length (clamped to L); null -> L
   long long id_base = 0;

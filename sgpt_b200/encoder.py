@@ -1,0 +1,198 @@
+"""Device-side encoder: HF-layout weights -> packed bf16 device buffers -> one C call per batch.
+
+Replaces ``AutoModel.from_pretrained(...).to(device)`` + ``self.model(**batch_tokens, output_hidden_states=True)`` +
+the pooling block of the reference (biencoder/beir/beir_dense_retriever.py:123, :205, :233-304; ST path:
+sentence_transformers/models/Transformer.py:72 + models/Pooling.py:85-168).  PyTorch is used for device memory,
+streams and host<->device copies only; all arithmetic runs in libsgpt_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import ModelConfig
+
+POOL_MODES = {"mean": _lib.POOL_MEAN, "weightedmean": _lib.POOL_WEIGHTEDMEAN, "lasttoken": _lib.POOL_LASTTOKEN}
+
+
+def pack_ragged(input_ids, attention_mask) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:
+    """[B,S] padded ids + mask (host) -> ragged layout: packed ids[T], padded-row index pos[T], cu_seqlens[B+1].
+
+    `pos` is the index of the token inside its PADDED row: that is what both the position embedding
+    (HF:gpt_neo/modeling_gpt_neo.py:455-463: position_ids = arange(S)) and the pooling weights
+    (beir_dense_retriever.py:259-265: arange(1, S+1)) are functions of, for left- or right-padded rows alike.
+    Each row's mask must be one contiguous run of ones (what tokenizer.pad produces, BDR:201).
+    """
+    ids = np.asarray(input_ids)
+    mask = np.asarray(attention_mask).astype(bool)
+    if ids.ndim != 2 or mask.shape != ids.shape:
+        raise ValueError(f"input_ids / attention_mask must be [B,S] of equal shape, got {ids.shape} and {mask.shape}")
+    B, S = ids.shape
+    lens = mask.sum(axis=1)
+    first = np.where(lens > 0, mask.argmax(axis=1), 0)
+    last = np.where(lens > 0, S - 1 - mask[:, ::-1].argmax(axis=1), -1)
+    if np.any((last - first + 1)[lens > 0] != lens[lens > 0]):
+        raise ValueError("attention_mask rows must be contiguous runs of ones (left- or right-padded)")
+    cu = np.zeros(B + 1, dtype=np.int32)
+    np.cumsum(lens, out=cu[1:])
+    flat = mask.reshape(-1)
+    packed_ids = ids.reshape(-1)[flat].astype(np.int32)
+    pos = np.broadcast_to(np.arange(S, dtype=np.int32), (B, S)).reshape(-1)[flat]
+    return packed_ids, np.ascontiguousarray(pos), cu, int(lens.max()) if B else 0
+
+
+class Encoder:
+    """GPT encoder + pooling on one GPU.
+
+    state_dict: tensors keyed like HF ``GPTNeoModel.state_dict()`` (``wte.weight``, ``h.0.ln_1.weight``, ...; a
+    ``transformer.`` prefix as in ``GPTNeoForCausalLM`` checkpoints is accepted).  Linear weights are stored in bf16,
+    LayerNorm parameters and biases in fp32.
+    """
+
+    def __init__(self, cfg: ModelConfig, state_dict: Dict[str, torch.Tensor], device="cuda:0", max_tokens: int = 32768,
+                 max_batch: int = 1024):
+        if cfg.arch != "gpt_neo":
+            raise NotImplementedError(f"arch {cfg.arch!r}: only gpt_neo is built so far (GPT-J / BLOOM are next)")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("sgpt_b200.Encoder needs a CUDA device; there is no CPU path")
+        self.max_tokens = int(max_tokens)
+        self.max_batch = int(max_batch)
+        self._lib = _lib.lib()
+        self._keep = []  # device tensors the C handle borrows
+        sd = {(k[len("transformer."):] if k.startswith("transformer.") else k): v for k, v in state_dict.items()}
+
+        def dev(t, dtype):
+            x = t.detach().to(device=self.device, dtype=dtype).contiguous()
+            self._keep.append(x)
+            return x
+
+        with torch.cuda.device(self.device):
+            d = cfg.d_model
+            wte = dev(sd["wte.weight"], torch.bfloat16)
+            wpe = dev(sd["wpe.weight"], torch.bfloat16)
+            if wte.shape != (cfg.vocab, d) or wpe.shape != (cfg.max_pos, d):
+                raise ValueError(f"embedding shapes {tuple(wte.shape)}, {tuple(wpe.shape)} do not match the config")
+            layers = (_lib.LayerWeightsC * cfg.n_layer)()
+            for i in range(cfg.n_layer):
+                p = f"h.{i}."
+                a = p + "attn.attention."
+                w_qkv = dev(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0),
+                            torch.bfloat16)
+                b_qkv = None
+                if (a + "q_proj.bias") in sd:
+                    b_qkv = dev(torch.cat([sd[a + "q_proj.bias"], sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0),
+                                torch.float32)
+                lw = layers[i]
+                lw.ln1_g = dev(sd[p + "ln_1.weight"], torch.float32).data_ptr()
+                lw.ln1_b = dev(sd[p + "ln_1.bias"], torch.float32).data_ptr()
+                lw.w_qkv = w_qkv.data_ptr()
+                lw.b_qkv = _lib.ptr(b_qkv)
+                lw.w_o = dev(sd[a + "out_proj.weight"], torch.bfloat16).data_ptr()
+                lw.b_o = dev(sd[a + "out_proj.bias"], torch.float32).data_ptr()
+                lw.ln2_g = dev(sd[p + "ln_2.weight"], torch.float32).data_ptr()
+                lw.ln2_b = dev(sd[p + "ln_2.bias"], torch.float32).data_ptr()
+                lw.w_fc = dev(sd[p + "mlp.c_fc.weight"], torch.bfloat16).data_ptr()
+                lw.b_fc = dev(sd[p + "mlp.c_fc.bias"], torch.float32).data_ptr()
+                lw.w_proj = dev(sd[p + "mlp.c_proj.weight"], torch.bfloat16).data_ptr()
+                lw.b_proj = dev(sd[p + "mlp.c_proj.bias"], torch.float32).data_ptr()
+                lw.local_attention = 1 if cfg.attention_layers[i] == "local" else 0
+            mw = _lib.ModelWeightsC()
+            mw.wte = wte.data_ptr()
+            mw.wpe = wpe.data_ptr()
+            mw.lnf_g = dev(sd["ln_f.weight"], torch.float32).data_ptr()
+            mw.lnf_b = dev(sd["ln_f.bias"], torch.float32).data_ptr()
+            mw.layers = layers
+            self._layers = layers
+            mc = _lib.ModelConfigC(arch=_lib.ARCH_GPT_NEO, n_layer=cfg.n_layer, d_model=d, n_head=cfg.n_head,
+                                   d_ff=cfg.d_ff, vocab=cfg.vocab, max_pos=cfg.max_pos, window=cfg.window,
+                                   rotary_dim=cfg.rotary_dim, ln_eps=cfg.ln_eps, max_tokens=self.max_tokens,
+                                   max_batch=self.max_batch)
+            handle = C.c_void_p()
+            _lib.check(self._lib.sgpt_model_create(C.byref(mc), C.byref(mw), C.byref(handle)), "sgpt_model_create")
+            self._handle = handle
+        # two pinned staging buffers for [ids | pos | cu] and their device twins: one H2D copy per batch, and the
+        # host may pack batch i+1 while the GPU still runs batch i
+        cap = 2 * self.max_tokens + self.max_batch + 1
+        self._stage_host = [torch.empty(cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        self._stage_dev = [torch.empty(cap, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self._stage_evt = [torch.cuda.Event() for _ in range(2)]
+        self._stage_idx = 0
+        self.h2d_bytes_last = 0
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.sgpt_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def embedding_dim(self) -> int:
+        return self.cfg.d_model
+
+    def encode_packed(self, ids: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, B: int, T: int, max_seqlen: int,
+                      method: str = "weightedmean", layer_idx: int = -1, clamp: bool = False, normalize: bool = False,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Ragged batch already on the device (int32 tensors) -> fp32 [B, d] embeddings on the device."""
+        if method not in POOL_MODES:
+            raise ValueError(f"pooling method {method!r} not in {sorted(POOL_MODES)}")
+        if out is None:
+            out = torch.empty((B, self.cfg.d_model), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.sgpt_encode(self._handle, ids.data_ptr(), pos.data_ptr(), cu.data_ptr(), B, T, max_seqlen,
+                                       layer_idx, POOL_MODES[method], int(clamp), int(normalize), out.data_ptr(),
+                                       _lib.current_stream())
+        _lib.check(rc, "sgpt_encode")
+        return out
+
+    def encode_tokens(self, input_ids, attention_mask, method: str = "weightedmean", layer_idx: int = -1,
+                      clamp: bool = False, normalize: bool = False) -> torch.Tensor:
+        """Padded [B,S] ids + mask (numpy or CPU/GPU torch) -> fp32 [B, d] embeddings on the device.
+
+        The padded batch is packed on the host (padding never reaches the GPU) and shipped with ONE pinned H2D copy.
+        """
+        if isinstance(input_ids, torch.Tensor):
+            input_ids = input_ids.detach().cpu().numpy()
+        if isinstance(attention_mask, torch.Tensor):
+            attention_mask = attention_mask.detach().cpu().numpy()
+        ids, pos, cu, max_len = pack_ragged(input_ids, attention_mask)
+        B, T = len(cu) - 1, int(cu[-1])
+        if T > self.max_tokens or B > self.max_batch:
+            raise ValueError(f"batch of {B} rows / {T} tokens exceeds the encoder workspace "
+                             f"({self.max_batch} rows / {self.max_tokens} tokens)")
+        if max_len > self.cfg.max_pos:
+            raise ValueError(f"sequence length {max_len} exceeds max_position_embeddings {self.cfg.max_pos}")
+        n = 2 * T + B + 1
+        slot = self._stage_idx
+        self._stage_idx ^= 1
+        self._stage_evt[slot].synchronize()  # the copy that last used this pinned buffer has finished
+        host = self._stage_host[slot][:n].numpy()
+        host[:T] = ids
+        host[T:2 * T] = pos
+        host[2 * T:] = cu
+        dev = self._stage_dev[slot]
+        with torch.cuda.device(self.device):
+            dev[:n].copy_(self._stage_host[slot][:n], non_blocking=True)
+            self._stage_evt[slot].record()
+        self.h2d_bytes_last = n * 4
+        return self.encode_packed(dev[:T], dev[T:2 * T], dev[2 * T:n], B, T, max_len, method, layer_idx, clamp,
+                                  normalize)
+
+    def last_residual(self) -> torch.Tensor:
+        """fp32 [T, d] residual stream of the last encode call (parity/debug tap), copied out of the workspace."""
+        T, d = C.c_int32(), C.c_int32()
+        buf = torch.empty(self.max_tokens * self.cfg.d_model, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sgpt_model_read_residual(self._handle, buf.data_ptr(), buf.numel(), C.byref(T),
+                                                          C.byref(d), _lib.current_stream()))
+        return buf[:T.value * d.value].view(T.value, d.value)

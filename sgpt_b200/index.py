@@ -1,0 +1,118 @@
+"""Corpus shard in HBM + exact top-k search over it (rows S1–S3 of SURVEY.md §8a).
+
+A shard holds the embeddings of a contiguous range of documents as a bf16 matrix [n, D] (read once per search at
+HBM speed) plus fp32 1/||row|| of the STORED rows, so cosine scores are exactly ``cos_sim`` of the stored vectors
+(sentence_transformers/util.py:24-43) and dot scores are exactly ``dot_score`` (:46-63).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+SCORE_FUNCTIONS = ("cos_sim", "dot")
+
+
+def _check_score_function(score_function: str) -> None:
+    if score_function not in SCORE_FUNCTIONS:
+        # same message as biencoder/beir/custommodels/exact_search.py:46-51
+        raise ValueError(
+            "score function: {} must be either (cos_sim) for cosine similarity or (dot) for dot product".format(
+                score_function))
+
+
+def to_bf16_rows(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [n, D] (device) -> bf16 [n, D] (round-to-nearest-even) with the library's conversion kernel."""
+    x = x.contiguous()
+    assert x.dtype == torch.float32 and x.is_cuda and x.numel() % 4 == 0
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().sgpt_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _lib.current_stream()))
+    return out
+
+
+def row_inv_norms(x_bf16: torch.Tensor) -> torch.Tensor:
+    n, D = x_bf16.shape
+    out = torch.empty(n, dtype=torch.float32, device=x_bf16.device)
+    with torch.cuda.device(x_bf16.device):
+        _lib.check(_lib.lib().sgpt_row_inv_norms(x_bf16.data_ptr(), out.data_ptr(), n, D, _lib.current_stream()))
+    return out
+
+
+class CorpusShard:
+    """Documents [id_base, id_base + n) of a corpus, resident in the HBM of one GPU."""
+
+    def __init__(self, dim: int, capacity: int, device="cuda:0", id_base: int = 0):
+        if dim % 8 != 0:
+            raise ValueError("embedding dimension must be a multiple of 8")
+        self.dim, self.capacity, self.id_base = int(dim), int(capacity), int(id_base)
+        self.device = torch.device(device)
+        self.vectors = torch.empty((self.capacity, self.dim), dtype=torch.bfloat16, device=self.device)
+        self.inv_norms = torch.empty(self.capacity, dtype=torch.float32, device=self.device)
+        self.n = 0
+        self._ws: Optional[torch.Tensor] = None
+
+    @classmethod
+    def from_embeddings(cls, emb: torch.Tensor, device=None, id_base: int = 0) -> "CorpusShard":
+        device = device or emb.device
+        shard = cls(emb.shape[1], emb.shape[0], device=device, id_base=id_base)
+        shard.add(emb)
+        return shard
+
+    def add(self, emb: torch.Tensor) -> None:
+        """Append fp32 (or bf16) embeddings [m, D]; they are stored bf16-rounded."""
+        m = emb.shape[0]
+        if self.n + m > self.capacity:
+            raise ValueError(f"shard capacity {self.capacity} exceeded ({self.n} + {m})")
+        emb = emb.to(self.device)
+        rows = emb if emb.dtype == torch.bfloat16 else to_bf16_rows(emb.float())
+        self.vectors[self.n:self.n + m].copy_(rows)
+        self.inv_norms[self.n:self.n + m].copy_(row_inv_norms(self.vectors[self.n:self.n + m]))
+        self.n += m
+
+    def stored(self) -> torch.Tensor:
+        return self.vectors[:self.n]
+
+    def search(self, queries: torch.Tensor, k: int, score_function: str = "cos_sim") -> Tuple[torch.Tensor, torch.Tensor]:
+        """Exact top-k of this shard for fp32/bf16 queries [Q, D] (device).
+
+        Returns (scores fp32 [Q,k] descending, global ids int64 [Q,k]); when the shard has fewer than k documents the
+        tail is (-inf, -1).  Queries are rounded to bf16 (the tensor-core input type); their 1/||q|| is taken from the
+        rounded rows so the result equals cos_sim of the stored/rounded vectors evaluated in fp32.
+        """
+        _check_score_function(score_function)
+        q = queries.to(self.device)
+        qb = q.contiguous() if q.dtype == torch.bfloat16 else to_bf16_rows(q.float())
+        nq = qb.shape[0]
+        cos = score_function == "cos_sim"
+        q_scale = row_inv_norms(qb) if cos else None
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        lib = _lib.lib()
+        need = lib.sgpt_search_workspace_bytes(nq, self.n, k)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = lib.sgpt_search(qb.data_ptr(), self.vectors.data_ptr(), _lib.ptr(q_scale),
+                                 self.inv_norms.data_ptr() if cos else None, nq, self.n, self.dim, k, self.id_base,
+                                 out_s.data_ptr(), out_i.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                 _lib.current_stream())
+        _lib.check(rc, "sgpt_search")
+        return out_s, out_i
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, exclude_ids: Optional[torch.Tensor] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge G candidate lists per query: scores fp32 [G,Q,k], ids int64 [G,Q,k] -> ([Q,k], [Q,k]) descending.
+    Entries with id < 0, or id == exclude_ids[q] (int64 [Q], the XS:118 self-match rule), are dropped."""
+    G, Q, k = scores.shape
+    scores, ids = scores.contiguous(), ids.contiguous()
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        rc = _lib.lib().sgpt_topk_merge(scores.data_ptr(), ids.data_ptr(), G, Q, k, out_s.data_ptr(), out_i.data_ptr(),
+                                        _lib.ptr(exclude_ids), None, _lib.current_stream())
+    _lib.check(rc, "sgpt_topk_merge")
+    return out_s, out_i

@@ -371,7 +371,7 @@ static void test_scores_topk(int nq, int n, int D, int k) {
     int64_t* dmi = to_dev(mi);
     float* dos = dalloc<float>((size_t)nq * k);
     int64_t* doi = dalloc<int64_t>((size_t)nq * k);
-    SG(sgpt_topk_merge(dms, dmi, G, nq, k, dos, doi, nullptr, 0));
+    SG(sgpt_topk_merge(dms, dmi, G, nq, k, dos, doi, nullptr, nullptr, 0));
     CK(cudaDeviceSynchronize());
     auto os = to_host(dos, (size_t)nq * k);
     auto oi = to_host(doi, (size_t)nq * k);

@@ -1,0 +1,277 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI (ctypes -> libsgpt_b200.so).
+
+Bars (BASELINE.json north_star): pooled embeddings within 1e-3 cosine of the reference HF path on the same inputs and
+weights; identical top-k document ids vs the oracle evaluated on the same stored (bf16-rounded) vectors, ties at the
+cut compared as sets.  Golden fixtures were produced by the reference code itself (tests/golden/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpt_neo, pooling, search
+from tests.helpers import ToyTokenizer, min_row_cosine, planted_corpus, ragged_batch
+
+pytestmark = pytest.mark.gpu
+
+COS_TOL = 1e-3  # north_star: "within 1e-3 cosine on pooled embeddings"
+
+
+def _cfg_from_spec(spec):
+    from sgpt_b200 import ModelConfig
+
+    return ModelConfig(arch="gpt_neo", n_layer=spec.n_layer, d_model=spec.d_model, n_head=spec.n_head, d_ff=spec.d_ff,
+                       vocab=spec.vocab, max_pos=spec.max_pos, window=spec.window, ln_eps=spec.ln_eps,
+                       attention_layers=list(spec.attention_layers))
+
+
+def _spec_from(npz):
+    L, d, H, ff, vocab, max_pos, window = [int(x) for x in npz["spec"]]
+    return gpt_neo.NeoSpec(n_layer=L, d_model=d, n_head=H, d_ff=ff, vocab=vocab, max_pos=max_pos, window=window)
+
+
+@pytest.fixture(scope="module")
+def tiny_encoder(golden_dir):
+    from sgpt_b200 import Encoder
+
+    z = np.load(os.path.join(golden_dir, "neo_tiny.npz"))
+    spec = _spec_from(z)
+    w = gpt_neo.init_weights(spec, seed=int(z["weight_seed"]))
+    enc = Encoder(_cfg_from_spec(spec), w, device="cuda:0", max_tokens=4096, max_batch=64)
+    yield z, spec, w, enc
+    enc.close()
+
+
+def test_tiny_model_all_pooling_modes_vs_reference_fixture(tiny_encoder):
+    """4-layer model with window 16 < S 48 (local-attention layers active), ragged lengths incl. 1 and S."""
+    z, spec, w, enc = tiny_encoder
+    ids, mask = z["input_ids"], z["attention_mask"]
+    got = enc.encode_tokens(ids, mask, method="weightedmean").cpu()
+    assert min_row_cosine(got, z["pooled_weightedmean"]) > 1 - COS_TOL
+    assert np.abs(got.numpy() - z["pooled_weightedmean"]).max() < 0.05
+    got = enc.encode_tokens(ids, mask, method="mean").cpu()
+    assert min_row_cosine(got, z["pooled_mean"]) > 1 - COS_TOL
+    # lasttoken: script semantics (BDR:271-282); Pooling.py's argmin variant is wrong on unpadded rows, so compare with
+    # the oracle's script variant on the reference hidden states
+    hs_last = torch.from_numpy(z["hidden_states"][-1])
+    want = pooling.last_token(hs_last, torch.from_numpy(mask).long())
+    got = enc.encode_tokens(ids, mask, method="lasttoken").cpu()
+    assert min_row_cosine(got, want) > 1 - COS_TOL
+    mid = int(z["mid_layer"])
+    got = enc.encode_tokens(ids, mask, method="weightedmean", layer_idx=mid).cpu()
+    assert min_row_cosine(got, z["pooled_weightedmean_mid"]) > 1 - COS_TOL
+    # normalize + clamp flags (ST path)
+    got = enc.encode_tokens(ids, mask, method="weightedmean", clamp=True, normalize=True).cpu()
+    assert torch.allclose(got.norm(dim=1), torch.ones(len(got)), atol=1e-5)
+    assert min_row_cosine(got, z["pooled_weightedmean"]) > 1 - COS_TOL
+
+
+def test_tiny_model_residual_stream_vs_reference_hidden_states(tiny_encoder):
+    """Per-token check: the fp32 residual stream after all blocks, passed through ln_f on the host, must match HF's
+    last hidden state (bf16 activations between kernels bound the error)."""
+    z, spec, w, enc = tiny_encoder
+    ids, mask = z["input_ids"], z["attention_mask"]
+    enc.encode_tokens(ids, mask, method="weightedmean")
+    resid = enc.last_residual().cpu()
+    h = gpt_neo.layer_norm(resid, w["ln_f.weight"], w["ln_f.bias"], spec.ln_eps)
+    ref = torch.from_numpy(z["hidden_states"][-1])[torch.from_numpy(mask).bool()]
+    assert h.shape == ref.shape
+    cos = torch.nn.functional.cosine_similarity(h.double(), ref.double(), dim=1)
+    assert cos.min().item() > 1 - COS_TOL
+    assert (h - ref).abs().max().item() < 0.08
+
+
+def test_left_padded_rows_use_padded_positions(tiny_encoder):
+    """Pooling weights / position ids follow the PADDED index (Pooling.py:104-112; HF position_ids = arange(S))."""
+    z, spec, w, enc = tiny_encoder
+    g = torch.Generator().manual_seed(3)
+    S = 24
+    ids = torch.randint(0, spec.vocab, (3, S), generator=g)
+    mask = torch.zeros(3, S, dtype=torch.long)
+    mask[0, 5:] = 1
+    mask[1, :] = 1
+    mask[2, S - 1:] = 1
+    with torch.no_grad():
+        hs = gpt_neo.forward(spec, w, ids, mask)
+    want = pooling.weighted_mean(hs[-1], mask)
+    got = enc.encode_tokens(ids.numpy(), mask.numpy(), method="weightedmean").cpu()
+    # row 1 (unpadded) is exact-path; left-padded rows: HF lets pad positions be attended by nothing real (causal+mask),
+    # real tokens see only real tokens, so the ragged execution is still exact
+    assert min_row_cosine(got, want) > 1 - COS_TOL
+
+
+def test_config1_sgpt125m_b32_s64_vs_reference_fixture(golden_dir):
+    """BASELINE.json configs[0]: SGPT-125M-weightedmean bi-encoder, 32 synthetic sentences, seq_len 64 —
+    pooled-embedding + cosine parity vs the reference (HF GPTNeoModel fp32 + Pooling.py)."""
+    from sgpt_b200 import CorpusShard, Encoder
+
+    z = np.load(os.path.join(golden_dir, "neo_125m_b32_s64.npz"))
+    spec = _spec_from(z)
+    w = gpt_neo.init_weights(spec, seed=int(z["weight_seed"]))
+    enc = Encoder(_cfg_from_spec(spec), w, device="cuda:0", max_tokens=32 * 64, max_batch=32)
+    got = enc.encode_tokens(z["input_ids"], z["attention_mask"], method="weightedmean")
+    ref = torch.from_numpy(z["pooled_weightedmean"])
+    assert min_row_cosine(got.cpu(), ref) > 1 - COS_TOL
+    got_mean = enc.encode_tokens(z["input_ids"], z["attention_mask"], method="mean").cpu()
+    assert min_row_cosine(got_mean, z["pooled_mean"]) > 1 - COS_TOL
+    mid = int(z["mid_layer"])
+    got_mid = enc.encode_tokens(z["input_ids"], z["attention_mask"], method="weightedmean", layer_idx=mid).cpu()
+    assert min_row_cosine(got_mid, z["pooled_weightedmean_mid"]) > 1 - COS_TOL
+    # cosine parity: pairwise cos_sim of our embeddings vs of the reference embeddings
+    ours = search.cos_sim(got.cpu(), got.cpu())
+    theirs = search.cos_sim(ref, ref)
+    assert (ours - theirs).abs().max().item() < 2e-3
+    # and through the device scorer: each embedding's nearest neighbour among the 32 is itself with score ~1
+    shard = CorpusShard.from_embeddings(got, device="cuda:0")
+    s, i = shard.search(got, 1, "cos_sim")
+    assert i.view(-1).cpu().tolist() == list(range(32))
+    assert (s.view(-1).cpu() - 1).abs().max().item() < 1e-5
+    enc.close()
+
+
+def test_encode_is_batch_invariant_and_deterministic(tiny_encoder):
+    """Size-independent properties: a row's embedding does not depend on its batch mates; repeated calls are bit-equal."""
+    z, spec, w, enc = tiny_encoder
+    ids, mask = ragged_batch(40, 100, spec.vocab, seed=9)
+    a = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
+    b = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
+    assert torch.equal(a, b)
+    perm = torch.randperm(40, generator=torch.Generator().manual_seed(1))
+    c = enc.encode_tokens(ids[perm].numpy(), mask[perm].numpy()).cpu()
+    assert torch.allclose(c, a[perm], atol=1e-6)
+    solo = enc.encode_tokens(ids[7:8].numpy(), mask[7:8].numpy()).cpu()
+    assert torch.allclose(solo[0], a[7], atol=1e-6)
+
+
+def test_full_size_batch_256x128_properties():
+    """BASELINE.json configs[1] shape (SGPT-125M, batch 256, seq_len 128): finite output, permutation equivariance and
+    agreement of a few rows with the CPU oracle (full oracle run would take minutes)."""
+    from sgpt_b200 import Encoder, preset
+
+    spec = gpt_neo.NeoSpec()
+    w = gpt_neo.init_weights(spec, seed=0)
+    enc = Encoder(preset("sgpt-125m"), w, device="cuda:0", max_tokens=256 * 128, max_batch=256)
+    ids, mask = ragged_batch(256, 128, spec.vocab, seed=1235)
+    mask[2:130] = 1  # half of the rows full length
+    out = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
+    assert torch.isfinite(out).all()
+    rows = [0, 1, 2, 200]
+    with torch.no_grad():
+        hs = gpt_neo.forward(spec, w, ids[rows], mask[rows])
+    want = pooling.weighted_mean(hs[-1], mask[rows])
+    assert min_row_cosine(out[rows], want) > 1 - COS_TOL
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(2))
+    out2 = enc.encode_tokens(ids[perm].numpy(), mask[perm].numpy()).cpu()
+    assert torch.allclose(out2, out[perm], atol=1e-6)
+    enc.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _oracle_topk_on_stored(q, c, k, fn):
+    """Oracle scores on the bf16-rounded vectors the device stores, fp32 arithmetic."""
+    qs, cs = q.to(torch.bfloat16).float(), c.to(torch.bfloat16).float()
+    return search.SCORE_FUNCTIONS[fn](qs, cs)
+
+
+def _assert_same_topk(scores_dev, ids_dev, full, k, id_base=0):
+    ids_dev, scores_dev = ids_dev.cpu(), scores_dev.cpu()
+    for qi in range(full.shape[0]):
+        order = torch.argsort(-full[qi].double(), stable=True)
+        want_ids = order[:k]
+        got = ids_dev[qi] - id_base
+        cut = full[qi, want_ids[-1]].item()
+        # ids identical except among scores within 1e-6 of the cut (compared as sets)
+        safe_want = {int(j) for j in want_ids if full[qi, j].item() > cut + 1e-6}
+        got_set = {int(j) for j in got}
+        assert safe_want <= got_set, (qi, len(safe_want - got_set))
+        assert all(full[qi, j].item() >= cut - 1e-6 for j in got_set)
+        assert (scores_dev[qi] - full[qi, got]).abs().max().item() < 2e-5
+        assert torch.all(scores_dev[qi][:-1] >= scores_dev[qi][1:])  # descending
+
+
+@pytest.mark.parametrize("nq,n,D,k,fn", [(128, 20000, 768, 1001, "cos_sim"), (16, 5003, 2048, 1001, "dot"),
+                                         (1, 3000, 768, 1001, "cos_sim"), (7, 600, 64, 1001, "cos_sim")])
+def test_search_identical_topk_ids(nq, n, D, k, fn):
+    from sgpt_b200 import CorpusShard
+
+    q, c = planted_corpus(n, D, nq, seed=4321)
+    shard = CorpusShard.from_embeddings(c.cuda(), device="cuda:0", id_base=1000)
+    s, i = shard.search(q.cuda(), k, fn)
+    full = _oracle_topk_on_stored(q, c, k, fn)
+    kk = min(k, n)
+    _assert_same_topk(s[:, :kk], i[:, :kk], full, kk, id_base=1000)
+    if n < k:
+        assert torch.all(i[:, n:] == -1) and torch.all(torch.isinf(s[:, n:]))
+
+
+def test_search_nan_scores_become_minus_one():
+    """XS:99: cos_scores[isnan] = -1."""
+    from sgpt_b200 import CorpusShard
+
+    q, c = planted_corpus(500, 64, 4, seed=1)
+    c[17] = float("nan")
+    shard = CorpusShard.from_embeddings(c.cuda(), device="cuda:0")
+    s, i = shard.search(q.cuda(), 500, "cos_sim")
+    pos = (i[0] == 17).nonzero().item()
+    assert s[0, pos].item() == -1.0
+
+
+def test_dres_search_matches_oracle_search_loop(tiny_encoder):
+    """End to end through the reference's plug-in surface: CustomEmbedder(specb) + DenseRetrievalExactSearch with chunked
+    corpus (3 chunks) vs the oracle's restatement of XS:80-134 run on the device-produced embeddings."""
+    from sgpt_b200 import CustomEmbedder, DenseRetrievalExactSearch
+
+    z, spec, w, _ = tiny_encoder
+    tok = ToyTokenizer(vocab=spec.vocab)
+    emb = CustomEmbedder("toy-gpt-neo", batch_size=16, device="cuda:0", method="weightedmean", specb=True, maxseqlen=40,
+                         config=_cfg_from_spec(spec), state_dict=w, tokenizer=tok)
+    rs = np.random.RandomState(0)
+    words = [f"w{i}" for i in range(300)]
+    corpus = {f"d{i}": {"title": " ".join(rs.choice(words, 3)), "text": " ".join(rs.choice(words, rs.randint(1, 60)))}
+              for i in range(130)}
+    queries = {f"q{i}": " ".join(rs.choice(words, rs.randint(1, 12))) for i in range(9)}
+    queries["d5"] = corpus["d5"]["text"]  # a query that IS a corpus doc id -> self match must be dropped (XS:118)
+    dres = DenseRetrievalExactSearch(emb, batch_size=16, corpus_chunk_size=50)
+    top_k = 20
+    res = dres.search(corpus, queries, top_k, "cos_sim")
+    # oracle loop on the same embeddings and the same (length-sorted) corpus order
+    corpus_ids = sorted(corpus, key=lambda k: len(corpus[k].get("title", "") + corpus[k].get("text", "")), reverse=True)
+    q_emb = emb.encode_queries([(qid, queries[qid]) for qid in queries], convert_to_tensor=True)
+    c_emb = emb.encode_corpus([(cid, corpus[cid]) for cid in corpus_ids], convert_to_tensor=True)
+    want = search.search_embeddings(list(queries), q_emb.cpu().to(torch.bfloat16).float(), corpus_ids,
+                                    c_emb.cpu().to(torch.bfloat16).float(), top_k, "cos_sim", corpus_chunk_size=50)
+    assert set(res) == set(want)
+    for qid in queries:
+        assert "d5" not in res["d5"]
+        got_sorted = sorted(res[qid], key=res[qid].get, reverse=True)
+        want_sorted = sorted(want[qid], key=want[qid].get, reverse=True)
+        assert len(res[qid]) == len(want[qid]) <= top_k + 1
+        assert got_sorted == want_sorted, qid
+        assert max(abs(res[qid][c] - want[qid][c]) for c in want[qid]) < 2e-5
+    with pytest.raises(ValueError):
+        dres.search(corpus, queries, top_k, "euclid")
+
+
+def test_sentence_encoder_encode_signature(tiny_encoder):
+    """ST-path surface: encode() sorts by length internally but returns rows in input order; str in -> 1-D out;
+    specb markers are replaced by brackets (models/Transformer.py:131-153)."""
+    from sgpt_b200 import SentenceBERTBOSEOS, SentenceEncoder
+
+    z, spec, w, _ = tiny_encoder
+    tok = ToyTokenizer(vocab=spec.vocab)
+    st = SentenceEncoder(_cfg_from_spec(spec), w, tok, device="cuda:0", max_seq_length=32, batch_capacity=8)
+    sents = ["a b c d e f", "x", "hello world this is a test", "q r"]
+    e = st.encode(sents, batch_size=2)
+    assert isinstance(e, np.ndarray) and e.shape == (4, spec.d_model)
+    one = st.encode("x")
+    assert one.shape == (spec.d_model,) and np.allclose(one, e[1], atol=1e-6)
+    t = st.encode(sents, batch_size=8, convert_to_tensor=True, normalize_embeddings=True)
+    assert t.is_cuda and torch.allclose(t.norm(dim=1), torch.ones(4, device=t.device), atol=1e-5)
+    wrapped = SentenceBERTBOSEOS(st, specb=True)
+    ids, mask = st.tokenize(["[SOS]" + "a b", "{SOS}" + "c"])
+    assert ids[0, 0] == 58 and ids[0, 3] == 60 and ids[1, 0] == 90 and ids[1, 2] == 92
+    qe = wrapped.encode_queries(["a b"], batch_size=4)
+    de = wrapped.encode_corpus([{"title": "a", "text": "b"}], batch_size=4)
+    assert qe.shape == de.shape == (1, spec.d_model) and not np.allclose(qe, de)
+    st.encoder.close()
