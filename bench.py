@@ -258,6 +258,9 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up -----------------------------------------------------------------------------------------------
+    # nvidia-smi needs ~0.5 s to produce its first sample: start it before the warm-up; samples cover warm-up + both
+    # timed loops (all of them run the same kernels back to back)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for w_ in range(max(args.warmup, 1)):
         r = resident[w_ % len(resident)]
         enc.encode_packed(r[0], r[1], r[2], B, B * S, S)
@@ -273,7 +276,6 @@ def run_b200(args, rank, world, local_rank):
     tot_n1 = (ctypes.c_int64 * 8)()
     lib.sgpt_profile_read(None, None, tot_n0)
     lib.sgpt_profile_enable(1)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -285,7 +287,6 @@ def run_b200(args, rank, world, local_rank):
         ev[k][2].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if sampler else None
     lib.sgpt_profile_enable(0)
     lib.sgpt_profile_read(prof_ms, prof_n, tot_n1)
     enc_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
@@ -316,6 +317,7 @@ def run_b200(args, rank, world, local_rank):
         enc.encode_tokens(batches[k % 4].numpy(), mask).cpu()
     barrier()
     e2e_enc_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
 
     def maxr(x):
         if world == 1:
@@ -377,7 +379,7 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
     const float alpha = exp2f(m_run - m_use);
     float lsum = 0.f;
+    // The P buffer (and O) still belong to the previous tile's P V MMA until it has completed.
+    if (j > j_lo) {
+      mbar_wait(bar_o, ph ^ 1u);
+      tc_fence_after();
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
@@ -182,11 +188,8 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     l_run = l_run * alpha + lsum;
     m_run = m_new;
 
-    // ---- O = alpha * O (needs the previous P V MMA to have landed) ----
+    // ---- O = alpha * O (the previous P V MMA has landed: waited for above) ----
     if (j > j_lo) {
-      mbar_wait(bar_o, ph ^ 1u);
-      tc_fence_after();
-      __syncwarp();
 #pragma unroll 1
       for (int c = 0; c < HD / 32; ++c) {
         uint32_t v[32];

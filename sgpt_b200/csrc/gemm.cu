@@ -1,15 +1,17 @@
-// Host launchers for the tcgen05 GEMM (gemm.cuh): nn.Linear with fused epilogues (F3/F5/F6) and the
-// query x corpus similarity (S1).
+// Host launchers for the tcgen05 GEMM (gemm.cuh): nn.Linear with fused epilogues (F3/F5/F6), the query x corpus
+// similarity (S1) and its threshold-filter variant used by the fused search (search.cu).
 #include "gemm.cuh"
 
 #include "../../include/sgpt_b200.h"
+#include "gemm_api.h"
 #include "host_utils.h"
 
 namespace sgpt {
 
 template <int BN, class Epi>
 static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K,
-                       const typename Epi::Params& ep, cudaStream_t stream, int cat = kCatGemm) {
+                       const typename Epi::Params& ep, cudaStream_t stream, int cat = kCatGemm,
+                       TileMap tmap = TileMap()) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
   int rc = make_tma_2d_bf16(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
@@ -25,12 +27,13 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
     attr_set = true;
   }
   const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
-  const int n_tiles = (N + BN - 1) / BN;
+  const int n_tiles = tmap.count((N + BN - 1) / BN);
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  if (tiles == 0) return SGPT_OK;
   int grid = sm_count();
   if (tiles < grid) grid = static_cast<int>(tiles);
   LaunchScope _ls(cat, stream);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep, tmap);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }
@@ -47,6 +50,16 @@ static int pick_bn(int M, int N) {
     return useful / (static_cast<double>(waves) * sms * kGemmBM * bn);
   };
   return (eff(256) * 1.08 >= eff(128)) ? 256 : 128;
+}
+
+int launch_filter_candidates(const void* Q, const void* C, const float* q_scale, const float* c_scale,
+                             const float* tau, uint2* cand, int* count, long long cap, int nq, int n, int D,
+                             int tile_mode, int tile_stride, cudaStream_t stream) {
+  OpFilterCandidates::Params p{q_scale, c_scale, tau, cand, count, cap};
+  TileMap tm;
+  tm.mode = tile_mode;
+  tm.stride = tile_stride;
+  return launch_gemm<kSimBN, EpiFilterCandidates>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
 }
 
 }  // namespace sgpt
@@ -98,5 +111,5 @@ extern "C" int sgpt_scores(const void* Q, const void* C, const float* q_scale, c
   if (nq == 0 || n == 0) return SGPT_OK;
   EpiScoresF32::Params p{scores, q_scale, c_scale, static_cast<long long>(lds)};
   // lanes = queries (A operand), columns = corpus rows (B operand, streamed once from HBM)
-  return launch_gemm<256, EpiScoresF32>(Q, D, C, D, nq, static_cast<int>(n), D, p, stream, kCatScores);
+  return launch_gemm<kSimBN, EpiScoresF32>(Q, D, C, D, nq, static_cast<int>(n), D, p, stream, kCatScores);
 }

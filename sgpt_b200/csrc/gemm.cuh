@@ -7,17 +7,16 @@
 //   warp 0      TMA producer   (one elected lane; kStages-deep smem ring of {A 128x64, B BNx64} bf16 tiles, SW128)
 //   warp 1      MMA issuer     (one elected lane; tcgen05.mma M=128, N=BN, K=16; 2 TMEM accumulator stages)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       (tcgen05.ld 32 lanes x 32 columns per warp-instruction; functor `Epi` consumes them)
+//   warps 4..7  epilogue       (tcgen05.ld -> per-warp smem transpose -> coalesced global access)
 //
 // The accumulator is double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs; smem stages and TMEM
 // stages are handed over with mbarriers only (no __syncthreads in the main loop).
 //
-// `Epi` contract:
-//   struct Epi { struct Params{...}; struct State{...};
-//     static __device__ void init(State&, const Params&, int row_in_tile_lane);
-//     static __device__ void tile(State&, const Params&, int m0, int n0, int row, uint32_t tmem_row_addr,
-//                                 int M, int N);   // called per output tile; reads BN columns via tmem_ld_32x32
-//     static __device__ void finish(State&, const Params&, int lane_row); }
+// Epilogue data path.  tcgen05.ld hands thread r of a warp row r of the tile (32 consecutive columns per load), so a
+// direct global store would touch 32 different rows per instruction.  Each epilogue warp therefore owns a
+// [32 rows][64 cols] fp32 staging slab in smem (row pitch 66 floats: conflict-free 8-byte accesses both ways): it
+// writes its rows, then re-reads the slab row by row with lane l holding columns 2l, 2l+1 — every global load/store
+// of a warp is one contiguous 128-B (bf16) or 256-B (fp32) row segment.  `Op` supplies the per-element arithmetic.
 #pragma once
 #include "common.cuh"
 
@@ -26,6 +25,8 @@ namespace sgpt {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 256;
+constexpr int kStagePitch = 66;                                  // floats per staged row (64 + 2 pad)
+constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;         // 8448
 
 template <int BN>
 struct GemmCfg {
@@ -34,21 +35,41 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512 (power of two)
-  // smem: [<=1024 align slack][stages * (A|B)][barriers + tmem holder]
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+  // smem: [<=1024 align slack][stages * (A|B)][4 epilogue staging slabs][barriers + tmem holder]
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 4 * kStageBytesPerWarp + 256;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+};
+
+// Optional selection of N-tiles: the similarity search scans a strided sample of corpus tiles first (to establish
+// per-query thresholds) and the remaining tiles afterwards.
+//   mode 0: all tiles;  mode 1: tiles 0, s, 2s, ...;  mode 2: every tile that is NOT a multiple of s   (s >= 2)
+struct TileMap {
+  int mode = 0;
+  int stride = 1;
+  __host__ __device__ int count(int n_tiles) const {
+    if (mode == 0) return n_tiles;
+    const int sampled = (n_tiles + stride - 1) / stride;
+    return mode == 1 ? sampled : n_tiles - sampled;
+  }
+  __host__ __device__ int map(int j) const {
+    if (mode == 0) return j;
+    if (mode == 1) return j * stride;
+    return j + j / (stride - 1) + 1;
+  }
 };
 
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
-                    int N, int K, typename Epi::Params ep) {
+                    int N, int K, typename Epi::Params ep, TileMap tmap) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  float* stage_base = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + 4 * kStageBytesPerWarp);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -58,7 +79,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int lane = threadIdx.x & 31;
 
   const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
-  const int n_tiles = (N + BN - 1) / BN;
+  const int n_tiles = tmap.count((N + BN - 1) / BN);  // N-tiles this launch visits
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + kGemmBK - 1) / kGemmBK;
 
@@ -93,7 +114,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * kGemmBM;
-        const int n0 = (tile % n_tiles) * BN;
+        const int n0 = tmap.map(tile % n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_tiles + stage * Cfg::kStageBytes;
@@ -138,25 +159,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;               // == warp % 4 -> TMEM lane quarter this warp may access
-    const int row_in_tile = ew * 32 + lane;
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may access
+    float* stage_slab = stage_base + ew * (kStageBytesPerWarp / 4);
     typename Epi::State st;
-    Epi::init(st, ep, row_in_tile);
+    Epi::init(st, ep, ew * 32 + lane);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * kGemmBM;
-      const int n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * kGemmBM + ew * 32;  // first row of this warp's 32-row slab
+      const int n0 = tmap.map(tile % n_tiles) * BN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
-      Epi::template tile<BN>(st, ep, m0, n0, row_in_tile, trow, M, N);
+      Epi::template tile<BN>(st, ep, m0, n0, lane, trow, stage_slab, M, N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    Epi::finish(st, ep, row_in_tile);
+    Epi::finish(st, ep, ew * 32 + lane);
   }
 
   tc_fence_before();
@@ -168,171 +189,279 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Epilogues
+// Staged epilogue driver: TMEM -> registers (thread = row) -> smem slab -> (lane = column pair) -> Op::rows()
 // ---------------------------------------------------------------------------------------------------------------
 struct EpiNoState {};
 
+template <class Op>
+struct EpiStaged {
+  using Params = typename Op::Params;
+  using State = EpiNoState;
+  static __device__ __forceinline__ void init(State&, const Params&, int) {}
+  static __device__ __forceinline__ void finish(State&, const Params&, int) {}
+
+  template <int BN>
+  static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int lane, uint32_t trow,
+                                              float* slab, int M, int N) {
+    const int rows = min(32, M - m0);  // warp-uniform; <= 0 when the whole slab is out of range
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 64) {
+      const int n = n0 + c;
+      if (n >= N) break;  // warp-uniform
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(trow + c, v0);
+      if (n + 32 < N) {
+        tmem_ld_32x32(trow + c + 32, v1);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v1[i] = 0u;
+      }
+      tmem_ld_wait();
+      __syncwarp();  // the previous slab's readers are done
+      float2* srow = reinterpret_cast<float2*>(slab + lane * kStagePitch);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) srow[i] = make_float2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        srow[16 + i] = make_float2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+      __syncwarp();
+      if (rows > 0) Op::rows(p, slab, m0, rows, n + 2 * lane, N, lane);
+    }
+  }
+};
+
+__device__ __forceinline__ float2 slab_read(const float* slab, int r, int lane) {
+  return *reinterpret_cast<const float2*>(slab + r * kStagePitch + 2 * lane);
+}
+
 // out_bf16[m, n] = act(acc + bias[n])          act = identity | gelu_new
 template <bool kGelu>
-struct EpiBiasActBF16 {
+struct OpBiasActBF16 {
   struct Params {
     __nv_bfloat16* out;
     const float* bias;  // may be null
     int ldc;
   };
-  using State = EpiNoState;
-  static __device__ __forceinline__ void init(State&, const Params&, int) {}
-  static __device__ __forceinline__ void finish(State&, const Params&, int) {}
-  template <int BN>
-  static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int row, uint32_t trow,
-                                              int M, int N) {
-    const int m = m0 + row;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      const int n = n0 + c;
-      if (n >= N) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld_32x32(trow + c, v);
-      tmem_ld_wait();
-      if (m < M) {
-        __nv_bfloat16* dst = p.out + static_cast<size_t>(m) * p.ldc + n;
-        if (n + 32 <= N) {
-          uint32_t o[16];
+  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
+                                              int lane) {
+    const bool ok0 = col < N, ok1 = col + 1 < N;
+    float b0 = 0.f, b1 = 0.f;
+    if (p.bias) {
+      if (ok0) b0 = __ldg(p.bias + col);
+      if (ok1) b1 = __ldg(p.bias + col + 1);
+    }
+    __nv_bfloat16* dst = p.out + static_cast<size_t>(m0) * p.ldc + col;
+    // Rows in batches of 8: all smem reads of a batch are issued before its global stores (the compiler cannot prove
+    // the slab and the output do not alias, so without explicit batching every iteration would serialise on LDS latency).
+    int r = 0;
+    for (; r + 8 <= rows; r += 8) {
+      float2 a[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-            if (p.bias) { a += __ldg(p.bias + n + 2 * j); b += __ldg(p.bias + n + 2 * j + 1); }
-            if (kGelu) { a = gelu_new(a); b = gelu_new(b); }
-            o[j] = pack_bf16(a, b);
-          }
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (int u = 0; u < 8; ++u) a[u] = slab_read(slab, r + u, lane);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n + j < N) {
-              float a = __uint_as_float(v[j]);
-              if (p.bias) a += __ldg(p.bias + n + j);
-              if (kGelu) a = gelu_new(a);
-              dst[j] = __float2bfloat16_rn(a);
-            }
-          }
-        }
+      for (int u = 0; u < 8; ++u) {
+        float x = a[u].x + b0, y = a[u].y + b1;
+        if (kGelu) { x = gelu_new(x); y = gelu_new(y); }
+        if (ok1) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(x, y);
+        else if (ok0) *dst = __float2bfloat16_rn(x);
+        dst += p.ldc;
       }
+    }
+    for (; r < rows; ++r) {
+      const float2 a = slab_read(slab, r, lane);
+      float x = a.x + b0, y = a.y + b1;
+      if (kGelu) { x = gelu_new(x); y = gelu_new(y); }
+      if (ok1) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(x, y);
+      else if (ok0) *dst = __float2bfloat16_rn(x);
+      dst += p.ldc;
     }
   }
 };
 
 // resid_f32[m, n] = resid_in[m, n] + acc + bias[n]      (fp32 residual stream; in-place allowed)
-struct EpiResidualF32 {
+struct OpResidualF32 {
   struct Params {
     float* out;
     const float* resid;  // may alias out
     const float* bias;   // may be null
     int ldc;
   };
-  using State = EpiNoState;
-  static __device__ __forceinline__ void init(State&, const Params&, int) {}
-  static __device__ __forceinline__ void finish(State&, const Params&, int) {}
-  template <int BN>
-  static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int row, uint32_t trow,
-                                              int M, int N) {
-    const int m = m0 + row;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      const int n = n0 + c;
-      if (n >= N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(trow + c, v);
-      tmem_ld_wait();
-      if (m < M) {
-        const size_t off = static_cast<size_t>(m) * p.ldc + n;
-        if (n + 32 <= N) {
-          const float4* r4 = reinterpret_cast<const float4*>(p.resid + off);
-          float4* o4 = reinterpret_cast<float4*>(p.out + off);
+  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
+                                              int lane) {
+    const bool ok0 = col < N, ok1 = col + 1 < N;
+    float b0 = 0.f, b1 = 0.f;
+    if (p.bias) {
+      if (ok0) b0 = __ldg(p.bias + col);
+      if (ok1) b1 = __ldg(p.bias + col + 1);
+    }
+    const size_t base = static_cast<size_t>(m0) * p.ldc + col;
+    int r = 0;
+    if (ok1) {
+      // 16 rows per batch: issue all residual (global) and accumulator (smem) loads first, then combine and store —
+      // one exposed global-load latency per 16 rows instead of per row
+      for (; r + 16 <= rows; r += 16) {
+        float2 g[16], a[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 r = r4[j];
-            float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
-              b0 = b.x; b1 = b.y; b2 = b.z; b3 = b.w;
-            }
-            r.x += __uint_as_float(v[4 * j + 0]) + b0;
-            r.y += __uint_as_float(v[4 * j + 1]) + b1;
-            r.z += __uint_as_float(v[4 * j + 2]) + b2;
-            r.w += __uint_as_float(v[4 * j + 3]) + b3;
-            o4[j] = r;
-          }
-        } else {
+        for (int u = 0; u < 16; ++u)
+          g[u] = *reinterpret_cast<const float2*>(p.resid + base + static_cast<size_t>(r + u) * p.ldc);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n + j < N) {
-              float a = __uint_as_float(v[j]) + p.resid[off + j];
-              if (p.bias) a += __ldg(p.bias + n + j);
-              p.out[off + j] = a;
-            }
-          }
+        for (int u = 0; u < 16; ++u) a[u] = slab_read(slab, r + u, lane);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          g[u].x += a[u].x + b0;
+          g[u].y += a[u].y + b1;
+          *reinterpret_cast<float2*>(p.out + base + static_cast<size_t>(r + u) * p.ldc) = g[u];
         }
       }
+    }
+    for (; r < rows; ++r) {
+      const float2 a = slab_read(slab, r, lane);
+      const size_t off = base + static_cast<size_t>(r) * p.ldc;
+      // same association as the batched path (resid + (acc + bias)): a row's result must not depend on where it
+      // falls relative to the 16-row batches
+      if (ok0) p.out[off] = p.resid[off] + (a.x + b0);
+      if (ok1) p.out[off + 1] = p.resid[off + 1] + (a.y + b1);
     }
   }
 };
 
 // scores_f32[q, doc] = fixnan(acc * row_scale[q] * col_scale[doc])       (cos_sim / dot_score, NaN -> -1)
-struct EpiScoresF32 {
+struct OpScoresF32 {
   struct Params {
     float* out;
     const float* row_scale;  // per query  (1/||q|| for cos_sim; null = 1)
     const float* col_scale;  // per doc    (1/||d|| for cos_sim; null = 1)
     long long ldc;
   };
-  using State = EpiNoState;
-  static __device__ __forceinline__ void init(State&, const Params&, int) {}
-  static __device__ __forceinline__ void finish(State&, const Params&, int) {}
-  template <int BN>
-  static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int row, uint32_t trow,
-                                              int M, int N) {
-    const int m = m0 + row;
-    const float rs = (p.row_scale && m < M) ? __ldg(p.row_scale + m) : 1.0f;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      const int n = n0 + c;
-      if (n >= N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(trow + c, v);
-      tmem_ld_wait();
-      if (m < M) {
-        float* dst = p.out + static_cast<size_t>(m) * p.ldc + n;
-        if (n + 32 <= N && (p.ldc & 3) == 0) {
+  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
+                                              int lane) {
+    const bool ok0 = col < N, ok1 = col + 1 < N;
+    float c0 = 1.f, c1 = 1.f;
+    if (p.col_scale) {
+      if (ok0) c0 = __ldg(p.col_scale + col);
+      if (ok1) c1 = __ldg(p.col_scale + col + 1);
+    }
+    const bool vec = ok1 && ((p.ldc & 1) == 0);
+    float* dst = p.out + static_cast<size_t>(m0) * p.ldc + col;
+    float my_rs = 1.f;  // lane r keeps row m0 + r's scale; broadcast per row with a shuffle
+    if (p.row_scale && lane < rows) my_rs = __ldg(p.row_scale + m0 + lane);
+    int r = 0;
+    for (; r + 8 <= rows; r += 8) {
+      float2 a[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.col_scale) cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n) + j);
-            float4 s;
-            s.x = __uint_as_float(v[4 * j + 0]) * rs * cs.x;
-            s.y = __uint_as_float(v[4 * j + 1]) * rs * cs.y;
-            s.z = __uint_as_float(v[4 * j + 2]) * rs * cs.z;
-            s.w = __uint_as_float(v[4 * j + 3]) * rs * cs.w;
-            s.x = (s.x != s.x) ? -1.f : s.x;
-            s.y = (s.y != s.y) ? -1.f : s.y;
-            s.z = (s.z != s.z) ? -1.f : s.z;
-            s.w = (s.w != s.w) ? -1.f : s.w;
-            reinterpret_cast<float4*>(dst)[j] = s;
-          }
-        } else {
+      for (int u = 0; u < 8; ++u) a[u] = slab_read(slab, r + u, lane);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n + j < N) {
-              float s = __uint_as_float(v[j]) * rs * (p.col_scale ? __ldg(p.col_scale + n + j) : 1.f);
-              dst[j] = (s != s) ? -1.f : s;
-            }
-          }
+      for (int u = 0; u < 8; ++u) {
+        const float rs = __shfl_sync(0xffffffffu, my_rs, r + u);
+        float x = a[u].x * rs * c0, y = a[u].y * rs * c1;
+        x = (x != x) ? -1.f : x;
+        y = (y != y) ? -1.f : y;
+        if (vec) *reinterpret_cast<float2*>(dst) = make_float2(x, y);
+        else {
+          if (ok0) dst[0] = x;
+          if (ok1) dst[1] = y;
         }
+        dst += p.ldc;
+      }
+    }
+    for (; r < rows; ++r) {
+      const float rs = __shfl_sync(0xffffffffu, my_rs, r);
+      const float2 a = slab_read(slab, r, lane);
+      float x = a.x * rs * c0, y = a.y * rs * c1;
+      x = (x != x) ? -1.f : x;
+      y = (y != y) ? -1.f : y;
+      if (vec) *reinterpret_cast<float2*>(dst) = make_float2(x, y);
+      else {
+        if (ok0) dst[0] = x;
+        if (ok1) dst[1] = y;
+      }
+      dst += p.ldc;
+    }
+  }
+};
+
+// Threshold filter: score = fixnan(acc * row_scale[q] * col_scale[doc]); every score > tau[q] is appended as a packed
+// (score bits, local doc index) pair to the query's candidate list.  One warp-aggregated atomicAdd per (query row,
+// 64-column slab); the score matrix itself is never written to HBM.
+struct OpFilterCandidates {
+  struct Params {
+    const float* row_scale;  // per query or null
+    const float* col_scale;  // per doc or null
+    const float* tau;        // per query threshold; null = accept everything (sampling pass)
+    uint2* cand;             // [nq, cap]
+    int* count;              // [nq]
+    long long cap;
+  };
+  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
+                                              int lane) {
+    const bool ok0 = col < N, ok1 = col + 1 < N;
+    float c0 = 1.f, c1 = 1.f;
+    if (p.col_scale) {
+      if (ok0) c0 = __ldg(p.col_scale + col);
+      if (ok1) c1 = __ldg(p.col_scale + col + 1);
+    }
+    // lane r keeps the scale/threshold of row m0 + r; broadcast per row with a shuffle
+    float my_rs = 1.f, my_tau = -INFINITY;
+    if (lane < rows) {
+      if (p.row_scale) my_rs = __ldg(p.row_scale + m0 + lane);
+      if (p.tau) my_tau = __ldg(p.tau + m0 + lane);
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    // Phase 1: hit counts of all rows of the slab; lane r ends up owning row r's count.
+    int my_total = 0;
+    for (int rb = 0; rb < rows; rb += 8) {
+      float2 ab[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ab[u] = (rb + u < rows) ? slab_read(slab, rb + u, lane) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = rb + u;
+        const float rs = __shfl_sync(0xffffffffu, my_rs, r & 31);
+        const float t = __shfl_sync(0xffffffffu, my_tau, r & 31);
+        float x = ab[u].x * rs * c0, y = ab[u].y * rs * c1;
+        x = (x != x) ? -1.f : x;
+        y = (y != y) ? -1.f : y;
+        const bool in = r < rows;
+        const unsigned b0 = __ballot_sync(0xffffffffu, in && ok0 && (x > t));
+        const unsigned b1 = __ballot_sync(0xffffffffu, in && ok1 && (y > t));
+        if (lane == r) my_total = __popc(b0) + __popc(b1);
+      }
+    }
+    if (__ballot_sync(0xffffffffu, my_total != 0) == 0u) return;  // nothing admitted in this slab (warp-uniform)
+    // ONE atomic instruction reserves space in all the slab's query lists (32 different addresses): a single global
+    // round trip per slab instead of one per row.
+    int my_base = 0;
+    if (my_total != 0) my_base = atomicAdd(p.count + m0 + lane, my_total);
+    // Phase 2: rows with hits recompute their scores (smem re-read) and write (score, doc) pairs.
+    for (int r = 0; r < rows; ++r) {
+      const int total = __shfl_sync(0xffffffffu, my_total, r);
+      if (total == 0) continue;  // warp-uniform
+      const int base = __shfl_sync(0xffffffffu, my_base, r);
+      const float rs = __shfl_sync(0xffffffffu, my_rs, r);
+      const float t = __shfl_sync(0xffffffffu, my_tau, r);
+      const float2 a = slab_read(slab, r, lane);
+      float x = a.x * rs * c0, y = a.y * rs * c1;
+      x = (x != x) ? -1.f : x;
+      y = (y != y) ? -1.f : y;
+      const bool h0 = ok0 && (x > t), h1 = ok1 && (y > t);
+      const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+      uint2* dst = p.cand + static_cast<long long>(m0 + r) * p.cap;
+      if (h0) {
+        const long long s = base + __popc(b0 & lt);
+        if (s < p.cap) dst[s] = make_uint2(__float_as_uint(x), static_cast<uint32_t>(col));
+      }
+      if (h1) {
+        const long long s = base + __popc(b0) + __popc(b1 & lt);
+        if (s < p.cap) dst[s] = make_uint2(__float_as_uint(y), static_cast<uint32_t>(col + 1));
       }
     }
   }
 };
+using EpiFilterCandidates = EpiStaged<OpFilterCandidates>;
+
+template <bool kGelu>
+using EpiBiasActBF16 = EpiStaged<OpBiasActBF16<kGelu>>;
+using EpiResidualF32 = EpiStaged<OpResidualF32>;
+using EpiScoresF32 = EpiStaged<OpScoresF32>;
 
 }  // namespace sgpt

@@ -61,7 +61,7 @@ constexpr int kBins = 2048;
 // sorted[] / sorted_id[]: KP (power of two >= k) slots in dynamic smem
 __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, int k, int KP,
                                                                    float* __restrict__ out_scores,
-                                                                   long long* __restrict__ out_ids) {
+                                                                   long long* __restrict__ out_ids, TopkExtra extra) {
   extern __shared__ uint8_t dsm[];
   uint32_t* skey = reinterpret_cast<uint32_t*>(dsm);
   long long* sid = reinterpret_cast<long long*>(dsm + static_cast<size_t>(KP) * 4);
@@ -193,14 +193,27 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
       __syncthreads();
     }
   }
-  for (int i = tid; i < k; i += kTopkThreads) {
-    const uint32_t key = skey[i];
-    out_scores[static_cast<size_t>(q) * k + i] = key ? key_score(key) : -INFINITY;
-    out_ids[static_cast<size_t>(q) * k + i] = key ? sid[i] : -1;
+  if (out_scores != nullptr) {
+    for (int i = tid; i < k; i += kTopkThreads) {
+      const uint32_t key = skey[i];
+      out_scores[static_cast<size_t>(q) * k + i] = key ? key_score(key) : -INFINITY;
+      out_ids[static_cast<size_t>(q) * k + i] = key ? sid[i] : -1;
+    }
   }
+  // optional side outputs for the two-pass search: winners re-packed as the head of another candidate list, and the
+  // k-th best score as that query's admission threshold
+  if (extra.packed != nullptr) {
+    for (int i = tid; i < static_cast<int>(kk); i += kTopkThreads)
+      extra.packed[static_cast<long long>(q) * extra.cap + i] =
+          make_uint2(__float_as_uint(key_score(skey[i])), static_cast<uint32_t>(sid[i] - src.id_base));
+    if (tid == 0) extra.count[q] = static_cast<int>(kk);
+  }
+  if (extra.tau != nullptr && tid == 0)
+    extra.tau[q] = (kk >= static_cast<uint32_t>(k)) ? key_score(skey[k - 1]) : -INFINITY;
 }
 
-int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream) {
+int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
+                       const TopkExtra& extra) {
   if (k <= 0 || k > 4096) {
     set_error("top-k: k=%d outside [1, 4096]", k);
     return SGPT_ERR_INVALID;
@@ -214,7 +227,8 @@ int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int
     attr_set = true;
   }
   LaunchScope _ls(kCatTopk, stream);
-  topk_select_kernel<<<nq, kTopkThreads, dsm, stream>>>(src, k, KP, out_scores, reinterpret_cast<long long*>(out_ids));
+  topk_select_kernel<<<nq, kTopkThreads, dsm, stream>>>(src, k, KP, out_scores, reinterpret_cast<long long*>(out_ids),
+                                                        extra);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }

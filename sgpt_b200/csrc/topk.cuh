@@ -18,6 +18,17 @@ struct TopkSrc {
   long long stride_g = 0, stride_q = 0;
 };
 
-int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream);
+// Optional side outputs of a selection (two-pass search): the winners re-packed as the head of a candidate list
+// (local index = id - src.id_base) with its count, and the k-th best score as the query's admission threshold.
+struct TopkExtra {
+  uint2* packed = nullptr;  // [nq, cap]
+  int* count = nullptr;     // [nq]
+  long long cap = 0;
+  float* tau = nullptr;     // [nq]
+};
+
+// out_scores / out_ids may be null when only the side outputs are wanted.
+int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
+                       const TopkExtra& extra = TopkExtra());
 
 }  // namespace sgpt

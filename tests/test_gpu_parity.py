@@ -163,7 +163,9 @@ def test_full_size_batch_256x128_properties():
     assert min_row_cosine(out[rows], want) > 1 - COS_TOL
     perm = torch.randperm(256, generator=torch.Generator().manual_seed(2))
     out2 = enc.encode_tokens(ids[perm].numpy(), mask[perm].numpy()).cpu()
-    assert torch.allclose(out2, out[perm], atol=1e-6)
+    again = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
+    assert torch.equal(again, out), f"non-deterministic: max diff {(again - out).abs().max().item():.3e}"
+    assert torch.allclose(out2, out[perm], atol=1e-6), f"batch-order dependent: {(out2 - out[perm]).abs().max().item():.3e}"
     enc.close()
 
 
@@ -181,12 +183,13 @@ def _assert_same_topk(scores_dev, ids_dev, full, k, id_base=0):
         want_ids = order[:k]
         got = ids_dev[qi] - id_base
         cut = full[qi, want_ids[-1]].item()
-        # ids identical except among scores within 1e-6 of the cut (compared as sets)
-        safe_want = {int(j) for j in want_ids if full[qi, j].item() > cut + 1e-6}
+        # ids identical except among scores within 1e-6 (relative to the score scale) of the cut, compared as sets
+        tol = 1e-6 * max(1.0, full[qi].abs().max().item())  # fp32 accumulation-order noise scales with |score| (dot)
+        safe_want = {int(j) for j in want_ids if full[qi, j].item() > cut + 2 * tol}
         got_set = {int(j) for j in got}
         assert safe_want <= got_set, (qi, len(safe_want - got_set))
-        assert all(full[qi, j].item() >= cut - 1e-6 for j in got_set)
-        assert (scores_dev[qi] - full[qi, got]).abs().max().item() < 2e-5
+        assert all(full[qi, j].item() >= cut - 2 * tol for j in got_set)
+        assert (scores_dev[qi] - full[qi, got]).abs().max().item() < 20 * tol
         assert torch.all(scores_dev[qi][:-1] >= scores_dev[qi][1:])  # descending
 
 
