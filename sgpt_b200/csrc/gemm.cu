@@ -76,22 +76,37 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
   if (M == 0) return SGPT_OK;
   const int bn = pick_bn(M, N);
   switch (epilogue) {
-    case SGPT_EPI_BF16: {
-      SGPT_REQUIRE(ldo % 8 == 0, "sgpt_linear: ldo must be a multiple of 8 for bf16 output");
-      EpiBiasActBF16<false>::Params p{static_cast<__nv_bfloat16*>(out), bias, static_cast<int>(ldo)};
-      return bn == 256 ? launch_gemm<256, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream)
-                       : launch_gemm<128, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream);
-    }
+    case SGPT_EPI_BF16:
     case SGPT_EPI_GELU_BF16: {
       SGPT_REQUIRE(ldo % 8 == 0, "sgpt_linear: ldo must be a multiple of 8 for bf16 output");
-      EpiBiasActBF16<true>::Params p{static_cast<__nv_bfloat16*>(out), bias, static_cast<int>(ldo)};
+      // output boxes of 32 rows x 64 bf16 (one 128-byte row segment per row), written by the epilogue through TMA
+      CUtensorMap om;
+      int rc = make_tma_2d_bf16(&om, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N),
+                                static_cast<uint64_t>(ldo), 32, 64);
+      if (rc != SGPT_OK) return rc;
+      if (epilogue == SGPT_EPI_BF16) {
+        EpiBiasActBF16<false>::Params p{om, bias};
+        return bn == 256 ? launch_gemm<256, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream)
+                         : launch_gemm<128, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream);
+      }
+      EpiBiasActBF16<true>::Params p{om, bias};
       return bn == 256 ? launch_gemm<256, EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, stream)
                        : launch_gemm<128, EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, stream);
     }
     case SGPT_EPI_RESID_F32: {
       SGPT_REQUIRE(resid != nullptr, "sgpt_linear: SGPT_EPI_RESID_F32 needs resid");
       SGPT_REQUIRE(ldo % 4 == 0, "sgpt_linear: ldo must be a multiple of 4 for fp32 output");
-      EpiResidualF32::Params p{static_cast<float*>(out), resid, bias, static_cast<int>(ldo)};
+      if (resid != static_cast<const float*>(out)) {
+        // not in place: seed the output with the residual, the epilogue then adds acc + bias into it
+        SGPT_CHECK_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(ldo) * 4, resid, static_cast<size_t>(ldo) * 4,
+                                          static_cast<size_t>(N) * 4, static_cast<size_t>(M),
+                                          cudaMemcpyDeviceToDevice, stream));
+      }
+      CUtensorMap om;
+      int rc = make_tma_2d_f32(&om, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N),
+                               static_cast<uint64_t>(ldo), 32, 32);
+      if (rc != SGPT_OK) return rc;
+      EpiResidualF32::Params p{om, bias};
       return bn == 256 ? launch_gemm<256, EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, stream)
                        : launch_gemm<128, EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, stream);
     }

@@ -12,11 +12,16 @@
 // The accumulator is double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs; smem stages and TMEM
 // stages are handed over with mbarriers only (no __syncthreads in the main loop).
 //
-// Epilogue data path.  tcgen05.ld hands thread r of a warp row r of the tile (32 consecutive columns per load), so a
-// direct global store would touch 32 different rows per instruction.  Each epilogue warp therefore owns a
-// [32 rows][64 cols] fp32 staging slab in smem (row pitch 66 floats: conflict-free 8-byte accesses both ways): it
-// writes its rows, then re-reads the slab row by row with lane l holding columns 2l, 2l+1 — every global load/store
-// of a warp is one contiguous 128-B (bf16) or 256-B (fp32) row segment.  `Op` supplies the per-element arithmetic.
+// Epilogue data paths.  tcgen05.ld hands thread r of a warp row r of the tile (32 consecutive columns per load); a
+// direct global store from that layout would touch 32 different rows per instruction.  Two families:
+//   EpiTma<Op>    (nn.Linear outputs)  thread = row: bias/activation in registers, the 128-byte row segment is written
+//                 to a per-warp smem box in the SWIZZLE_128B layout and one elected lane hands the [32 x 128 B] box to
+//                 the TMA engine — a plain tensor store (bf16 outputs) or an fp32 reduce-add into the residual stream
+//                 (`resid += acc + bias`, performed by the L2; no residual load in the SM at all).  Two boxes per warp
+//                 are double-buffered with cp.async.bulk.wait_group.read; M/N tails are clipped by the tensor map.
+//   EpiStaged<Op> (similarity scores / threshold filter)  smem transpose so that lane = column pair and each warp
+//                 instruction touches one contiguous row segment; needed where the work is per-(query row) with
+//                 warp-wide ballots.
 #pragma once
 #include "common.cuh"
 
@@ -25,8 +30,7 @@ namespace sgpt {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 256;
-constexpr int kStagePitch = 66;                                  // floats per staged row (64 + 2 pad)
-constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;         // 8448
+constexpr int kStageBytesPerWarp = 8192;  // per epilogue warp: 2 TMA boxes of 32 x 128 B, or one 32 x 64 fp32 slab
 
 template <int BN>
 struct GemmCfg {
@@ -61,7 +65,7 @@ struct TileMap {
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
-                    int N, int K, typename Epi::Params ep, TileMap tmap) {
+                    int N, int K, const __grid_constant__ typename Epi::Params ep, TileMap tmap) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
 
@@ -189,7 +193,126 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// TMA epilogue driver: TMEM -> registers (thread = row) -> Op (bias / activation) -> swizzled smem box -> TMA
+// ---------------------------------------------------------------------------------------------------------------
+struct EpiTmaState {
+  uint32_t it;  // boxes issued so far by this warp (selects the double buffer)
+};
+
+template <class Op>
+struct EpiTma {
+  using Params = typename Op::Params;
+  using State = EpiTmaState;
+  static constexpr int kCols = 128 / Op::kElemBytes;  // columns per 128-byte row segment: 64 (bf16) or 32 (fp32)
+  static __device__ __forceinline__ void init(State& st, const Params&, int) { st.it = 0; }
+  static __device__ __forceinline__ void finish(State&, const Params&, int lane_row) {
+    if ((lane_row & 31) == 0) bulk_wait_group<0>();  // all stores of this warp have fully completed
+  }
+
+  template <int BN>
+  static __device__ __forceinline__ void tile(State& st, const Params& p, int m0, int n0, int lane, uint32_t trow,
+                                              float* slab, int M, int N) {
+    if (m0 >= M) return;  // whole 32-row slab out of range (warp-uniform)
+    const uint32_t sbase = smem_u32(slab);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += kCols) {
+      const int n = n0 + c;
+      if (n >= N) break;  // warp-uniform
+      const uint32_t box = sbase + (st.it & 1u) * 4096u;
+      if (st.it >= 2) {
+        if (lane == 0) bulk_wait_group_read<1>();  // the store issued two boxes ago has finished reading this buffer
+        __syncwarp();
+      }
+      uint32_t v[kCols];
+      tmem_ld_32x32(trow + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      if (kCols == 64) tmem_ld_32x32(trow + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[kCols - 32]));
+      tmem_ld_wait();
+      // 8 chunks of 16 bytes; chunk j of row r lives at position j ^ (r & 7) of the row (SWIZZLE_128B)
+      const uint32_t row_addr = box + lane * 128u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t o[4];
+        Op::chunk(p, &v[j * (kCols / 8)], n + j * (kCols / 8), N, o);
+        sts_v4(row_addr + ((j ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        Op::issue(p, reinterpret_cast<const void*>(__cvta_shared_to_generic(box)), n, m0);
+        bulk_commit_group();
+      }
+      ++st.it;
+    }
+  }
+};
+
+// bias index helper: columns beyond N are clipped by the tensor map, their bias is read from the last valid entry
+__device__ __forceinline__ float bias_at(const float* bias, int col, int N) {
+  return bias ? __ldg(bias + (col < N ? col : N - 1)) : 0.f;
+}
+
+// out_bf16[m, n] = act(acc + bias[n])          act = identity | gelu_new
+template <bool kGelu>
+struct OpTmaBiasActBF16 {
+  static constexpr int kElemBytes = 2;
+  struct Params {
+    CUtensorMap out_map;  // bf16 [M, N], box 32 rows x 64 cols, SWIZZLE_128B
+    const float* bias;    // may be null
+  };
+  // 8 consecutive columns starting at `col` -> 16 bytes
+  static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, uint32_t (&o)[4]) {
+    float x[8];
+    if (p.bias && col + 8 <= N) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + bb[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + bias_at(p.bias, col + i, N);
+    }
+    if (kGelu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = gelu_new(x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+  }
+  static __device__ __forceinline__ void issue(const Params& p, const void* box, int n, int m0) {
+    tma_store_2d(&p.out_map, box, n, m0);
+  }
+};
+
+// resid_f32[m, n] += acc + bias[n]      (fp32 residual stream updated in place by a TMA reduce-add)
+struct OpTmaResidAddF32 {
+  static constexpr int kElemBytes = 4;
+  struct Params {
+    CUtensorMap out_map;  // fp32 [M, N], box 32 rows x 32 cols, SWIZZLE_128B
+    const float* bias;    // may be null
+  };
+  // 4 consecutive columns -> 16 bytes
+  static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, uint32_t (&o)[4]) {
+    if (p.bias && col + 4 <= N) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      o[0] = __float_as_uint(__uint_as_float(acc[0]) + b.x);
+      o[1] = __float_as_uint(__uint_as_float(acc[1]) + b.y);
+      o[2] = __float_as_uint(__uint_as_float(acc[2]) + b.z);
+      o[3] = __float_as_uint(__uint_as_float(acc[3]) + b.w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = __float_as_uint(__uint_as_float(acc[i]) + bias_at(p.bias, col + i, N));
+    }
+  }
+  static __device__ __forceinline__ void issue(const Params& p, const void* box, int n, int m0) {
+    tma_reduce_add_2d(&p.out_map, box, n, m0);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // Staged epilogue driver: TMEM -> registers (thread = row) -> smem slab -> (lane = column pair) -> Op::rows()
+// The slab is [32 rows][32 column pairs] of float2 without padding; pair p of row r is stored at p ^ (r & 15), which
+// makes both the row-wise writes and the column-wise reads bank-conflict free for 8-byte accesses.
 // ---------------------------------------------------------------------------------------------------------------
 struct EpiNoState {};
 
@@ -202,8 +325,9 @@ struct EpiStaged {
 
   template <int BN>
   static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int lane, uint32_t trow,
-                                              float* slab, int M, int N) {
+                                              float* slab_ptr, int M, int N) {
     const int rows = min(32, M - m0);  // warp-uniform; <= 0 when the whole slab is out of range
+    const uint32_t slab = smem_u32(slab_ptr);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 64) {
       const int n = n0 + c;
@@ -218,112 +342,22 @@ struct EpiStaged {
       }
       tmem_ld_wait();
       __syncwarp();  // the previous slab's readers are done
-      float2* srow = reinterpret_cast<float2*>(slab + lane * kStagePitch);
+      const uint32_t wrow = slab + lane * 256u;
+      const uint32_t sw = lane & 15;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) srow[i] = make_float2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+      for (int i = 0; i < 16; ++i) sts_v2(wrow + ((i ^ sw) << 3), v0[2 * i], v0[2 * i + 1]);
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        srow[16 + i] = make_float2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+      for (int i = 0; i < 16; ++i) sts_v2(wrow + (((16 + i) ^ sw) << 3), v1[2 * i], v1[2 * i + 1]);
       __syncwarp();
       if (rows > 0) Op::rows(p, slab, m0, rows, n + 2 * lane, N, lane);
     }
   }
 };
 
-__device__ __forceinline__ float2 slab_read(const float* slab, int r, int lane) {
-  return *reinterpret_cast<const float2*>(slab + r * kStagePitch + 2 * lane);
+// columns (2*lane, 2*lane+1) of staged row r
+__device__ __forceinline__ float2 slab_read(uint32_t slab, int r, int lane) {
+  return lds_v2(slab + r * 256u + ((lane ^ (r & 15)) << 3));
 }
-
-// out_bf16[m, n] = act(acc + bias[n])          act = identity | gelu_new
-template <bool kGelu>
-struct OpBiasActBF16 {
-  struct Params {
-    __nv_bfloat16* out;
-    const float* bias;  // may be null
-    int ldc;
-  };
-  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
-                                              int lane) {
-    const bool ok0 = col < N, ok1 = col + 1 < N;
-    float b0 = 0.f, b1 = 0.f;
-    if (p.bias) {
-      if (ok0) b0 = __ldg(p.bias + col);
-      if (ok1) b1 = __ldg(p.bias + col + 1);
-    }
-    __nv_bfloat16* dst = p.out + static_cast<size_t>(m0) * p.ldc + col;
-    // Rows in batches of 8: all smem reads of a batch are issued before its global stores (the compiler cannot prove
-    // the slab and the output do not alias, so without explicit batching every iteration would serialise on LDS latency).
-    int r = 0;
-    for (; r + 8 <= rows; r += 8) {
-      float2 a[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] = slab_read(slab, r + u, lane);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float x = a[u].x + b0, y = a[u].y + b1;
-        if (kGelu) { x = gelu_new(x); y = gelu_new(y); }
-        if (ok1) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(x, y);
-        else if (ok0) *dst = __float2bfloat16_rn(x);
-        dst += p.ldc;
-      }
-    }
-    for (; r < rows; ++r) {
-      const float2 a = slab_read(slab, r, lane);
-      float x = a.x + b0, y = a.y + b1;
-      if (kGelu) { x = gelu_new(x); y = gelu_new(y); }
-      if (ok1) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(x, y);
-      else if (ok0) *dst = __float2bfloat16_rn(x);
-      dst += p.ldc;
-    }
-  }
-};
-
-// resid_f32[m, n] = resid_in[m, n] + acc + bias[n]      (fp32 residual stream; in-place allowed)
-struct OpResidualF32 {
-  struct Params {
-    float* out;
-    const float* resid;  // may alias out
-    const float* bias;   // may be null
-    int ldc;
-  };
-  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
-                                              int lane) {
-    const bool ok0 = col < N, ok1 = col + 1 < N;
-    float b0 = 0.f, b1 = 0.f;
-    if (p.bias) {
-      if (ok0) b0 = __ldg(p.bias + col);
-      if (ok1) b1 = __ldg(p.bias + col + 1);
-    }
-    const size_t base = static_cast<size_t>(m0) * p.ldc + col;
-    int r = 0;
-    if (ok1) {
-      // 16 rows per batch: issue all residual (global) and accumulator (smem) loads first, then combine and store —
-      // one exposed global-load latency per 16 rows instead of per row
-      for (; r + 16 <= rows; r += 16) {
-        float2 g[16], a[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u)
-          g[u] = *reinterpret_cast<const float2*>(p.resid + base + static_cast<size_t>(r + u) * p.ldc);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) a[u] = slab_read(slab, r + u, lane);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          g[u].x += a[u].x + b0;
-          g[u].y += a[u].y + b1;
-          *reinterpret_cast<float2*>(p.out + base + static_cast<size_t>(r + u) * p.ldc) = g[u];
-        }
-      }
-    }
-    for (; r < rows; ++r) {
-      const float2 a = slab_read(slab, r, lane);
-      const size_t off = base + static_cast<size_t>(r) * p.ldc;
-      // same association as the batched path (resid + (acc + bias)): a row's result must not depend on where it
-      // falls relative to the 16-row batches
-      if (ok0) p.out[off] = p.resid[off] + (a.x + b0);
-      if (ok1) p.out[off + 1] = p.resid[off + 1] + (a.y + b1);
-    }
-  }
-};
 
 // scores_f32[q, doc] = fixnan(acc * row_scale[q] * col_scale[doc])       (cos_sim / dot_score, NaN -> -1)
 struct OpScoresF32 {
@@ -333,7 +367,7 @@ struct OpScoresF32 {
     const float* col_scale;  // per doc    (1/||d|| for cos_sim; null = 1)
     long long ldc;
   };
-  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
+  static __device__ __forceinline__ void rows(const Params& p, uint32_t slab, int m0, int rows, int col, int N,
                                               int lane) {
     const bool ok0 = col < N, ok1 = col + 1 < N;
     float c0 = 1.f, c1 = 1.f;
@@ -392,7 +426,7 @@ struct OpFilterCandidates {
     int* count;              // [nq]
     long long cap;
   };
-  static __device__ __forceinline__ void rows(const Params& p, const float* slab, int m0, int rows, int col, int N,
+  static __device__ __forceinline__ void rows(const Params& p, uint32_t slab, int m0, int rows, int col, int N,
                                               int lane) {
     const bool ok0 = col < N, ok1 = col + 1 < N;
     float c0 = 1.f, c1 = 1.f;
@@ -460,8 +494,8 @@ struct OpFilterCandidates {
 using EpiFilterCandidates = EpiStaged<OpFilterCandidates>;
 
 template <bool kGelu>
-using EpiBiasActBF16 = EpiStaged<OpBiasActBF16<kGelu>>;
-using EpiResidualF32 = EpiStaged<OpResidualF32>;
+using EpiBiasActBF16 = EpiTma<OpTmaBiasActBF16<kGelu>>;
+using EpiResidualF32 = EpiTma<OpTmaResidAddF32>;
 using EpiScoresF32 = EpiStaged<OpScoresF32>;
 
 }  // namespace sgpt
