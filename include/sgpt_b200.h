@@ -62,14 +62,28 @@ int sgpt_layernorm(const float* x, const float* gamma, const float* beta, void* 
 int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out, int64_t ldo,
                 const float* resid, int M, int N, int K, int epilogue, sgpt_stream_t stream);
 
+/* F2'. In-place fp32 LayerNorm (BLOOM word_embeddings_layernorm, HF:bloom/modeling_bloom.py:496): x fp32[T,d]. */
+int sgpt_layernorm_f32_inplace(float* x, const float* gamma, const float* beta, int T, int d, float eps,
+                               sgpt_stream_t stream);
+
+/* F3'. GPT-J fused q/k/v projection with rotary position embedding in the epilogue
+ *     (HF:gptj/modeling_gptj.py:98-101 bias-free projections, :55-67 + :196-207 rotary on the first rotary_dim dims of
+ *     every q and k head, interleaved pairs).  x bf16[M,d] (pitch ldx), w_qkv bf16[3d,d] rows [q|k|v],
+ *     qkv bf16[M,3d]; pos int32[M]; cos_sin fp32[max_pos, rotary_dim/2, 2] = (cos, sin) of pos * 10000^(-2i/rotary_dim). */
+int sgpt_linear_qkv_rotary(const void* x, int64_t ldx, const void* w_qkv, void* qkv, const int32_t* pos,
+                           const float* cos_sin, int M, int d_model, int head_dim, int rotary_dim, int max_pos,
+                           sgpt_stream_t stream);
+
 /* F4. Causal self-attention over a ragged batch.    HF:gpt_neo/modeling_gpt_neo.py:105-130 (_attn)
  *     qkv bf16[T, 3*H*hd]: per token [q(H*hd) | k(H*hd) | v(H*hd)];  out bf16[T, H*hd].
  *     cu_seqlens int32[B+1] (row offsets of each sequence; cu[B] == T).
  *     scale: multiplies q.k before softmax (GPT-Neo: 1.0 — unscaled, :110; GPT-J: 1/sqrt(hd)).
  *     window: 0 = plain causal; w > 0 = GPT-Neo local attention (key j visible to query i iff i-w < j <= i, :63-66).
+ *     alibi_slopes: fp32[H] or NULL; adds slope_h * (key position in its sequence) to the scaled scores (BLOOM ALiBi,
+ *                   HF:bloom/modeling_bloom.py:43-86; the bias depends on the key only).
  *     impl: 0 = tcgen05 tensor-core kernel, 1 = SIMT cross-check kernel (test infrastructure). */
 int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seqlens, int B, int T, int H, int hd, float scale,
-                   int window, int max_seqlen, int impl, sgpt_stream_t stream);
+                   int window, int max_seqlen, const float* alibi_slopes, int impl, sgpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * P1/P2. Pooling over the ragged sequence dimension, fp32 accumulate.
@@ -126,6 +140,7 @@ typedef struct sgpt_model_weights {
   const void* wpe; /* bf16[max_pos, d] or NULL */
   const float *lnf_g, *lnf_b;
   const sgpt_layer_weights* layers; /* HOST array of n_layer entries (copied at create) */
+  const float *emb_ln_g, *emb_ln_b; /* BLOOM word_embeddings_layernorm, else NULL */
 } sgpt_model_weights;
 
 typedef struct sgpt_model* sgpt_model_t;

@@ -32,7 +32,8 @@ class LayerWeightsC(C.Structure):
 
 
 class ModelWeightsC(C.Structure):
-    _fields_ = [("wte", vp), ("wpe", vp), ("lnf_g", vp), ("lnf_b", vp), ("layers", C.POINTER(LayerWeightsC))]
+    _fields_ = [("wte", vp), ("wpe", vp), ("lnf_g", vp), ("lnf_b", vp), ("layers", C.POINTER(LayerWeightsC)),
+                ("emb_ln_g", vp), ("emb_ln_b", vp)]
 
 
 _SIGNATURES = {
@@ -40,8 +41,10 @@ _SIGNATURES = {
     "sgpt_last_error": (C.c_char_p, []),
     "sgpt_embed_tokens": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "sgpt_layernorm": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
+    "sgpt_layernorm_f32_inplace": (i32, [vp, vp, vp, i32, i32, f32, vp]),
+    "sgpt_linear_qkv_rotary": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "sgpt_linear": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp]),
-    "sgpt_attention": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, i32, vp]),
+    "sgpt_attention": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp, i32, vp]),
     "sgpt_pool": (i32, [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sgpt_model_create": (i32, [C.POINTER(ModelConfigC), C.POINTER(ModelWeightsC), C.POINTER(vp)]),
     "sgpt_model_destroy": (None, [vp]),

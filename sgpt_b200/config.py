@@ -13,13 +13,15 @@ class ModelConfig:
     n_head: int = 12
     d_ff: int = 3072
     vocab: int = 50257
-    max_pos: int = 2048
+    max_pos: int = 2048            # learned positions (GPT-Neo) / rotary table length (GPT-J); unused by BLOOM
     window: int = 256              # GPT-Neo local attention window
     rotary_dim: int = 0            # GPT-J
     ln_eps: float = 1e-5
     attention_layers: List[str] = field(default_factory=list)  # GPT-Neo: "global"/"local" per layer
 
     def __post_init__(self):
+        if self.arch not in ("gpt_neo", "gptj", "bloom"):
+            raise ValueError(f"unknown arch {self.arch!r}")
         if self.arch == "gpt_neo" and not self.attention_layers:
             self.attention_layers = ["global" if i % 2 == 0 else "local" for i in range(self.n_layer)]
 
@@ -29,7 +31,7 @@ class ModelConfig:
 
     @classmethod
     def from_hf(cls, hf_config) -> "ModelConfig":
-        """Build from a HuggingFace config object (GPTNeoConfig today)."""
+        """Build from a HuggingFace config object (GPTNeoConfig / GPTJConfig / BloomConfig)."""
         mt = getattr(hf_config, "model_type", "")
         if mt == "gpt_neo":
             inter = hf_config.intermediate_size or 4 * hf_config.hidden_size
@@ -37,7 +39,17 @@ class ModelConfig:
                        n_head=hf_config.num_heads, d_ff=inter, vocab=hf_config.vocab_size,
                        max_pos=hf_config.max_position_embeddings, window=hf_config.window_size,
                        ln_eps=hf_config.layer_norm_epsilon, attention_layers=list(hf_config.attention_layers))
-        raise NotImplementedError(f"model_type {mt!r} is not supported yet (GPT-J and BLOOM are planned)")
+        if mt == "gptj":
+            inter = hf_config.n_inner or 4 * hf_config.n_embd
+            return cls(arch="gptj", n_layer=hf_config.n_layer, d_model=hf_config.n_embd, n_head=hf_config.n_head,
+                       d_ff=inter, vocab=hf_config.vocab_size, max_pos=hf_config.n_positions,
+                       rotary_dim=hf_config.rotary_dim or (hf_config.n_embd // hf_config.n_head),
+                       ln_eps=hf_config.layer_norm_epsilon)
+        if mt == "bloom":
+            return cls(arch="bloom", n_layer=hf_config.n_layer, d_model=hf_config.hidden_size, n_head=hf_config.n_head,
+                       d_ff=4 * hf_config.hidden_size, vocab=hf_config.vocab_size, max_pos=1 << 20,
+                       ln_eps=hf_config.layer_norm_epsilon)
+        raise NotImplementedError(f"model_type {mt!r} is not supported (gpt_neo, gptj, bloom are)")
 
 
 PRESETS = {
@@ -47,6 +59,10 @@ PRESETS = {
     "sgpt-1.3b": dict(arch="gpt_neo", n_layer=24, d_model=2048, n_head=16, d_ff=8192),
     # SGPT-2.7B-weightedmean-* (EleutherAI/gpt-neo-2.7B)
     "sgpt-2.7b": dict(arch="gpt_neo", n_layer=32, d_model=2560, n_head=20, d_ff=10240),
+    # SGPT-5.8B-weightedmean-* (EleutherAI/gpt-j-6B)
+    "sgpt-5.8b": dict(arch="gptj", n_layer=28, d_model=4096, n_head=16, d_ff=16384, vocab=50400, rotary_dim=64),
+    # sgpt-bloom-7b1-msmarco (bigscience/bloom-7b1)
+    "sgpt-bloom-7b1": dict(arch="bloom", n_layer=30, d_model=4096, n_head=32, d_ff=16384, vocab=250880, max_pos=1 << 20),
 }
 
 

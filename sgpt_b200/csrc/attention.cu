@@ -38,7 +38,7 @@ template <int HD>
 __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv,
                                                            __nv_bfloat16* __restrict__ out,
                                                            const int32_t* __restrict__ cu, int H, float sl2,
-                                                           int window) {
+                                                           int window, const float* __restrict__ alibi) {
   using Cfg = AttnCfg<HD>;
   const int qt = blockIdx.x, b = blockIdx.y, h = blockIdx.z;
   const int seq0 = __ldg(cu + b);
@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, true);
 
+  // BLOOM ALiBi (HF:bloom/modeling_bloom.py:84-86): + slope_h * (key position) before the softmax, here pre-multiplied
+  // by log2(e) because the softmax runs in the exp2 domain
+  const float slope2 = (alibi != nullptr) ? __ldg(alibi + h) * 1.4426950408889634f : 0.f;
   const int qpos = qp0 + tid;
   const int vis_hi = min(qpos, len - 1);
   const int vis_lo = (window > 0) ? (qpos - window + 1) : 0;
@@ -146,11 +149,11 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int kp = kv0 + c * 32 + i;
-        const float s = __uint_as_float(v[i]);
+        const float s = fmaf(__uint_as_float(v[i]), sl2, slope2 * static_cast<float>(kp));
         if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, s);
       }
     }
-    const float m_new = fmaxf(m_run, mx * sl2);
+    const float m_new = fmaxf(m_run, mx);
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
     const float alpha = exp2f(m_run - m_use);
     float lsum = 0.f;
@@ -169,8 +172,8 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int kp = kv0 + c * 32 + 2 * i;
-        float p0 = exp2f(__uint_as_float(v[2 * i]) * sl2 - m_use);
-        float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * sl2 - m_use);
+        float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, slope2 * static_cast<float>(kp)) - m_use);
+        float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, slope2 * static_cast<float>(kp + 1)) - m_use);
         if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
         if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
         lsum += p0 + p1;
@@ -272,7 +275,7 @@ template <int HD>
 __global__ void __launch_bounds__(256) attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                              __nv_bfloat16* __restrict__ out,
                                                              const int32_t* __restrict__ cu, int B, int T, int H,
-                                                             float scale, int window) {
+                                                             float scale, int window, const float* __restrict__ alibi) {
   constexpr int E = HD / 32;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int h = blockIdx.y;
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const __nv_bfloat16
 #pragma unroll
     for (int e = 0; e < E; ++e) s += q[e] * __bfloat162float(qkv[kt * ld + d + h * HD + lane * E + e]);
     s = warp_sum(s) * scale;
+    if (alibi != nullptr) s += __ldg(alibi + h) * static_cast<float>(kt - seq0);
     const float mn = fmaxf(m, s);
     const float a = expf(m - mn), p = expf(s - mn);
     l = l * a + p;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const __nv_bfloat16
 
 template <int HD>
 static int launch_attention_tc(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale,
-                               int window, int max_seqlen, cudaStream_t stream) {
+                               int window, int max_seqlen, const float* alibi, cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
   CUtensorMap map;
   int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
@@ -330,18 +334,18 @@ static int launch_attention_tc(const void* qkv, void* out, const int32_t* cu, in
   dim3 grid((max_seqlen + kAttnTile - 1) / kAttnTile, B, H);
   const float sl2 = scale * 1.4426950408889634f;
   LaunchScope _ls(kCatAttention, stream);
-  kern<<<grid, 128, Cfg::kSmemBytes, stream>>>(map, static_cast<__nv_bfloat16*>(out), cu, H, sl2, window);
+  kern<<<grid, 128, Cfg::kSmemBytes, stream>>>(map, static_cast<__nv_bfloat16*>(out), cu, H, sl2, window, alibi);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }
 
 template <int HD>
 static int launch_attention_simt(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale,
-                                 int window, cudaStream_t stream) {
+                                 int window, const float* alibi, cudaStream_t stream) {
   dim3 grid((T + 7) / 8, H);
   LaunchScope _ls(kCatAttention, stream);
   attention_simt_kernel<HD><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                      static_cast<__nv_bfloat16*>(out), cu, B, T, H, scale, window);
+                                                      static_cast<__nv_bfloat16*>(out), cu, B, T, H, scale, window, alibi);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }
@@ -351,7 +355,8 @@ static int launch_attention_simt(const void* qkv, void* out, const int32_t* cu, 
 using namespace sgpt;
 
 extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seqlens, int B, int T, int H, int hd,
-                              float scale, int window, int max_seqlen, int impl, sgpt_stream_t stream_) {
+                              float scale, int window, int max_seqlen, const float* alibi_slopes, int impl,
+                              sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(B >= 0 && T >= 0 && H > 0, "sgpt_attention: bad sizes B=%d T=%d H=%d", B, T, H);
   SGPT_REQUIRE(hd == 64 || hd == 128 || hd == 256, "sgpt_attention: head_dim %d not in {64,128,256}", hd);
@@ -362,15 +367,15 @@ extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seql
   if (impl == 0) {
     SGPT_REQUIRE(H <= 65535 && B <= 65535, "sgpt_attention: grid limits exceeded (B=%d H=%d)", B, H);
     switch (hd) {
-      case 64: return launch_attention_tc<64>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, stream);
-      case 128: return launch_attention_tc<128>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, stream);
-      default: return launch_attention_tc<256>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, stream);
+      case 64: return launch_attention_tc<64>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, alibi_slopes, stream);
+      case 128: return launch_attention_tc<128>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, alibi_slopes, stream);
+      default: return launch_attention_tc<256>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, alibi_slopes, stream);
     }
   } else if (impl == 1) {
     switch (hd) {
-      case 64: return launch_attention_simt<64>(qkv, out, cu_seqlens, B, T, H, scale, window, stream);
-      case 128: return launch_attention_simt<128>(qkv, out, cu_seqlens, B, T, H, scale, window, stream);
-      default: return launch_attention_simt<256>(qkv, out, cu_seqlens, B, T, H, scale, window, stream);
+      case 64: return launch_attention_simt<64>(qkv, out, cu_seqlens, B, T, H, scale, window, alibi_slopes, stream);
+      case 128: return launch_attention_simt<128>(qkv, out, cu_seqlens, B, T, H, scale, window, alibi_slopes, stream);
+      default: return launch_attention_simt<256>(qkv, out, cu_seqlens, B, T, H, scale, window, alibi_slopes, stream);
     }
   }
   set_error("sgpt_attention: unknown impl %d", impl);

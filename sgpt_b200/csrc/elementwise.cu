@@ -59,10 +59,16 @@ __device__ __forceinline__ float group_sum(float v, float* scratch /* [rows_per_
   return s;
 }
 
-template <int TPR, int V>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ g,
-                                                        const float4* __restrict__ b, uint2* __restrict__ y, int T,
-                                                        int d4, float eps) {
+__device__ __forceinline__ void ln_store(uint2* y, size_t idx, float o0, float o1, float o2, float o3) {
+  y[idx] = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+}
+__device__ __forceinline__ void ln_store(float4* y, size_t idx, float o0, float o1, float o2, float o3) {
+  y[idx] = make_float4(o0, o1, o2, o3);
+}
+
+template <int TPR, int V, class OutT>
+__device__ __forceinline__ void layernorm_body(const float4* x, const float4* __restrict__ g,
+                                               const float4* __restrict__ b, OutT* y, int T, int d4, float eps) {
   constexpr int ROWS = 256 / TPR;
   __shared__ float scratch[ROWS * (TPR / 32) + 1];
   const int row_in_cta = threadIdx.x / TPR;
@@ -100,9 +106,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float4* __restrict
       const float o1 = (v[i].y - mean) * rstd * gg.y + bb.y;
       const float o2 = (v[i].z - mean) * rstd * gg.z + bb.z;
       const float o3 = (v[i].w - mean) * rstd * gg.w + bb.w;
-      y[static_cast<size_t>(row) * d4 + c] = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      ln_store(y, static_cast<size_t>(row) * d4 + c, o0, o1, o2, o3);
     }
   }
+}
+
+template <int TPR, int V>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ g,
+                                                        const float4* __restrict__ b, uint2* __restrict__ y, int T,
+                                                        int d4, float eps) {
+  layernorm_body<TPR, V>(x, g, b, y, T, d4, eps);
+}
+
+// fp32 output, may run in place (each thread rewrites exactly the elements it read)
+template <int TPR, int V>
+__global__ void __launch_bounds__(256) layernorm_f32_kernel(const float4* x, const float4* __restrict__ g,
+                                                            const float4* __restrict__ b, float4* y, int T, int d4,
+                                                            float eps) {
+  layernorm_body<TPR, V>(x, g, b, y, T, d4, eps);
 }
 
 // Row statistics only (mean, rstd) -> stats[2*t], used by the pooling kernel to apply ln_f on the fly.
@@ -302,6 +323,20 @@ extern "C" int sgpt_layernorm(const float* x, const float* gamma, const float* b
   SGPT_ROW_DISPATCH(layernorm_kernel, d4, T, stream, reinterpret_cast<const float4*>(x),
                     reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
                     static_cast<uint2*>(y), T, d4, eps);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_layernorm_f32_inplace(float* x, const float* gamma, const float* beta, int T, int d, float eps,
+                                          sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(T >= 0 && d > 0 && d % 4 == 0, "sgpt_layernorm_f32_inplace: d=%d must be a positive multiple of 4", d);
+  if (T == 0) return SGPT_OK;
+  const int d4 = d / 4;
+  LaunchScope _ls(kCatLayerNorm, stream);
+  SGPT_ROW_DISPATCH(layernorm_f32_kernel, d4, T, stream, reinterpret_cast<const float4*>(x),
+                    reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
+                    reinterpret_cast<float4*>(x), T, d4, eps);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }

@@ -116,6 +116,29 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
   }
 }
 
+extern "C" int sgpt_linear_qkv_rotary(const void* x, int64_t ldx, const void* w_qkv, void* qkv, const int32_t* pos,
+                                      const float* cos_sin, int M, int d_model, int head_dim, int rotary_dim,
+                                      int max_pos, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(M >= 0 && d_model > 0 && d_model % 8 == 0 && ldx % 8 == 0 && ldx >= d_model,
+               "sgpt_linear_qkv_rotary: bad sizes M=%d d=%d ldx=%lld", M, d_model, (long long)ldx);
+  SGPT_REQUIRE(head_dim > 0 && d_model % head_dim == 0 && head_dim % 8 == 0, "sgpt_linear_qkv_rotary: bad head_dim %d",
+               head_dim);
+  SGPT_REQUIRE(rotary_dim >= 0 && rotary_dim <= head_dim && rotary_dim % 8 == 0,
+               "sgpt_linear_qkv_rotary: rotary_dim %d must be a multiple of 8 and <= head_dim", rotary_dim);
+  SGPT_REQUIRE(pos != nullptr && cos_sin != nullptr && max_pos > 0, "sgpt_linear_qkv_rotary: pos / cos_sin missing");
+  if (M == 0) return SGPT_OK;
+  const int N = 3 * d_model;
+  CUtensorMap om;
+  int rc = make_tma_2d_bf16(&om, qkv, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(N), 32,
+                            64);
+  if (rc != SGPT_OK) return rc;
+  EpiRotaryBF16::Params p{om, pos, reinterpret_cast<const float2*>(cos_sin), M, d_model, head_dim, rotary_dim, max_pos};
+  return pick_bn(M, N) == 256
+             ? launch_gemm<256, EpiRotaryBF16>(x, ldx, w_qkv, d_model, M, N, d_model, p, stream)
+             : launch_gemm<128, EpiRotaryBF16>(x, ldx, w_qkv, d_model, M, N, d_model, p, stream);
+}
+
 extern "C" int sgpt_scores(const void* Q, const void* C, const float* q_scale, const float* c_scale, float* scores,
                            int64_t lds, int nq, int64_t n, int D, sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -228,13 +228,15 @@ struct EpiTma {
       if (kCols == 64) tmem_ld_32x32(trow + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[kCols - 32]));
       tmem_ld_wait();
       // 8 chunks of 16 bytes; chunk j of row r lives at position j ^ (r & 7) of the row (SWIZZLE_128B)
+      // All 8 chunks are computed before any of them is stored: the bias / rotary-table loads inside Op::chunk are then
+      // independent ordinary loads the compiler batches up front (one exposed latency per box instead of one per chunk;
+      // the volatile smem stores would otherwise fence them apart).
       const uint32_t row_addr = box + lane * 128u;
+      uint32_t o[8][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t o[4];
-        Op::chunk(p, &v[j * (kCols / 8)], n + j * (kCols / 8), N, o);
-        sts_v4(row_addr + ((j ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
-      }
+      for (int j = 0; j < 8; ++j) Op::chunk(p, &v[j * (kCols / 8)], n + j * (kCols / 8), N, m0 + lane, o[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts_v4(row_addr + ((j ^ (lane & 7)) << 4), o[j][0], o[j][1], o[j][2], o[j][3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -260,7 +262,8 @@ struct OpTmaBiasActBF16 {
     const float* bias;    // may be null
   };
   // 8 consecutive columns starting at `col` -> 16 bytes
-  static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, uint32_t (&o)[4]) {
+  static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, int /*row*/,
+                                               uint32_t (&o)[4]) {
     float x[8];
     if (p.bias && col + 8 <= N) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
@@ -284,6 +287,45 @@ struct OpTmaBiasActBF16 {
   }
 };
 
+// GPT-J fused q/k/v projection: out_bf16[m, n] = rotary(acc) for the first `rotary_dim` dims of every q and k head
+// (HF:gptj/modeling_gptj.py:55-67, 196-207: interleaved pairs (x[2i], x[2i+1]) -> (x[2i] c - x[2i+1] s, x[2i+1] c + x[2i] s)
+// with angle pos[m] * 10000^(-2i/rotary_dim)); v columns and the non-rotary dims pass through.  No bias (:98-101).
+struct OpTmaRotaryBF16 {
+  static constexpr int kElemBytes = 2;
+  struct Params {
+    CUtensorMap out_map;     // bf16 [M, 3d]
+    const int32_t* pos;      // [M] position of each token row
+    const float2* table;     // [max_pos, rotary_dim/2] (cos, sin)
+    int M, d_model, head_dim, rotary_dim, max_pos;
+  };
+  static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, int row,
+                                               uint32_t (&o)[4]) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]);
+    const int in_head = col % p.head_dim;  // 8-column chunks never straddle heads (head_dim % 8 == 0)
+    if (col < 2 * p.d_model && in_head < p.rotary_dim) {
+      int ps = __ldg(p.pos + (row < p.M ? row : p.M - 1));
+      ps = min(max(ps, 0), p.max_pos - 1);
+      const float4* t4 = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(ps) * (p.rotary_dim >> 1) +
+                                                         (in_head >> 1));
+      const float4 a = __ldg(t4), b = __ldg(t4 + 1);  // (c0,s0,c1,s1), (c2,s2,c3,s3)
+      const float cs[4] = {a.x, a.z, b.x, b.z}, sn[4] = {a.y, a.w, b.y, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float e = x[2 * i], od = x[2 * i + 1];
+        x[2 * i] = e * cs[i] - od * sn[i];
+        x[2 * i + 1] = od * cs[i] + e * sn[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+  }
+  static __device__ __forceinline__ void issue(const Params& p, const void* box, int n, int m0) {
+    tma_store_2d(&p.out_map, box, n, m0);
+  }
+};
+
 // resid_f32[m, n] += acc + bias[n]      (fp32 residual stream updated in place by a TMA reduce-add)
 struct OpTmaResidAddF32 {
   static constexpr int kElemBytes = 4;
@@ -292,7 +334,8 @@ struct OpTmaResidAddF32 {
     const float* bias;    // may be null
   };
   // 4 consecutive columns -> 16 bytes
-  static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, uint32_t (&o)[4]) {
+  static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, int /*row*/,
+                                               uint32_t (&o)[4]) {
     if (p.bias && col + 4 <= N) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
       o[0] = __float_as_uint(__uint_as_float(acc[0]) + b.x);
@@ -496,6 +539,7 @@ using EpiFilterCandidates = EpiStaged<OpFilterCandidates>;
 template <bool kGelu>
 using EpiBiasActBF16 = EpiTma<OpTmaBiasActBF16<kGelu>>;
 using EpiResidualF32 = EpiTma<OpTmaResidAddF32>;
+using EpiRotaryBF16 = EpiTma<OpTmaRotaryBF16>;
 using EpiScoresF32 = EpiStaged<OpScoresF32>;
 
 }  // namespace sgpt

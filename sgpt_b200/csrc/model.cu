@@ -1,8 +1,16 @@
 // Whole-encoder handle: token ids -> GPT forward (F1..F7) -> pooled embeddings (P1/P2) in one C call.
 // Replaces `self.model(**batch_tokens, output_hidden_states=True)` + the pooling block of the reference
-// (biencoder/beir/beir_dense_retriever.py:205, :233-304).  The handle borrows the caller's weight buffers and owns
-// only its activation workspace, laid out for a ragged batch of at most cfg.max_tokens rows:
+// (biencoder/beir/beir_dense_retriever.py:205, :233-304).  Three block layouts (SURVEY.md §8 model table):
+//   GPT-Neo  HF:gpt_neo/modeling_gpt_neo.py:320-350   ln_1 -> attn (unscaled QK^T, local window on odd layers) -> +res
+//                                                       -> ln_2 -> c_fc/gelu_new/c_proj -> +res
+//   GPT-J    HF:gptj/modeling_gptj.py:390-415          ln_1 -> {attn (rotary q,k; 1/sqrt(hd)), fc_in/gelu_new/fc_out}
+//                                                       in parallel on the SAME ln_1 output -> res + attn + mlp
+//   BLOOM    HF:bloom/modeling_bloom.py:340-420        LN(word_emb) -> input_layernorm -> attn (ALiBi, 1/sqrt(hd), qkv
+//                                                       bias) -> +res -> post_attention_layernorm -> mlp (tanh gelu) -> +res
+// The handle borrows the caller's weight buffers and owns only its activation workspace, laid out for a ragged batch
+// of at most cfg.max_tokens rows:
 //     resid fp32[T,d] | xn bf16[T,d] | qkv bf16[T,3d] | attn bf16[T,d] | ffn bf16[T,ff] | stats fp32[2T+B]
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -22,6 +30,8 @@ struct sgpt_model {
   void* attn = nullptr;
   void* ffn = nullptr;
   float* stats = nullptr;
+  float* rotary = nullptr;  // GPT-J: (cos, sin)[max_pos, rotary_dim/2]
+  float* alibi = nullptr;   // BLOOM: slopes[n_head]
   int last_T = 0;
 };
 
@@ -29,15 +39,25 @@ using namespace sgpt;
 
 extern "C" int sgpt_abi_version(void) { return SGPT_ABI_VERSION; }
 
+// build_alibi_tensor slopes, HF:bloom/modeling_bloom.py:62-78
+static std::vector<float> alibi_slopes(int n_head) {
+  const int cp2 = 1 << static_cast<int>(floor(log2(static_cast<double>(n_head))));
+  std::vector<float> s;
+  const float base = static_cast<float>(pow(2.0, -pow(2.0, -(log2(static_cast<double>(cp2)) - 3.0))));
+  for (int i = 1; i <= cp2; ++i) s.push_back(powf(base, static_cast<float>(i)));
+  if (cp2 != n_head) {
+    const float extra = static_cast<float>(pow(2.0, -pow(2.0, -(log2(2.0 * cp2) - 3.0))));
+    const int rem = n_head - cp2 < cp2 ? n_head - cp2 : cp2;
+    for (int i = 0; i < rem; ++i) s.push_back(powf(extra, static_cast<float>(1 + 2 * i)));
+  }
+  return s;
+}
+
 extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_weights* w, sgpt_model_t* out) {
   SGPT_REQUIRE(cfg != nullptr && w != nullptr && out != nullptr, "sgpt_model_create: null argument");
   *out = nullptr;
   SGPT_REQUIRE(cfg->arch == SGPT_ARCH_GPT_NEO || cfg->arch == SGPT_ARCH_GPTJ || cfg->arch == SGPT_ARCH_BLOOM,
                "sgpt_model_create: unknown arch %d", cfg->arch);
-  if (cfg->arch != SGPT_ARCH_GPT_NEO) {
-    set_error("sgpt_model_create: arch %d (GPT-J / BLOOM) is not built yet", cfg->arch);
-    return SGPT_ERR_UNSUPPORTED;
-  }
   SGPT_REQUIRE(cfg->n_layer > 0 && cfg->d_model > 0 && cfg->n_head > 0 && cfg->d_ff > 0, "sgpt_model_create: bad dims");
   SGPT_REQUIRE(cfg->d_model % cfg->n_head == 0, "sgpt_model_create: d_model %% n_head != 0");
   const int hd = cfg->d_model / cfg->n_head;
@@ -46,7 +66,12 @@ extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_
   SGPT_REQUIRE(cfg->max_tokens > 0 && cfg->max_batch > 0, "sgpt_model_create: max_tokens/max_batch must be positive");
   SGPT_REQUIRE(w->wte != nullptr && w->lnf_g != nullptr && w->lnf_b != nullptr && w->layers != nullptr,
                "sgpt_model_create: missing weights");
-  SGPT_REQUIRE(w->wpe != nullptr, "sgpt_model_create: GPT-Neo needs wpe");
+  if (cfg->arch == SGPT_ARCH_GPT_NEO) SGPT_REQUIRE(w->wpe != nullptr, "sgpt_model_create: GPT-Neo needs wpe");
+  if (cfg->arch == SGPT_ARCH_GPTJ)
+    SGPT_REQUIRE(cfg->rotary_dim > 0 && cfg->rotary_dim <= hd && cfg->rotary_dim % 8 == 0 && cfg->max_pos > 0,
+                 "sgpt_model_create: GPT-J needs 0 < rotary_dim <= head_dim, multiple of 8");
+  if (cfg->arch == SGPT_ARCH_BLOOM)
+    SGPT_REQUIRE(w->emb_ln_g != nullptr && w->emb_ln_b != nullptr, "sgpt_model_create: BLOOM needs the embedding LayerNorm");
 
   sgpt_model* m = new sgpt_model();
   m->cfg = *cfg;
@@ -55,7 +80,9 @@ extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_
   m->w.layers = m->layers.data();
   for (int l = 0; l < cfg->n_layer; ++l) {
     const sgpt_layer_weights& lw = m->layers[l];
-    if (!lw.ln1_g || !lw.ln1_b || !lw.w_qkv || !lw.w_o || !lw.ln2_g || !lw.ln2_b || !lw.w_fc || !lw.w_proj) {
+    const bool need_ln2 = cfg->arch != SGPT_ARCH_GPTJ;
+    if (!lw.ln1_g || !lw.ln1_b || !lw.w_qkv || !lw.w_o || !lw.w_fc || !lw.w_proj ||
+        (need_ln2 && (!lw.ln2_g || !lw.ln2_b))) {
       delete m;
       set_error("sgpt_model_create: layer %d has missing weights", l);
       return SGPT_ERR_INVALID;
@@ -69,6 +96,25 @@ extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_
   if (e == cudaSuccess) e = cudaMalloc(&m->attn, T * d * 2);
   if (e == cudaSuccess) e = cudaMalloc(&m->ffn, T * static_cast<size_t>(cfg->d_ff) * 2);
   if (e == cudaSuccess) e = cudaMalloc(&m->stats, (2 * T + static_cast<size_t>(cfg->max_batch)) * 4);
+  if (e == cudaSuccess && cfg->arch == SGPT_ARCH_GPTJ) {
+    // create_sinusoidal_positions, HF:gptj/modeling_gptj.py:45-48: angle(p, i) = p * 10000^(-2i/rotary_dim), fp32
+    const int half = cfg->rotary_dim / 2;
+    std::vector<float> tab(static_cast<size_t>(cfg->max_pos) * half * 2);
+    for (int p = 0; p < cfg->max_pos; ++p)
+      for (int i = 0; i < half; ++i) {
+        const float inv_freq = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / static_cast<float>(cfg->rotary_dim));
+        const float ang = static_cast<float>(p) * inv_freq;
+        tab[(static_cast<size_t>(p) * half + i) * 2 + 0] = static_cast<float>(cos(static_cast<double>(ang)));
+        tab[(static_cast<size_t>(p) * half + i) * 2 + 1] = static_cast<float>(sin(static_cast<double>(ang)));
+      }
+    e = cudaMalloc(&m->rotary, tab.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(m->rotary, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess && cfg->arch == SGPT_ARCH_BLOOM) {
+    const std::vector<float> s = alibi_slopes(cfg->n_head);
+    e = cudaMalloc(&m->alibi, s.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(m->alibi, s.data(), s.size() * 4, cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     set_error("sgpt_model_create: workspace allocation failed: %s", cudaGetErrorString(e));
     sgpt_model_destroy(m);
@@ -86,12 +132,14 @@ extern "C" void sgpt_model_destroy(sgpt_model_t m) {
   cudaFree(m->attn);
   cudaFree(m->ffn);
   cudaFree(m->stats);
+  cudaFree(m->rotary);
+  cudaFree(m->alibi);
   delete m;
 }
 
-#define SGPT_TRY(call)            \
-  do {                            \
-    int _rc = (call);             \
+#define SGPT_TRY(call)              \
+  do {                              \
+    int _rc = (call);               \
     if (_rc != SGPT_OK) return _rc; \
   } while (0)
 
@@ -103,28 +151,52 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
   SGPT_REQUIRE(B >= 0 && T >= 0, "sgpt_encode: negative sizes");
   SGPT_REQUIRE(T <= c.max_tokens && B <= c.max_batch, "sgpt_encode: batch (B=%d, T=%d) exceeds workspace (B<=%d, T<=%d)",
                B, T, c.max_batch, c.max_tokens);
-  SGPT_REQUIRE(max_seqlen <= c.max_pos, "sgpt_encode: max_seqlen %d exceeds max_position_embeddings %d", max_seqlen,
-               c.max_pos);
+  SGPT_REQUIRE(c.arch == SGPT_ARCH_BLOOM || max_seqlen <= c.max_pos,
+               "sgpt_encode: max_seqlen %d exceeds max_position_embeddings %d", max_seqlen, c.max_pos);
   if (layer_idx < 0) layer_idx += c.n_layer + 1;
   SGPT_REQUIRE(layer_idx >= 0 && layer_idx <= c.n_layer, "sgpt_encode: layer index out of range for %d hidden states",
                c.n_layer + 1);
   if (B == 0) return SGPT_OK;
-  const int d = c.d_model, H = c.n_head, hd = d / H;
+  const int d = c.d_model, H = c.n_head, hd = d / H, ff = c.d_ff;
+  const float inv_sqrt_hd = 1.0f / sqrtf(static_cast<float>(hd));
   m->last_T = T;
 
-  SGPT_TRY(sgpt_embed_tokens(ids, pos, m->w.wte, m->w.wpe, m->resid, T, d, c.vocab, c.max_pos, stream));
+  SGPT_TRY(sgpt_embed_tokens(ids, pos, m->w.wte, c.arch == SGPT_ARCH_GPT_NEO ? m->w.wpe : nullptr, m->resid, T, d,
+                             c.vocab, c.max_pos, stream));
+  if (c.arch == SGPT_ARCH_BLOOM)
+    SGPT_TRY(sgpt_layernorm_f32_inplace(m->resid, m->w.emb_ln_g, m->w.emb_ln_b, T, d, c.ln_eps, stream));
   const int n_run = layer_idx;  // hidden_states[i] is the input of block i; hidden_states[L] is ln_f(output of block L-1)
   for (int l = 0; l < n_run && l < c.n_layer; ++l) {
     const sgpt_layer_weights& lw = m->layers[l];
     SGPT_TRY(sgpt_layernorm(m->resid, lw.ln1_g, lw.ln1_b, m->xn, T, d, c.ln_eps, stream));
-    SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
-    const int window = (lw.local_attention && c.window > 0 && max_seqlen > c.window) ? c.window : 0;
-    SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, /*scale=*/1.0f, window, max_seqlen, 0, stream));
-    SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
-    SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
-    SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, c.d_ff, nullptr, T, c.d_ff, d, SGPT_EPI_GELU_BF16, stream));
-    SGPT_TRY(sgpt_linear(m->ffn, c.d_ff, lw.w_proj, c.d_ff, lw.b_proj, m->resid, d, m->resid, T, d, c.d_ff,
-                         SGPT_EPI_RESID_F32, stream));
+    if (c.arch == SGPT_ARCH_GPT_NEO) {
+      SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
+      const int window = (lw.local_attention && c.window > 0 && max_seqlen > c.window) ? c.window : 0;
+      SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, /*scale=*/1.0f, window, max_seqlen, nullptr, 0,
+                              stream));
+      SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
+      SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
+      SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
+      SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+                           stream));
+    } else if (c.arch == SGPT_ARCH_GPTJ) {
+      SGPT_TRY(sgpt_linear_qkv_rotary(m->xn, d, lw.w_qkv, m->qkv, pos, m->rotary, T, d, hd, c.rotary_dim, c.max_pos,
+                                      stream));
+      SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, inv_sqrt_hd, 0, max_seqlen, nullptr, 0, stream));
+      // both branches read the same ln_1 output and are accumulated into the residual stream (attn + mlp + residual)
+      SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
+      SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
+      SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+                           stream));
+    } else {  // BLOOM
+      SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
+      SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, inv_sqrt_hd, 0, max_seqlen, m->alibi, 0, stream));
+      SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
+      SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
+      SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
+      SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+                           stream));
+    }
   }
   const bool final_ln = (layer_idx == c.n_layer);
   SGPT_TRY(sgpt_pool(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr,

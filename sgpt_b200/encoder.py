@@ -48,15 +48,15 @@ def pack_ragged(input_ids, attention_mask) -> Tuple[np.ndarray, np.ndarray, np.n
 class Encoder:
     """GPT encoder + pooling on one GPU.
 
-    state_dict: tensors keyed like HF ``GPTNeoModel.state_dict()`` (``wte.weight``, ``h.0.ln_1.weight``, ...; a
-    ``transformer.`` prefix as in ``GPTNeoForCausalLM`` checkpoints is accepted).  Linear weights are stored in bf16,
+    state_dict: tensors keyed like the HF base model's ``state_dict()`` for the architecture — ``GPTNeoModel``
+    (``wte.weight``, ``h.0.attn.attention.q_proj.weight``, ...), ``GPTJModel`` (``h.0.attn.q_proj.weight``, ``mlp.fc_in``)
+    or ``BloomModel`` (``word_embeddings.weight``, ``h.0.self_attention.query_key_value.weight``, ...); a
+    ``transformer.`` prefix as in the ``*ForCausalLM`` checkpoints is accepted.  Linear weights are stored in bf16,
     LayerNorm parameters and biases in fp32.
     """
 
     def __init__(self, cfg: ModelConfig, state_dict: Dict[str, torch.Tensor], device="cuda:0", max_tokens: int = 32768,
                  max_batch: int = 1024):
-        if cfg.arch != "gpt_neo":
-            raise NotImplementedError(f"arch {cfg.arch!r}: only gpt_neo is built so far (GPT-J / BLOOM are next)")
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -72,47 +72,69 @@ class Encoder:
             self._keep.append(x)
             return x
 
+        def p32(name):
+            return dev(sd[name], torch.float32).data_ptr() if name in sd else None
+
+        def p16(t):
+            return dev(t, torch.bfloat16).data_ptr()
+
         with torch.cuda.device(self.device):
-            d = cfg.d_model
-            wte = dev(sd["wte.weight"], torch.bfloat16)
-            wpe = dev(sd["wpe.weight"], torch.bfloat16)
-            if wte.shape != (cfg.vocab, d) or wpe.shape != (cfg.max_pos, d):
-                raise ValueError(f"embedding shapes {tuple(wte.shape)}, {tuple(wpe.shape)} do not match the config")
+            d, H, hd = cfg.d_model, cfg.n_head, cfg.head_dim
             layers = (_lib.LayerWeightsC * cfg.n_layer)()
-            for i in range(cfg.n_layer):
-                p = f"h.{i}."
-                a = p + "attn.attention."
-                w_qkv = dev(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0),
-                            torch.bfloat16)
-                b_qkv = None
-                if (a + "q_proj.bias") in sd:
-                    b_qkv = dev(torch.cat([sd[a + "q_proj.bias"], sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0),
-                                torch.float32)
-                lw = layers[i]
-                lw.ln1_g = dev(sd[p + "ln_1.weight"], torch.float32).data_ptr()
-                lw.ln1_b = dev(sd[p + "ln_1.bias"], torch.float32).data_ptr()
-                lw.w_qkv = w_qkv.data_ptr()
-                lw.b_qkv = _lib.ptr(b_qkv)
-                lw.w_o = dev(sd[a + "out_proj.weight"], torch.bfloat16).data_ptr()
-                lw.b_o = dev(sd[a + "out_proj.bias"], torch.float32).data_ptr()
-                lw.ln2_g = dev(sd[p + "ln_2.weight"], torch.float32).data_ptr()
-                lw.ln2_b = dev(sd[p + "ln_2.bias"], torch.float32).data_ptr()
-                lw.w_fc = dev(sd[p + "mlp.c_fc.weight"], torch.bfloat16).data_ptr()
-                lw.b_fc = dev(sd[p + "mlp.c_fc.bias"], torch.float32).data_ptr()
-                lw.w_proj = dev(sd[p + "mlp.c_proj.weight"], torch.bfloat16).data_ptr()
-                lw.b_proj = dev(sd[p + "mlp.c_proj.bias"], torch.float32).data_ptr()
-                lw.local_attention = 1 if cfg.attention_layers[i] == "local" else 0
             mw = _lib.ModelWeightsC()
-            mw.wte = wte.data_ptr()
-            mw.wpe = wpe.data_ptr()
-            mw.lnf_g = dev(sd["ln_f.weight"], torch.float32).data_ptr()
-            mw.lnf_b = dev(sd["ln_f.bias"], torch.float32).data_ptr()
+            if cfg.arch == "gpt_neo":  # keys of HF GPTNeoModel.state_dict()
+                wte, wpe = dev(sd["wte.weight"], torch.bfloat16), dev(sd["wpe.weight"], torch.bfloat16)
+                if wte.shape != (cfg.vocab, d) or wpe.shape != (cfg.max_pos, d):
+                    raise ValueError(f"embedding shapes {tuple(wte.shape)}, {tuple(wpe.shape)} do not match the config")
+                mw.wte, mw.wpe = wte.data_ptr(), wpe.data_ptr()
+                for i in range(cfg.n_layer):
+                    p, lw = f"h.{i}.", layers[i]
+                    a = p + "attn.attention."
+                    lw.ln1_g, lw.ln1_b = p32(p + "ln_1.weight"), p32(p + "ln_1.bias")
+                    lw.w_qkv = p16(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0))
+                    if (a + "q_proj.bias") in sd:
+                        lw.b_qkv = dev(torch.cat([sd[a + "q_proj.bias"], sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0),
+                                       torch.float32).data_ptr()
+                    lw.w_o, lw.b_o = p16(sd[a + "out_proj.weight"]), p32(a + "out_proj.bias")
+                    lw.ln2_g, lw.ln2_b = p32(p + "ln_2.weight"), p32(p + "ln_2.bias")
+                    lw.w_fc, lw.b_fc = p16(sd[p + "mlp.c_fc.weight"]), p32(p + "mlp.c_fc.bias")
+                    lw.w_proj, lw.b_proj = p16(sd[p + "mlp.c_proj.weight"]), p32(p + "mlp.c_proj.bias")
+                    lw.local_attention = 1 if cfg.attention_layers[i] == "local" else 0
+                arch_id = _lib.ARCH_GPT_NEO
+            elif cfg.arch == "gptj":  # keys of HF GPTJModel.state_dict(); no attention biases, single LayerNorm per block
+                mw.wte = p16(sd["wte.weight"])
+                for i in range(cfg.n_layer):
+                    p, lw = f"h.{i}.", layers[i]
+                    lw.ln1_g, lw.ln1_b = p32(p + "ln_1.weight"), p32(p + "ln_1.bias")
+                    lw.w_qkv = p16(torch.cat([sd[p + "attn.q_proj.weight"], sd[p + "attn.k_proj.weight"],
+                                              sd[p + "attn.v_proj.weight"]], 0))
+                    lw.w_o = p16(sd[p + "attn.out_proj.weight"])
+                    lw.w_fc, lw.b_fc = p16(sd[p + "mlp.fc_in.weight"]), p32(p + "mlp.fc_in.bias")
+                    lw.w_proj, lw.b_proj = p16(sd[p + "mlp.fc_out.weight"]), p32(p + "mlp.fc_out.bias")
+                arch_id = _lib.ARCH_GPTJ
+            else:  # bloom: keys of HF BloomModel.state_dict()
+                mw.wte = p16(sd["word_embeddings.weight"])
+                mw.emb_ln_g, mw.emb_ln_b = p32("word_embeddings_layernorm.weight"), p32("word_embeddings_layernorm.bias")
+                for i in range(cfg.n_layer):
+                    p, lw = f"h.{i}.", layers[i]
+                    lw.ln1_g, lw.ln1_b = p32(p + "input_layernorm.weight"), p32(p + "input_layernorm.bias")
+                    # fused query_key_value rows are ordered per head [q(hd) | k(hd) | v(hd)] (HF:bloom:211-215);
+                    # regroup to [q_all | k_all | v_all], the layout the attention kernel reads
+                    wq = sd[p + "self_attention.query_key_value.weight"].view(H, 3, hd, d)
+                    bq = sd[p + "self_attention.query_key_value.bias"].view(H, 3, hd)
+                    lw.w_qkv = p16(wq.permute(1, 0, 2, 3).reshape(3 * d, d))
+                    lw.b_qkv = dev(bq.permute(1, 0, 2).reshape(3 * d), torch.float32).data_ptr()
+                    lw.w_o, lw.b_o = p16(sd[p + "self_attention.dense.weight"]), p32(p + "self_attention.dense.bias")
+                    lw.ln2_g, lw.ln2_b = p32(p + "post_attention_layernorm.weight"), p32(p + "post_attention_layernorm.bias")
+                    lw.w_fc, lw.b_fc = p16(sd[p + "mlp.dense_h_to_4h.weight"]), p32(p + "mlp.dense_h_to_4h.bias")
+                    lw.w_proj, lw.b_proj = p16(sd[p + "mlp.dense_4h_to_h.weight"]), p32(p + "mlp.dense_4h_to_h.bias")
+                arch_id = _lib.ARCH_BLOOM
+            mw.lnf_g, mw.lnf_b = p32("ln_f.weight"), p32("ln_f.bias")
             mw.layers = layers
             self._layers = layers
-            mc = _lib.ModelConfigC(arch=_lib.ARCH_GPT_NEO, n_layer=cfg.n_layer, d_model=d, n_head=cfg.n_head,
-                                   d_ff=cfg.d_ff, vocab=cfg.vocab, max_pos=cfg.max_pos, window=cfg.window,
-                                   rotary_dim=cfg.rotary_dim, ln_eps=cfg.ln_eps, max_tokens=self.max_tokens,
-                                   max_batch=self.max_batch)
+            mc = _lib.ModelConfigC(arch=arch_id, n_layer=cfg.n_layer, d_model=d, n_head=cfg.n_head, d_ff=cfg.d_ff,
+                                   vocab=cfg.vocab, max_pos=cfg.max_pos, window=cfg.window, rotary_dim=cfg.rotary_dim,
+                                   ln_eps=cfg.ln_eps, max_tokens=self.max_tokens, max_batch=self.max_batch)
             handle = C.c_void_p()
             _lib.check(self._lib.sgpt_model_create(C.byref(mc), C.byref(mw), C.byref(handle)), "sgpt_model_create")
             self._handle = handle
@@ -170,7 +192,7 @@ class Encoder:
         if T > self.max_tokens or B > self.max_batch:
             raise ValueError(f"batch of {B} rows / {T} tokens exceeds the encoder workspace "
                              f"({self.max_batch} rows / {self.max_tokens} tokens)")
-        if max_len > self.cfg.max_pos:
+        if self.cfg.arch != "bloom" and max_len > self.cfg.max_pos:
             raise ValueError(f"sequence length {max_len} exceeds max_position_embeddings {self.cfg.max_pos}")
         n = 2 * T + B + 1
         slot = self._stage_idx

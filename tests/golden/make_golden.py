@@ -63,6 +63,53 @@ def hf_model(spec: NeoSpec, weights):
     return model.float().eval()
 
 
+def hf_gptj(spec, weights):
+    from transformers import GPTJConfig, GPTJModel
+
+    cfg = GPTJConfig(vocab_size=spec.vocab, n_positions=spec.max_pos, n_embd=spec.d_model, n_layer=spec.n_layer,
+                     n_head=spec.n_head, rotary_dim=spec.rotary_dim, n_inner=spec.d_ff, activation_function="gelu_new",
+                     resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0, layer_norm_epsilon=spec.ln_eps)
+    model = GPTJModel(cfg)
+    missing, unexpected = model.load_state_dict(weights, strict=False)
+    assert not unexpected, unexpected
+    assert all("embed_positions" in k or "attn.bias" in k or "masked_bias" in k for k in missing), missing
+    assert model.config._attn_implementation == "eager"
+    return model.float().eval()
+
+
+def hf_bloom(spec, weights):
+    from transformers import BloomConfig, BloomModel
+
+    cfg = BloomConfig(vocab_size=spec.vocab, hidden_size=spec.d_model, n_layer=spec.n_layer, n_head=spec.n_head,
+                      layer_norm_epsilon=spec.ln_eps, hidden_dropout=0.0, attention_dropout=0.0)
+    model = BloomModel(cfg)
+    missing, unexpected = model.load_state_dict(weights, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    assert model.config._attn_implementation == "eager"
+    return model.float().eval()
+
+
+def run_family_case(name, model, spec_array, ids, mask, d_model):
+    """HF model (GPT-J / BLOOM) + the reference's Pooling.py -> fixture with hidden states and pooled embeddings."""
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask, output_hidden_states=True)
+    hs = out.hidden_states
+    assert torch.equal(hs[-1], out.last_hidden_state)
+    Pooling = load_by_path("ref_pooling", os.path.join(REF_ST, "models", "Pooling.py")).Pooling
+    pooled = {}
+    for mode, kw in (("weightedmean", dict(pooling_mode_weightedmean_tokens=True)),
+                     ("mean", dict(pooling_mode_mean_tokens=True))):
+        kwargs = dict(pooling_mode_cls_token=False, pooling_mode_max_tokens=False, pooling_mode_mean_tokens=False)
+        kwargs.update(kw)
+        pooled[mode] = Pooling(d_model, **kwargs)({"token_embeddings": hs[-1].clone(), "attention_mask": mask})[
+            "sentence_embedding"].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), input_ids=ids.numpy().astype(np.int32),
+                        attention_mask=mask.numpy().astype(np.int8), pooled_weightedmean=pooled["weightedmean"],
+                        pooled_mean=pooled["mean"], hidden_states=np.stack([h.numpy() for h in hs]),
+                        weight_seed=np.int32(0), spec=spec_array)
+    print(name, hs[-1].shape)
+
+
 def ragged_batch(B, S, vocab, seed, pad_id):
     g = torch.Generator().manual_seed(seed)
     lens = torch.randint(1, S + 1, (B,), generator=g)
@@ -138,3 +185,16 @@ if __name__ == "__main__":
     # BASELINE.json configs[0]: SGPT-125M-weightedmean, 32 sentences, seq_len 64
     run_case("neo_125m_b32_s64", NeoSpec(), B=32, S=64, seed=1234, keep_hidden=False)
     run_scoring()
+    # GPT-J (SGPT-5.8B family) and BLOOM (sgpt-bloom-7b1 family), tiny configs
+    from oracle import bloom as obloom
+    from oracle import gptj as ogptj
+
+    js = ogptj.GPTJSpec(n_layer=3, d_model=256, n_head=2, d_ff=1024, vocab=1000, max_pos=128, rotary_dim=32)
+    ids, mask = ragged_batch(5, 40, js.vocab, seed=21, pad_id=999)
+    run_family_case("gptj_tiny", hf_gptj(js, ogptj.init_weights(js, 0)),
+                    np.array([js.n_layer, js.d_model, js.n_head, js.d_ff, js.vocab, js.max_pos, js.rotary_dim], np.int32),
+                    ids, mask, js.d_model)
+    bs = obloom.BloomSpec(n_layer=3, d_model=256, n_head=4, vocab=1000)
+    ids, mask = ragged_batch(5, 40, bs.vocab, seed=22, pad_id=3)
+    run_family_case("bloom_tiny", hf_bloom(bs, obloom.init_weights(bs, 0)),
+                    np.array([bs.n_layer, bs.d_model, bs.n_head, bs.vocab], np.int32), ids, mask, bs.d_model)

@@ -150,7 +150,7 @@ static void test_linear(int M, int N, int K, int epi, int check_rows) {
 
 // ---------------------------------------------------------------------------------------------------------------
 static void attention_ref(const std::vector<float>& qkv, std::vector<float>& out, const std::vector<int>& cu, int H,
-                          int hd, float scale, int window) {
+                          int hd, float scale, int window, const std::vector<float>* alibi = nullptr) {
   const int B = (int)cu.size() - 1, d = H * hd;
   const size_t ld = 3 * (size_t)d;
   std::vector<double> p;
@@ -165,6 +165,7 @@ static void attention_ref(const std::vector<float>& qkv, std::vector<float>& out
           double s = 0;
           for (int e = 0; e < hd; ++e) s += (double)qkv[t * ld + h * hd + e] * qkv[kt * ld + d + h * hd + e];
           s *= scale;
+          if (alibi) s += (*alibi)[h] * (kt - cu[b]);
           p[kt - lo] = s;
           mx = std::max(mx, s);
         }
@@ -180,8 +181,12 @@ static void attention_ref(const std::vector<float>& qkv, std::vector<float>& out
   }
 }
 
-static void test_attention(const std::vector<int>& lens, int H, int hd, float scale, int window, float qk_sd) {
+static void test_attention(const std::vector<int>& lens, int H, int hd, float scale, int window, float qk_sd,
+                           bool use_alibi = false) {
   const int B = (int)lens.size();
+  std::vector<float> slopes(H);
+  for (int h = 0; h < H; ++h) slopes[h] = powf(2.f, -8.f * (h + 1) / H);
+  float* dalibi = use_alibi ? to_dev(slopes) : nullptr;
   std::vector<int> cu(B + 1, 0);
   int maxlen = 0;
   for (int b = 0; b < B; ++b) { cu[b + 1] = cu[b] + lens[b]; maxlen = std::max(maxlen, lens[b]); }
@@ -193,7 +198,7 @@ static void test_attention(const std::vector<int>& lens, int H, int hd, float sc
   auto* dout = dalloc<__nv_bfloat16>((size_t)T * d);
   auto* dout2 = dalloc<__nv_bfloat16>((size_t)T * d);
   std::vector<float> ref((size_t)T * d);
-  attention_ref(qkv, ref, cu, H, hd, scale, window);
+  attention_ref(qkv, ref, cu, H, hd, scale, window, use_alibi ? &slopes : nullptr);
   for (int impl = 1; impl >= 0; --impl) {
     __nv_bfloat16* o = impl ? dout2 : dout;
     CK(cudaMemset(o, 0xff, (size_t)T * d * 2));
@@ -201,7 +206,7 @@ static void test_attention(const std::vector<int>& lens, int H, int hd, float sc
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0));
-    SG(sgpt_attention(dqkv, o, dcu, B, T, H, hd, scale, window, maxlen, impl, 0));
+    SG(sgpt_attention(dqkv, o, dcu, B, T, H, hd, scale, window, maxlen, dalibi, impl, 0));
     CK(cudaEventRecord(e1));
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -497,6 +502,7 @@ int main(int argc, char** argv) {
     test_attention({130, 64, 300}, 2, 128, 0.0883883f, 0, 1.0f);
     test_attention({300, 77}, 2, 256, 0.0625f, 0, 1.0f);
     test_attention({700, 513}, 1, 64, 0.125f, 256, 1.0f);
+    test_attention({300, 41, 128}, 4, 128, 0.0883883f, 0, 1.0f, /*alibi=*/true);  // BLOOM-style
   }
   if (want("search")) {
     test_scores_topk(4, 1000, 64, 10);

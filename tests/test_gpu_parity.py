@@ -278,3 +278,39 @@ def test_sentence_encoder_encode_signature(tiny_encoder):
     de = wrapped.encode_corpus([{"title": "a", "text": "b"}], batch_size=4)
     assert qe.shape == de.shape == (1, spec.d_model) and not np.allclose(qe, de)
     st.encoder.close()
+
+
+# --- GPT-J (SGPT-5.8B family, BASELINE configs[3]) and BLOOM (sgpt-bloom-7b1, configs[4]) encoders --------------------
+@pytest.mark.parametrize("name", ["gptj_tiny", "bloom_tiny"])
+def test_gptj_bloom_pooled_embeddings_vs_reference_fixture(golden_dir, name):
+    """Tiny GPT-J (rotary q/k in the GEMM epilogue, parallel attn+MLP residual, hd 128) and BLOOM (ALiBi attention,
+    embedding LayerNorm, per-head fused qkv regrouped at load) vs fixtures produced by HF GPTJModel / BloomModel +
+    the reference's Pooling.py."""
+    from oracle import bloom, gptj
+    from sgpt_b200 import Encoder, ModelConfig
+
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    a = [int(x) for x in z["spec"]]
+    if name.startswith("gptj"):
+        spec = gptj.GPTJSpec(n_layer=a[0], d_model=a[1], n_head=a[2], d_ff=a[3], vocab=a[4], max_pos=a[5], rotary_dim=a[6])
+        w = gptj.init_weights(spec, seed=int(z["weight_seed"]))
+        cfg = ModelConfig(arch="gptj", n_layer=a[0], d_model=a[1], n_head=a[2], d_ff=a[3], vocab=a[4], max_pos=a[5],
+                          rotary_dim=a[6])
+    else:
+        spec = bloom.BloomSpec(n_layer=a[0], d_model=a[1], n_head=a[2], vocab=a[3])
+        w = bloom.init_weights(spec, seed=int(z["weight_seed"]))
+        cfg = ModelConfig(arch="bloom", n_layer=a[0], d_model=a[1], n_head=a[2], d_ff=4 * a[1], vocab=a[3], max_pos=1 << 20)
+    enc = Encoder(cfg, w, device="cuda:0", max_tokens=2048, max_batch=16)
+    ids, mask = z["input_ids"], z["attention_mask"]
+    got = enc.encode_tokens(ids, mask, method="weightedmean").cpu()
+    assert min_row_cosine(got, z["pooled_weightedmean"]) > 1 - COS_TOL
+    got = enc.encode_tokens(ids, mask, method="mean").cpu()
+    assert min_row_cosine(got, z["pooled_mean"]) > 1 - COS_TOL
+    # per-token residual stream -> ln_f on the host vs HF's last hidden state
+    enc.encode_tokens(ids, mask)
+    resid = enc.last_residual().cpu()
+    h = gpt_neo.layer_norm(resid, w["ln_f.weight"], w["ln_f.bias"], spec.ln_eps)
+    ref = torch.from_numpy(z["hidden_states"][-1])[torch.from_numpy(mask).bool()]
+    cos = torch.nn.functional.cosine_similarity(h.double(), ref.double(), dim=1)
+    assert cos.min().item() > 1 - COS_TOL
+    enc.close()

@@ -150,3 +150,34 @@ def test_search_embeddings_merge_equals_global_topk():
         assert len(res[qid]) <= k + 1
     with pytest.raises(ValueError):
         search.search_embeddings(qids, q, cids, c, k, "euclid")
+
+
+# --- GPT-J (SGPT-5.8B family) and BLOOM (sgpt-bloom-7b1 family) oracles vs HF GPTJModel / BloomModel fixtures ---------
+def _family(golden_dir, name):
+    from oracle import bloom, gptj
+
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    a = [int(x) for x in z["spec"]]
+    if name.startswith("gptj"):
+        spec = gptj.GPTJSpec(n_layer=a[0], d_model=a[1], n_head=a[2], d_ff=a[3], vocab=a[4], max_pos=a[5], rotary_dim=a[6])
+        mod = gptj
+    else:
+        spec = bloom.BloomSpec(n_layer=a[0], d_model=a[1], n_head=a[2], vocab=a[3])
+        mod = bloom
+    w = mod.init_weights(spec, seed=int(z["weight_seed"]))
+    return z, spec, mod, w
+
+
+@pytest.mark.parametrize("name", ["gptj_tiny", "bloom_tiny"])
+def test_gptj_bloom_oracle_matches_hf(golden_dir, name):
+    """Restated GPT-J (rotary, parallel residual) / BLOOM (ALiBi, embedding LayerNorm, fused qkv) forward == HF model."""
+    z, spec, mod, w = _family(golden_dir, name)
+    ids = torch.from_numpy(z["input_ids"]).long()
+    mask = torch.from_numpy(z["attention_mask"]).long()
+    with torch.no_grad():
+        hs = mod.forward(spec, w, ids, mask)
+    ref = torch.from_numpy(z["hidden_states"])
+    for i in range(len(hs)):
+        assert (hs[i] - ref[i]).abs()[mask.bool()].max().item() < 2e-5, i
+    np.testing.assert_allclose(pooling.weighted_mean(hs[-1], mask).numpy(), z["pooled_weightedmean"], atol=2e-5)
+    np.testing.assert_allclose(pooling.mean(hs[-1], mask).numpy(), z["pooled_mean"], atol=2e-5)
