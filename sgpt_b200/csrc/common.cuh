@@ -119,6 +119,36 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// Tile prefetch into L2 only (no smem, no barrier): turns the DRAM latency of a later tma_load_2d into an L2 hit.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* desc, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// Multicast tile load: the tile lands at the same smem offset in every CTA of the cluster whose bit is set in
+// cta_mask, and each destination CTA's mbarrier (same offset) receives the complete_tx.  One L2 read feeds all of them.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* desc, uint64_t* bar, int c0,
+                                                      int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+      : "memory");
+}
+
+// thread-block cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // smem tile -> global (bulk async-group completion).  Coordinates as for loads; out-of-range rows/columns are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* desc, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -183,6 +213,15 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// Same, arriving on the barrier at this smem offset in every CTA of the cluster selected by cta_mask.
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.

@@ -8,7 +8,7 @@
 
 namespace sgpt {
 
-template <int BN, class Epi>
+template <int BN, class Epi, int CL = 1>
 static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K,
                        const typename Epi::Params& ep, cudaStream_t stream, int cat = kCatGemm,
                        TileMap tmap = TileMap()) {
@@ -17,25 +17,50 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   int rc = make_tma_2d_bf16(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
                             kGemmBM, kGemmBK);
   if (rc != SGPT_OK) return rc;
-  rc = make_tma_2d_bf16(&tb, b, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), BN,
+  // with a 2-CTA cluster each CTA fetches (and multicasts) half of the B tile
+  rc = make_tma_2d_bf16(&tb, b, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), BN / CL,
                         kGemmBK);
   if (rc != SGPT_OK) return rc;
-  auto kern = gemm_bf16_tn_kernel<BN, Epi>;
+  auto kern = gemm_bf16_tn_kernel<BN, Epi, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  const int m_tiles = ((M + kGemmBM - 1) / kGemmBM + CL - 1) / CL;
   const int n_tiles = tmap.count((N + BN - 1) / BN);
-  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;  // tile groups (one per cluster iteration)
   if (tiles == 0) return SGPT_OK;
-  int grid = sm_count();
-  if (tiles < grid) grid = static_cast<int>(tiles);
+  long long clusters = sm_count() / CL;
+  if (tiles < clusters) clusters = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
+  cfg.blockDim = dim3(128 + 32 * Epi::kEpiWarps);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CL > 1) ? 1 : 0;
   LaunchScope _ls(cat, stream);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep, tmap);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep, tmap));
   return SGPT_OK;
+}
+
+// nn.Linear dispatch: tile width by wave efficiency; 2-CTA clusters (shared B operand) whenever there are at least two
+// M-tiles — the encoder GEMMs are L2->SM bandwidth bound and the cluster cuts that traffic by a third.
+template <class Epi>
+static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
+                         const typename Epi::Params& p, int bn, cudaStream_t stream) {
+  const bool pair = M > kGemmBM;
+  if (bn == 256)
+    return pair ? launch_gemm<256, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream)
+                : launch_gemm<256, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream);
+  return pair ? launch_gemm<128, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream)
+              : launch_gemm<128, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream);
 }
 
 // Tile-width heuristic: BN=256 halves the smem bytes the tensor core must read per FLOP, but with few tiles the
@@ -49,7 +74,7 @@ static int pick_bn(int M, int N) {
     const double useful = static_cast<double>(M) * N;
     return useful / (static_cast<double>(waves) * sms * kGemmBM * bn);
   };
-  return (eff(256) * 1.08 >= eff(128)) ? 256 : 128;
+  return (eff(256) * 1.25 >= eff(128)) ? 256 : 128;
 }
 
 int launch_filter_candidates(const void* Q, const void* C, const float* q_scale, const float* c_scale,
@@ -86,12 +111,10 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
       if (rc != SGPT_OK) return rc;
       if (epilogue == SGPT_EPI_BF16) {
         EpiBiasActBF16<false>::Params p{om, bias};
-        return bn == 256 ? launch_gemm<256, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream)
-                         : launch_gemm<128, EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, stream);
+        return launch_linear<EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
       }
       EpiBiasActBF16<true>::Params p{om, bias};
-      return bn == 256 ? launch_gemm<256, EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, stream)
-                       : launch_gemm<128, EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, stream);
+      return launch_linear<EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
     }
     case SGPT_EPI_RESID_F32: {
       SGPT_REQUIRE(resid != nullptr, "sgpt_linear: SGPT_EPI_RESID_F32 needs resid");
@@ -107,8 +130,27 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
                                static_cast<uint64_t>(ldo), 32, 32);
       if (rc != SGPT_OK) return rc;
       EpiResidualF32::Params p{om, bias};
-      return bn == 256 ? launch_gemm<256, EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, stream)
-                       : launch_gemm<128, EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, stream);
+      return launch_linear<EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+    }
+    case 102:
+    case 103:
+    case 104: {  // profiling aids: bf16 epilogue without the TMA store (102) / without the smem-reuse wait (103)
+      CUtensorMap om;
+      int rc = make_tma_2d_bf16(&om, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N),
+                                static_cast<uint64_t>(ldo), 32, 64);
+      if (rc != SGPT_OK) return rc;
+      OpTmaBiasActBF16<false>::Params p{om, bias};
+      if (epilogue == 102) return launch_linear<EpiTma<OpTmaBiasActBF16<false>, 1>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+      if (epilogue == 104) return launch_linear<EpiTma<OpTmaBiasActBF16<false>, 3>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+      return launch_linear<EpiTma<OpTmaBiasActBF16<false>, 2>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+    }
+    case 100: {  // profiling aid: mainloop only
+      EpiDebugNull<false>::Params p{0};
+      return launch_linear<EpiDebugNull<false>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+    }
+    case 101: {  // profiling aid: mainloop + TMEM loads
+      EpiDebugNull<true>::Params p{0};
+      return launch_linear<EpiDebugNull<true>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
     }
     default:
       set_error("sgpt_linear: unknown epilogue %d", epilogue);
@@ -134,9 +176,7 @@ extern "C" int sgpt_linear_qkv_rotary(const void* x, int64_t ldx, const void* w_
                             64);
   if (rc != SGPT_OK) return rc;
   EpiRotaryBF16::Params p{om, pos, reinterpret_cast<const float2*>(cos_sin), M, d_model, head_dim, rotary_dim, max_pos};
-  return pick_bn(M, N) == 256
-             ? launch_gemm<256, EpiRotaryBF16>(x, ldx, w_qkv, d_model, M, N, d_model, p, stream)
-             : launch_gemm<128, EpiRotaryBF16>(x, ldx, w_qkv, d_model, M, N, d_model, p, stream);
+  return launch_linear<EpiRotaryBF16>(x, ldx, w_qkv, d_model, M, N, d_model, p, pick_bn(M, N), stream);
 }
 
 extern "C" int sgpt_scores(const void* Q, const void* C, const float* q_scale, const float* c_scale, float* scores,

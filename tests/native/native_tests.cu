@@ -494,6 +494,32 @@ int main(int argc, char** argv) {
     test_linear(32768, 3072, 768, SGPT_EPI_GELU_BF16, 4);
     test_linear(32768, 768, 3072, SGPT_EPI_RESID_F32, 4);
   }
+  if (!strcmp(only, "nullepi")) {  // timing only: mainloop without / with TMEM loads in the epilogue
+    for (int epi = 100; epi <= 104; ++epi)
+      for (int K : {768}) {
+        const int M = 32768, N = 2304;
+        auto x = randn((size_t)M * K, 1.0f), w = randn((size_t)N * K, 0.05f);
+        auto xb = to_bf16(x), wb = to_bf16(w);
+        auto *dx = to_dev(xb), *dw = to_dev(wb);
+        auto* dout = dalloc<__nv_bfloat16>((size_t)M * N);
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        SG(sgpt_linear(dx, K, dw, K, nullptr, dout, N, nullptr, M, N, K, epi, 0));
+        CK(cudaEventRecord(e0));
+        for (int it = 0; it < 5; ++it) SG(sgpt_linear(dx, K, dw, K, nullptr, dout, N, nullptr, M, N, K, epi, 0));
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        const double ms = time_ms(e0, e1) / 5;
+        printf("INFO epi=%d M=%d N=%d K=%d: %.3f ms  %.1f TFLOP/s\n", epi, M, N, K, ms, 2.0 * M * N * K / (ms * 1e9));
+        cudaFree(dx); cudaFree(dw); cudaFree(dout);
+      }
+  }
+  if (!strcmp(only, "sweep")) {  // which dimension limits the GEMM rate?
+    const int shapes[][3] = {{32768, 2304, 768}, {32768, 2304, 2048}, {16384, 8192, 768},  {16384, 2304, 768},
+                             {32768, 8192, 768}, {8192, 8192, 2048},  {32768, 2304, 3072}, {65536, 2304, 768},
+                             {32768, 2048, 768}, {32768, 2048, 1024}};
+    for (auto& sh : shapes) test_linear(sh[0], sh[1], sh[2], SGPT_EPI_BF16, 2);
+  }
   if (want("attention")) {
     test_attention({128}, 1, 64, 1.0f, 0, 0.3f);
     test_attention({1, 37, 128, 5, 64, 100}, 3, 64, 1.0f, 0, 0.3f);
