@@ -25,21 +25,27 @@ namespace sgpt {
 constexpr int kAttnTile = 128;
 constexpr int kSubBytes = kAttnTile * 128;  // one [128 rows x 64 bf16] sub-tile
 
-template <int HD>
+// kSingle: every sequence of the batch fits one 128-key tile (max_seqlen <= 128 — all of the reference's NLI models
+// and BASELINE configs 1-2).  Then Q and K are dead once S = Q K^T has been read, so P reuses their smem, and O
+// reuses S's TMEM columns: 48 KB smem / 128 TMEM columns per CTA at hd = 64, i.e. FOUR co-resident CTAs per SM whose
+// load / MMA / softmax / store phases overlap each other (the general variant keeps separate buffers: 2 CTAs per SM).
+template <int HD, bool kSingle>
 struct AttnCfg {
   static constexpr int kSub = HD / 64;
   static constexpr int kQBytes = kSub * kSubBytes;
   static constexpr int kPBytes = 2 * kSubBytes;
-  static constexpr int kSmemBytes = 1024 + 3 * kQBytes + kPBytes + 64;
-  static constexpr int kTmemCols = (128 + HD <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = 1024 + 3 * kQBytes + (kSingle ? 0 : kPBytes) + 64;
+  static constexpr int kTmemNeed = kSingle ? (HD > 128 ? HD : 128) : 128 + HD;
+  static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);
+  static_assert(!kSingle || 2 * kQBytes >= kPBytes, "P must fit into the Q|K region");
 };
 
-template <int HD>
+template <int HD, bool kSingle>
 __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv,
                                                            __nv_bfloat16* __restrict__ out,
                                                            const int32_t* __restrict__ cu, int H, float sl2,
                                                            int window, const float* __restrict__ alibi) {
-  using Cfg = AttnCfg<HD>;
+  using Cfg = AttnCfg<HD, kSingle>;
   const int qt = blockIdx.x, b = blockIdx.y, h = blockIdx.z;
   const int seq0 = __ldg(cu + b);
   const int len = __ldg(cu + b + 1) - seq0;
@@ -51,8 +57,8 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kQBytes;
   uint8_t* sV = sK + Cfg::kQBytes;
-  uint8_t* sP = sV + Cfg::kQBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint8_t* sP = kSingle ? sQ : sV + Cfg::kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::kQBytes + (kSingle ? 0 : Cfg::kPBytes));
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k = bars + 1;
   uint64_t* bar_v = bars + 2;
@@ -65,8 +71,8 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   const int d = H * HD;
 
   const int lo_pos = (window > 0) ? max(0, qp0 - window + 1) : 0;
-  const int j_lo = lo_pos / kAttnTile;
-  const int j_hi = qt;  // len > qp0, so the diagonal tile always exists
+  const int j_lo = kSingle ? 0 : lo_pos / kAttnTile;
+  const int j_hi = kSingle ? 0 : qt;  // len > qp0, so the diagonal tile always exists
 
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tS = tmem_base;
-  const uint32_t tO = tmem_base + 128;
+  const uint32_t tO = kSingle ? tmem_base : tmem_base + 128;
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
 
   if (tid == 0) {
@@ -109,6 +115,12 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   const int qpos = qp0 + tid;
   const int vis_hi = min(qpos, len - 1);
   const int vis_lo = (window > 0) ? (qpos - window + 1) : 0;
+  // visibility bounds of this WARP's 32 query rows: a 32-key chunk entirely inside [w_lo_max, w_hi_min] needs no
+  // per-element mask, a chunk entirely outside [w_lo_min, w_hi_max] contributes nothing (causal: half of the diagonal
+  // tile on average)
+  const int wq0 = qp0 + warp * 32;
+  const int w_hi_min = min(wq0, len - 1), w_hi_max = min(wq0 + 31, len - 1);
+  const int w_lo_max = (window > 0) ? (wq0 + 31 - window + 1) : 0, w_lo_min = (window > 0) ? (wq0 - window + 1) : 0;
   float m_run = -INFINITY, l_run = 0.f;
 
   for (int j = j_lo; j <= j_hi; ++j) {
@@ -131,29 +143,37 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     mbar_wait(bar_s, ph);
     tc_fence_after();
     // K buffer is free again: prefetch K_{j+1} under the softmax
-    if (tid == 0 && j < j_hi) {
+    if (!kSingle && tid == 0 && j < j_hi) {
       mbar_expect_tx(bar_k, Cfg::kQBytes);
       for (int s = 0; s < Cfg::kSub; ++s)
         tma_load_2d(sK + s * kSubBytes, &tma_qkv, bar_k, d + h * HD + 64 * s, seq0 + (j + 1) * kAttnTile);
     }
     __syncwarp();
 
-    // ---- online softmax over this row's 128 scores ----
+    // ---- online softmax over this row's 128 scores (pass 1: row maximum) ----
     const int kv0 = j * kAttnTile;
     float mx = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
+      const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
+      if (c_lo > w_hi_max || c_hi < w_lo_min) continue;  // nothing visible for any row of this warp (warp-uniform)
       uint32_t v[32];
       tmem_ld_32x32(tS + lane_off + c * 32, v);
       tmem_ld_wait();
+      if (c_hi <= w_hi_min && c_lo >= w_lo_max && slope2 == 0.f) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int kp = kv0 + c * 32 + i;
-        const float s = fmaf(__uint_as_float(v[i]), sl2, slope2 * static_cast<float>(kp));
-        if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, s);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));  // scale applied after the reduction
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kp = c_lo + i;
+          const float s = (slope2 == 0.f) ? __uint_as_float(v[i])
+                                          : fmaf(__uint_as_float(v[i]), sl2, slope2 * static_cast<float>(kp)) / sl2;
+          if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, s);
+        }
       }
     }
-    const float m_new = fmaxf(m_run, mx);
+    const float m_new = fmaxf(m_run, mx * sl2);  // sl2 > 0
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
     const float alpha = exp2f(m_run - m_use);
     float lsum = 0.f;
@@ -163,29 +183,45 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
       tc_fence_after();
       __syncwarp();
     }
+    // ---- pass 2: p = exp2(s * sl2 (+ alibi) - m), P -> bf16 -> swizzled smem ----
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tS + lane_off + c * 32, v);
-      tmem_ld_wait();
+      const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
       uint32_t pk[16];
+      if (c_lo > w_hi_max || c_hi < w_lo_min) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int kp = kv0 + c * 32 + 2 * i;
-        float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, slope2 * static_cast<float>(kp)) - m_use);
-        float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, slope2 * static_cast<float>(kp + 1)) - m_use);
-        if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
-        if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
-        lsum += p0 + p1;
-        pk[i] = pack_bf16(p0, p1);
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      } else {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (c_hi <= w_hi_min && c_lo >= w_lo_max && slope2 == 0.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
+            const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int kp = c_lo + 2 * i;
+            float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, slope2 * static_cast<float>(kp)) - m_use);
+            float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, slope2 * static_cast<float>(kp + 1)) - m_use);
+            if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
+            if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        }
       }
       // P[row, kv 32c .. 32c+31] -> sub-tile (c >> 1), 16-B chunks 4*(c&1) .. +3, XOR-swizzled with (row & 7)
-      uint8_t* prow = sP + (c >> 1) * kSubBytes + tid * 128;
+      const uint32_t prow = smem_u32(sP) + (c >> 1) * kSubBytes + tid * 128;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int chunk = ((c & 1) * 4 + q4) ^ (tid & 7);
-        *reinterpret_cast<uint4*>(prow + chunk * 16) =
-            make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        sts_v4(prow + chunk * 16, pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       }
     }
     l_run = l_run * alpha + lsum;
@@ -203,11 +239,10 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
         tmem_st_32x32(tO + lane_off + c * 32, v);
       }
       tmem_st_wait();
-      // V buffer is free (previous P V done): fetch V_j now (it could not be prefetched earlier)
     }
     fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();           // all S reads and P writes of the CTA are done (kSingle: S columns become O)
     // ---- O += P V_j ----
     if (tid == 0) {
       tc_fence_after();
@@ -221,7 +256,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
         umma_bf16_ss(tO, da, db, idesc_o, (j > j_lo) || (kk != 0));
       }
       umma_commit(bar_o);
-      if (j < j_hi) {
+      if (!kSingle && j < j_hi) {
         // V buffer is reusable once this P V completes; wait for it, then prefetch V_{j+1} (lands during the next
         // tile's QK^T + softmax)
         mbar_wait(bar_o, ph);
@@ -318,14 +353,11 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const __nv_bfloat16
     out[static_cast<size_t>(t) * d + h * HD + lane * E + e] = __float2bfloat16_rn(o[e] / l);
 }
 
-template <int HD>
-static int launch_attention_tc(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale,
-                               int window, int max_seqlen, const float* alibi, cudaStream_t stream) {
-  using Cfg = AttnCfg<HD>;
-  CUtensorMap map;
-  int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
-  if (rc != SGPT_OK) return rc;
-  auto kern = attention_tc_kernel<HD>;
+template <int HD, bool kSingle>
+static int launch_attention_tc_impl(const CUtensorMap& map, void* out, const int32_t* cu, int B, int H, float scale,
+                                    int window, int max_seqlen, const float* alibi, cudaStream_t stream) {
+  using Cfg = AttnCfg<HD, kSingle>;
+  auto kern = attention_tc_kernel<HD, kSingle>;
   static bool attr_set = false;
   if (!attr_set) {
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -337,6 +369,17 @@ static int launch_attention_tc(const void* qkv, void* out, const int32_t* cu, in
   kern<<<grid, 128, Cfg::kSmemBytes, stream>>>(map, static_cast<__nv_bfloat16*>(out), cu, H, sl2, window, alibi);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
+}
+
+template <int HD>
+static int launch_attention_tc(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale,
+                               int window, int max_seqlen, const float* alibi, cudaStream_t stream) {
+  CUtensorMap map;
+  int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
+  if (rc != SGPT_OK) return rc;
+  if (max_seqlen <= kAttnTile)  // one key tile per sequence: compact variant, up to 4 CTAs per SM
+    return launch_attention_tc_impl<HD, true>(map, out, cu, B, H, scale, window, max_seqlen, alibi, stream);
+  return launch_attention_tc_impl<HD, false>(map, out, cu, B, H, scale, window, max_seqlen, alibi, stream);
 }
 
 template <int HD>
