@@ -110,10 +110,10 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
                                 static_cast<uint64_t>(ldo), 32, 64);
       if (rc != SGPT_OK) return rc;
       if (epilogue == SGPT_EPI_BF16) {
-        EpiBiasActBF16<false>::Params p{om, bias};
+        EpiBiasActBF16<false>::Params p{om, bias, out, static_cast<int>(ldo)};
         return launch_linear<EpiBiasActBF16<false>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
       }
-      EpiBiasActBF16<true>::Params p{om, bias};
+      EpiBiasActBF16<true>::Params p{om, bias, out, static_cast<int>(ldo)};
       return launch_linear<EpiBiasActBF16<true>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
     }
     case SGPT_EPI_RESID_F32: {
@@ -129,18 +129,20 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
       int rc = make_tma_2d_f32(&om, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N),
                                static_cast<uint64_t>(ldo), 32, 32);
       if (rc != SGPT_OK) return rc;
-      EpiResidualF32::Params p{om, bias};
+      EpiResidualF32::Params p{om, bias, out, static_cast<int>(ldo)};
       return launch_linear<EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, bn, stream);
     }
     case 102:
     case 103:
-    case 104: {  // profiling aids: bf16 epilogue without the TMA store (102) / without the smem-reuse wait (103)
+    case 104:
+    case 105: {  // profiling aids: bf16 epilogue without the TMA store (102) / without the smem-reuse wait (103)
       CUtensorMap om;
       int rc = make_tma_2d_bf16(&om, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N),
                                 static_cast<uint64_t>(ldo), 32, 64);
       if (rc != SGPT_OK) return rc;
-      OpTmaBiasActBF16<false>::Params p{om, bias};
+      OpTmaBiasActBF16<false>::Params p{om, bias, out, static_cast<int>(ldo)};
       if (epilogue == 102) return launch_linear<EpiTma<OpTmaBiasActBF16<false>, 1>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+      if (epilogue == 105) return launch_linear<EpiTma<OpTmaBiasActBF16<false>, 4>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
       if (epilogue == 104) return launch_linear<EpiTma<OpTmaBiasActBF16<false>, 3>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
       return launch_linear<EpiTma<OpTmaBiasActBF16<false>, 2>>(x, ldx, w, ldw, M, N, K, p, bn, stream);
     }
@@ -175,7 +177,8 @@ extern "C" int sgpt_linear_qkv_rotary(const void* x, int64_t ldx, const void* w_
   int rc = make_tma_2d_bf16(&om, qkv, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(N), 32,
                             64);
   if (rc != SGPT_OK) return rc;
-  EpiRotaryBF16::Params p{om, pos, reinterpret_cast<const float2*>(cos_sin), M, d_model, head_dim, rotary_dim, max_pos};
+  EpiRotaryBF16::Params p{om, pos, reinterpret_cast<const float2*>(cos_sin), M, d_model, head_dim, rotary_dim, max_pos,
+                          qkv, N};
   return launch_linear<EpiRotaryBF16>(x, ldx, w_qkv, d_model, M, N, d_model, p, pick_bn(M, N), stream);
 }
 

@@ -266,6 +266,16 @@ struct EpiTma {
       uint32_t o[8][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) Op::chunk(p, &v[j * (kCols / 8)], n + j * (kCols / 8), N, m0 + lane, o[j]);
+      if (kDebug == 4) {  // experiment: straight 16-byte global stores from the thread = row layout (no smem, no TMA)
+        if (m0 + lane < M) {
+          uint4* g = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out_ptr) +
+                                              (static_cast<size_t>(m0 + lane) * p.ldc + n) * Op::kElemBytes);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+        }
+        ++st.it;
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts_v4(row_addr + ((j ^ (lane & 7)) << 4), o[j][0], o[j][1], o[j][2], o[j][3]);
       if (kDebug != 3) fence_proxy_async_smem();
@@ -291,6 +301,8 @@ struct OpTmaBiasActBF16 {
   struct Params {
     CUtensorMap out_map;  // bf16 [M, N], box 32 rows x 64 cols, SWIZZLE_128B
     const float* bias;    // may be null
+    void* out_ptr;        // same tensor as out_map (direct-store variant)
+    int ldc;
   };
   // 8 consecutive columns starting at `col` -> 16 bytes
   static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, int /*row*/,
@@ -328,6 +340,8 @@ struct OpTmaRotaryBF16 {
     const int32_t* pos;      // [M] position of each token row
     const float2* table;     // [max_pos, rotary_dim/2] (cos, sin)
     int M, d_model, head_dim, rotary_dim, max_pos;
+    void* out_ptr;
+    int ldc;
   };
   static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, int row,
                                                uint32_t (&o)[4]) {
@@ -363,6 +377,8 @@ struct OpTmaResidAddF32 {
   struct Params {
     CUtensorMap out_map;  // fp32 [M, N], box 32 rows x 32 cols, SWIZZLE_128B
     const float* bias;    // may be null
+    void* out_ptr;
+    int ldc;
   };
   // 4 consecutive columns -> 16 bytes
   static __device__ __forceinline__ void chunk(const Params& p, const uint32_t* acc, int col, int N, int /*row*/,
@@ -566,7 +582,70 @@ struct OpFilterCandidates {
     }
   }
 };
-using EpiFilterCandidates = EpiStaged<OpFilterCandidates>;
+// Row-native threshold filter (the one the search uses).  In the accumulator's native layout thread r of a warp owns
+// query row r, i.e. ONE admission threshold and ONE candidate list: the compare needs no transpose, no shuffles and no
+// ballots.  Per 32-document chunk: scale, count the admitted scores (branch-free), reserve list space with one
+// atomicAdd per lane (32 different addresses, only when the warp has any hit), then predicated stores.  8 epilogue
+// warps (two per TMEM lane quarter, half the tile's documents each); no shared memory at all.
+struct EpiFilterRows {
+  using Params = OpFilterCandidates::Params;
+  using State = EpiNoState;
+  static constexpr int kEpiWarps = 8;
+  static __device__ __forceinline__ void init(State&, const Params&, int) {}
+  static __device__ __forceinline__ void finish(State&, const Params&, int) {}
+
+  template <int COLS>
+  static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int lane, uint32_t trow, float*,
+                                              int M, int N) {
+    if (m0 >= M) return;  // warp-uniform
+    const int q = m0 + lane;
+    const bool qok = q < M;
+    const float rs = (qok && p.row_scale) ? __ldg(p.row_scale + q) : 1.f;
+    const float tau = (qok && p.tau) ? __ldg(p.tau + q) : -INFINITY;
+    uint2* dst = p.cand + static_cast<long long>(qok ? q : 0) * p.cap;
+#pragma unroll 1
+    for (int c = 0; c < COLS; c += 32) {
+      const int n = n0 + c;
+      if (n >= N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(trow + c, v);
+      float cs[32];
+      if (p.col_scale != nullptr && n + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.col_scale + n) + i);  // same address in all lanes
+          cs[4 * i] = t.x; cs[4 * i + 1] = t.y; cs[4 * i + 2] = t.z; cs[4 * i + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cs[i] = (p.col_scale != nullptr) ? __ldg(p.col_scale + min(n + i, N - 1)) : 1.f;
+      }
+      tmem_ld_wait();
+      float x[32];
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float s = __uint_as_float(v[i]) * rs * cs[i];
+        s = (s != s) ? -1.f : s;  // XS:99 NaN -> -1
+        x[i] = s;
+        cnt += (qok && n + i < N && s > tau) ? 1 : 0;
+      }
+      if (__any_sync(0xffffffffu, cnt != 0)) {
+        long long k = 0;
+        if (cnt != 0) k = atomicAdd(p.count + q, cnt);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (qok && n + i < N && x[i] > tau) {
+            if (k < p.cap) dst[k] = make_uint2(__float_as_uint(x[i]), static_cast<uint32_t>(n + i));
+            ++k;
+          }
+        }
+      }
+    }
+  }
+};
+using EpiFilterCandidates = EpiFilterRows;
+
 
 template <bool kGelu>
 using EpiBiasActBF16 = EpiTma<OpTmaBiasActBF16<kGelu>>;

@@ -495,7 +495,7 @@ int main(int argc, char** argv) {
     test_linear(32768, 768, 3072, SGPT_EPI_RESID_F32, 4);
   }
   if (!strcmp(only, "nullepi")) {  // timing only: mainloop without / with TMEM loads in the epilogue
-    for (int epi = 100; epi <= 104; ++epi)
+    for (int epi = 100; epi <= 105; ++epi)
       for (int K : {768}) {
         const int M = 32768, N = 2304;
         auto x = randn((size_t)M * K, 1.0f), w = randn((size_t)N * K, 0.05f);
