@@ -314,3 +314,53 @@ def test_gptj_bloom_pooled_embeddings_vs_reference_fixture(golden_dir, name):
     cos = torch.nn.functional.cosine_similarity(h.double(), ref.double(), dim=1)
     assert cos.min().item() > 1 - COS_TOL
     enc.close()
+
+
+# --- full-width layers at reduced depth: the GEMM / attention shapes of the large configs ----------------------------
+def test_wide_gpt_neo_hd128_long_sequences_vs_oracle():
+    """SGPT-1.3B-width blocks (d 2048, 16 heads of 128, ff 8192) at depth 2, sequences up to 300 tokens: multi-tile
+    attention (online softmax across key tiles) and the GPT-Neo local window (256 < 300) on the second layer."""
+    from sgpt_b200 import Encoder
+
+    spec = gpt_neo.NeoSpec(n_layer=2, d_model=2048, n_head=16, d_ff=8192, vocab=2000, max_pos=512, window=256)
+    w = gpt_neo.init_weights(spec, seed=0)
+    for k in list(w):  # keep the un-scaled GPT-Neo logits at a sane spread for the wider model
+        if "q_proj" in k or "k_proj" in k:
+            w[k] = (w[k] * (768 / 2048) ** 0.5 * 0.7).to(torch.bfloat16).float()
+    enc = Encoder(_cfg_from_spec(spec), w, device="cuda:0", max_tokens=6 * 300, max_batch=6)
+    ids, mask = ragged_batch(6, 300, spec.vocab, seed=5)
+    mask[2] = 1  # a second full-length row
+    with torch.no_grad():
+        hs = gpt_neo.forward(spec, w, ids, mask)
+    want = pooling.weighted_mean(hs[-1], mask)
+    got = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
+    assert min_row_cosine(got, want) > 1 - COS_TOL
+    enc.close()
+
+
+def test_wide_gptj_hd256_and_bloom_hd128_vs_oracle():
+    """GPT-J blocks with the real head_dim 256 / rotary_dim 64 and BLOOM blocks with head_dim 128, depth 2, S up to 300."""
+    from oracle import bloom, gptj
+    from sgpt_b200 import Encoder, ModelConfig
+
+    js = gptj.GPTJSpec(n_layer=2, d_model=1024, n_head=4, d_ff=4096, vocab=2000, max_pos=512, rotary_dim=64)
+    jw = gptj.init_weights(js, seed=1)
+    enc = Encoder(ModelConfig(arch="gptj", n_layer=2, d_model=1024, n_head=4, d_ff=4096, vocab=2000, max_pos=512,
+                              rotary_dim=64), jw, device="cuda:0", max_tokens=5 * 300, max_batch=5)
+    ids, mask = ragged_batch(5, 300, js.vocab, seed=6)
+    with torch.no_grad():
+        want = pooling.weighted_mean(gptj.forward(js, jw, ids, mask)[-1], mask)
+    got = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
+    assert min_row_cosine(got, want) > 1 - COS_TOL
+    enc.close()
+
+    bs = bloom.BloomSpec(n_layer=2, d_model=1024, n_head=8, vocab=2000)
+    bw = bloom.init_weights(bs, seed=2)
+    enc = Encoder(ModelConfig(arch="bloom", n_layer=2, d_model=1024, n_head=8, d_ff=4096, vocab=2000, max_pos=1 << 20),
+                  bw, device="cuda:0", max_tokens=5 * 300, max_batch=5)
+    ids, mask = ragged_batch(5, 300, bs.vocab, seed=7)
+    with torch.no_grad():
+        want = pooling.weighted_mean(bloom.forward(bs, bw, ids, mask)[-1], mask)
+    got = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
+    assert min_row_cosine(got, want) > 1 - COS_TOL
+    enc.close()
