@@ -146,21 +146,43 @@ def reference_cpu_model(weights):
 _REF_MODEL = {}
 
 
-def cpu_reference_times(weights, enc_batch=32, n_enc=2, search_docs=100_000):
-    """Bounded sample of the reference CPU path: encode `n_enc` batches of `enc_batch` x 128 tokens (+1 warm-up of 8),
-    and cos_sim + topk(1001) of 128 queries over `search_docs` docs in 50k chunks with the heapq merge (XS:80-132)."""
+def usable_cores():
+    """Host threads this process may really use: CPU affinity mask capped by the cgroup CPU quota (os.cpu_count() alone
+    over-counts inside a container and oversubscribed MKL threads make the CPU baseline unrealistically slow)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, quota // period))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
+def cpu_reference_times(weights, enc_batch=32, n_enc=2, search_docs=100_000, warm=True):
+    """Bounded sample of the reference CPU path: encode `n_enc` batches of `enc_batch` x 128 tokens, and cos_sim +
+    topk(1001) of 128 queries over `search_docs` docs in 50k chunks with the heapq merge (XS:80-132)."""
     from oracle import pooling, search
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(usable_cores())
     if "m" not in _REF_MODEL:
         _REF_MODEL["m"] = reference_cpu_model(weights)  # built once per process
     fwd, how = _REF_MODEL["m"]
     ids = token_batches(1, seed=77)[0]
     mask = torch.ones_like(ids)
-    pooling.weighted_mean(fwd(ids[:8], mask[:8]), mask[:8])
+    if warm:
+        pooling.weighted_mean(fwd(ids[:2], mask[:2]), mask[:2])
     t0 = time.perf_counter()
     for i in range(n_enc):
-        sl = slice(i * enc_batch, (i + 1) * enc_batch)
+        sl = slice((i * enc_batch) % B, (i * enc_batch) % B + enc_batch)
         pooling.weighted_mean(fwd(ids[sl], mask[sl]), mask[sl])
     t_enc = time.perf_counter() - t0
     g = torch.Generator().manual_seed(4321)
@@ -172,31 +194,41 @@ def cpu_reference_times(weights, enc_batch=32, n_enc=2, search_docs=100_000):
     emb_s = n_enc * enc_batch / t_enc
     qps_1m = NQ / (t_search * (NDOCS / search_docs))
     return dict(emb_s=emb_s, qps_1m=qps_1m, how=how, t_enc=t_enc, t_search=t_search,
-                sample=f"encode {n_enc}x{enc_batch} seqs of {S} tokens (+8-seq warm-up); search {NQ} queries over "
-                       f"{search_docs} docs in 50k chunks incl. python heapq merge, scaled x{NDOCS // search_docs} to 1M docs")
+                sample=f"encode {n_enc}x{enc_batch} seqs of {S} tokens; search {NQ} queries over {search_docs} docs in "
+                       f"50k chunks incl. python heapq merge, scaled x{NDOCS / search_docs:g} to 1M docs")
+
+
+def calibrate_reference(weights, enc_seconds, search_seconds):
+    """Pick sample sizes so that one reference step costs about enc_seconds + search_seconds on this host."""
+    r = cpu_reference_times(weights, enc_batch=8, n_enc=1, search_docs=10_000, warm=True)
+    enc_batch = int(min(64, max(4, round(r["emb_s"] * enc_seconds))))
+    docs = int(min(200_000, max(10_000, round(10_000 * search_seconds / max(r["t_search"], 1e-3) / 10_000) * 10_000)))
+    return enc_batch, docs
 
 
 def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU path (HF GPTNeoModel fp32 on all host cores + Pooling / exact-search ports),
+    each step a bounded sample of the workload (~3 s), throughput in the same unit as the B200 arm."""
     if rank != 0:
         return
     w = synthetic_weights(0)
+    enc_batch, docs = calibrate_reference(w, enc_seconds=2.0, search_seconds=1.0)
     vals = []
     for _ in range(args.warmup):
-        cpu_reference_times(w, enc_batch=8, n_enc=1, search_docs=50_000)
+        cpu_reference_times(w, enc_batch=enc_batch, n_enc=1, search_docs=docs, warm=False)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = cpu_reference_times(w, enc_batch=32, n_enc=1, search_docs=100_000)
-        vals.append(r)
+        vals.append(cpu_reference_times(w, enc_batch=enc_batch, n_enc=1, search_docs=docs, warm=False))
     wall = time.perf_counter() - t0
-    emb_s = float(np.mean([v["emb_s"] for v in vals]))
-    qps = float(np.mean([v["qps_1m"] for v in vals]))
-    cores = os.cpu_count() or 1
+    emb_s = float(sum(enc_batch for _ in vals) / sum(v["t_enc"] for v in vals))
+    qps = float(NQ * len(vals) / (sum(v["t_search"] for v in vals) * (NDOCS / docs)))
+    cores = usable_cores()
     line = {"impl": "reference", "metric": METRIC, "value": emb_s, "unit": "embeddings/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": workload_config(args.gpus), "search": {"value": qps, "unit": "queries/s"},
             "cpu_baseline": {"value": emb_s, "unit": "embeddings/s", "cores": cores, "kind": "port",
-                             "sample": vals[-1]["sample"], "how": vals[-1]["how"], "search_qps_1m": qps},
+                             "sample": vals[-1]["sample"] + " per step", "how": vals[-1]["how"], "search_qps_1m": qps},
             "e2e": {"value": emb_s, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -372,8 +404,9 @@ def run_b200(args, rank, world, local_rank):
     e2e_search_ms = 1000 * e2e_s / K - 1000 * e2e_enc_s / K
     line["e2e"]["search_queries_per_s"] = NQ / (e2e_search_ms / 1e3) if e2e_search_ms > 0 else None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_times(weights)
-        line["cpu_baseline"] = {"value": r["emb_s"], "unit": "embeddings/s", "cores": os.cpu_count() or 1,
+        eb, docs = calibrate_reference(weights, enc_seconds=5.0, search_seconds=2.0)
+        r = cpu_reference_times(weights, enc_batch=eb, n_enc=2, search_docs=docs, warm=False)
+        line["cpu_baseline"] = {"value": r["emb_s"], "unit": "embeddings/s", "cores": usable_cores(),
                                 "kind": "port", "sample": r["sample"], "how": r["how"], "search_qps_1m": r["qps_1m"]}
     print(json.dumps(line), flush=True)
     enc.close()
