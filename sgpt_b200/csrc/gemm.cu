@@ -12,12 +12,12 @@ template <int BN, class Epi, int CL = 1>
 static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K,
                        const typename Epi::Params& ep, cudaStream_t stream, int cat = kCatGemm,
                        TileMap tmap = TileMap()) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   CUtensorMap ta, tb;
   int rc = make_tma_2d_bf16(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
                             kGemmBM, kGemmBK);
   if (rc != SGPT_OK) return rc;
-  // with a 2-CTA cluster each CTA fetches (and multicasts) half of the B tile
+  // in a CTA pair each CTA fetches (and holds) half of the B tile
   rc = make_tma_2d_bf16(&tb, b, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), BN / CL,
                         kGemmBK);
   if (rc != SGPT_OK) return rc;
@@ -50,8 +50,8 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   return SGPT_OK;
 }
 
-// nn.Linear dispatch: tile width by wave efficiency; 2-CTA clusters (shared B operand) whenever there are at least two
-// M-tiles — the encoder GEMMs are L2->SM bandwidth bound and the cluster cuts that traffic by a third.
+// nn.Linear dispatch: tile width by wave efficiency; CTA pairs (cta_group::2, M = 256) whenever there are at least two
+// M-tiles — a third less L2->SM and smem traffic per FLOP than independent CTAs.
 template <class Epi>
 static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                          const typename Epi::Params& p, int bn, cudaStream_t stream) {

@@ -32,15 +32,17 @@ constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 256;
 constexpr int kStageBytesPerWarp = 8192;  // per epilogue warp: 2 TMA boxes of 32 x 128 B, or one 32 x 64 fp32 slab
 
-template <int BN>
+template <int BN, int CL = 1>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
-  static constexpr int kBBytes = BN * kGemmBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBBytes = (BN / CL) * kGemmBK * 2;  // a CTA pair splits the B tile between its two CTAs
+  static constexpr int kStageBytes = kABytes + kBBytes;    // 48 / 32 KB (single CTA, BN 256 / 128); 32 / 24 KB (pair)
+  static constexpr int kStages = (kStageBytes == 49152) ? 4 : (kStageBytes == 32768) ? 5 : 6;
+  // epilogue staging: 4 KB boxes, one per epilogue warp behind the 48 KB stages, two (double-buffered) otherwise
+  static constexpr int kStagingBytes = (kStageBytes == 49152) ? 4 * kStageBytesPerWarp : 8 * kStageBytesPerWarp;
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512 (power of two)
-  // smem: [<=1024 align slack][stages * (A|B)][4 epilogue staging slabs][barriers + tmem holder]
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 4 * kStageBytesPerWarp + 256;
+  // smem: [<=1024 align slack][stages * (A|B)][epilogue staging][barriers + tmem holder]
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
@@ -62,25 +64,30 @@ struct TileMap {
   }
 };
 
-// CL = thread-block-cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically adjacent output
-// tiles (same N-tile, consecutive M-tiles) and share the B operand: each CTA fetches only HALF of the B tile from L2
-// and TMA-multicasts it into both CTAs' smem, so L2->SM operand traffic per CTA drops from (128 + BN) x 64 to
-// (128 + BN/2) x 64 elements per k-block — the linear layers of the encoder are L2->SM bandwidth bound (ncu:
-// lts2xbar at 75-80 % of its sustained peak with independent CTAs).  A smem stage may be refilled only after BOTH
-// CTAs' MMAs have consumed it (the peer writes into it), hence empty barriers count CL arrivals and tcgen05.commit
-// multicasts its arrival to both CTAs.
+// CL = 1: independent CTAs, tcgen05.mma.cta_group::1, one 128 x BN tile per CTA iteration.
+// CL = 2: CTA pairs (2-CTA clusters = the two SMs of a TPC) executing tcgen05.mma.cta_group::2 with M = 256: CTA r of
+//   the pair owns rows [128 r, 128 r + 128) of the 256 x BN tile (its A rows in its smem, its accumulator rows in its
+//   TMEM) and holds B rows [BN/2 r, BN/2 r + BN/2) — half of the weight tile — in its smem.  Only the leader (rank 0)
+//   issues MMAs; both CTAs run a TMA producer (signalling the LEADER's full barrier) and the epilogue of their rows.
+//   Per SM this removes a third of the smem writes (TMA) and operand reads (MMA) of the single-CTA kernel — measured:
+//   with cta_group::1 the mainloop alone ran at the tensor peak but every byte the epilogue moved through smem
+//   (st.shared + TMA-store reads) slowed it down (75 -> 103 us on the 32768 x 2304 x 768 QKV GEMM).
+//   Barrier protocol: full[s] (leader, 1 arrive + 2 x stage bytes) <- both producers' TMA; empty[s] (each CTA, count 1)
+//   <- leader's tcgen05.commit multicast; tmem_full[a] (each CTA) <- commit multicast; tmem_empty[a] (leader, count
+//   2 x epilogue warps) <- both CTAs' epilogue warps (remote arrive from the peer).
 template <int BN, class Epi, int CL = 1>
 __global__ void __launch_bounds__(128 + 32 * Epi::kEpiWarps, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
                     int N, int K, const __grid_constant__ typename Epi::Params ep, TileMap tmap) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   constexpr int kStages = Cfg::kStages;
+  static_assert(CL == 1 || CL == 2, "cluster size");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_tiles = smem;
   float* stage_base = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + 4 * kStageBytesPerWarp);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -108,20 +115,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], Epi::kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], CL * Epi::kEpiWarps);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == kWarpTmem) {
-    tmem_alloc(tmem_holder, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CL == 2) {
+      tmem_alloc_pair(tmem_holder, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_holder, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  if (CL == 2) cluster_sync_all();  // peer barriers must be initialised before any remote arrive / multicast lands
+  if (CL == 2) cluster_sync_all();  // peer barriers / TMEM must exist before any remote arrive, commit or pair MMA
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
@@ -138,23 +150,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * kGemmBK, m0);
           if (CL == 2) {
-            // my half of the B tile (BN/2 rows) goes to both CTAs; the other half arrives from the peer
-            constexpr int kHalfRows = BN / 2;
-            tma_load_2d_multicast(sb + crank * (kHalfRows * 128), &tma_b, &full_bar[stage], kb * kGemmBK,
-                                  n0 + static_cast<int>(crank) * kHalfRows, 0x3);
-          } else
-          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * kGemmBK, n0);
+            // my A rows and my half of the B tile land in MY smem; the bytes are accounted on the leader's barrier
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &tma_a, leader_full, kb * kGemmBK, m0);
+            tma_load_2d_pair(sb, &tma_b, leader_full, kb * kGemmBK, n0 + static_cast<int>(crank) * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * kGemmBK, m0);
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * kGemmBK, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN, false);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM * CL, BN, false);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -173,14 +187,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CL == 2) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          // frees this smem stage (in both CTAs of a cluster) once the MMAs above have read it
-          if (CL == 2) umma_commit_multicast(&empty_bar[stage], 0x3);
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (CL == 2) umma_commit_pair(&empty_bar[stage], 0x3);
           else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CL == 2) umma_commit_pair(&tmem_full_bar[acc], 0x3);
+        else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -191,7 +208,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int ew = warp & 3;              // TMEM lane quarter (hardware: warp id % 4) == 32-row slab of the tile
     const int half = warp >> 2;           // column half handled by this warp (always 0 with 4 epilogue warps)
     constexpr int kColsPerWarp = BN / (Epi::kEpiWarps / 4);
-    float* stage_slab = stage_base + warp * ((4 * kStageBytesPerWarp / Epi::kEpiWarps) / 4);
+    constexpr int kSlabBytes = Cfg::kStagingBytes / Epi::kEpiWarps;
+    float* stage_slab = stage_base + warp * (kSlabBytes / 4);
+    const uint32_t leader_tmem_empty0 = (CL == 2) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     typename Epi::State st;
     Epi::init(st, ep, ew * 32 + lane);
     int acc = 0;
@@ -202,10 +221,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + half * kColsPerWarp;
-      Epi::template tile<kColsPerWarp>(st, ep, m0, n0, lane, trow, stage_slab, M, N);
+      Epi::template tile<kColsPerWarp, kSlabBytes>(st, ep, m0, n0, lane, trow, stage_slab, M, N);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (CL == 2) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     Epi::finish(st, ep, ew * 32 + lane);
@@ -216,7 +238,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   else __syncthreads();
   if (warp == kWarpTmem) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CL == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -238,7 +261,7 @@ struct EpiTma {
     if ((lane_row & 31) == 0) bulk_wait_group<0>();  // all stores of this warp have fully completed
   }
 
-  template <int BN>
+  template <int BN, int kSlabBytes>
   static __device__ __forceinline__ void tile(State& st, const Params& p, int m0, int n0, int lane, uint32_t trow,
                                               float* slab, int M, int N) {
     if (m0 >= M) return;  // whole 32-row slab out of range (warp-uniform)
@@ -247,11 +270,13 @@ struct EpiTma {
     for (int c = 0; c < BN; c += kCols) {
       const int n = n0 + c;
       if (n >= N) break;  // warp-uniform
-      const uint32_t box = sbase;
-      if (st.it >= 1 && kDebug == 0) {
-        // this warp's previous store must have finished reading the box (the partner warp on the same scheduler
-        // keeps the SM busy meanwhile)
-        if (lane == 0) bulk_wait_group_read<0>();
+      // kBoxes smem boxes per warp, used round-robin: a box may be rewritten once the TMA store issued kBoxes
+      // iterations ago has finished READING it (the stores themselves complete asynchronously)
+      constexpr int kBoxes = kSlabBytes / 4096;
+      static_assert(kBoxes == 1 || kBoxes == 2, "one or two 4 KB boxes per epilogue warp");
+      const uint32_t box = sbase + (kBoxes == 2 ? (st.it & 1u) * 4096u : 0u);
+      if (st.it >= kBoxes && kDebug == 0) {
+        if (lane == 0) bulk_wait_group_read<kBoxes - 1>();
         __syncwarp();
       }
       uint32_t v[kCols];
@@ -414,7 +439,7 @@ struct EpiStaged {
   static __device__ __forceinline__ void init(State&, const Params&, int) {}
   static __device__ __forceinline__ void finish(State&, const Params&, int) {}
 
-  template <int BN>
+  template <int BN, int kSlabBytes>
   static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int lane, uint32_t trow,
                                               float* slab_ptr, int M, int N) {
     const int rows = min(32, M - m0);  // warp-uniform; <= 0 when the whole slab is out of range
@@ -594,7 +619,7 @@ struct EpiFilterRows {
   static __device__ __forceinline__ void init(State&, const Params&, int) {}
   static __device__ __forceinline__ void finish(State&, const Params&, int) {}
 
-  template <int COLS>
+  template <int COLS, int kSlabBytes>
   static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int lane, uint32_t trow, float*,
                                               int M, int N) {
     if (m0 >= M) return;  // warp-uniform
@@ -660,7 +685,7 @@ struct EpiDebugNull {
   static constexpr int kEpiWarps = 4;
   static __device__ __forceinline__ void init(State&, const Params&, int) {}
   static __device__ __forceinline__ void finish(State&, const Params&, int) {}
-  template <int BN>
+  template <int BN, int kSlabBytes>
   static __device__ __forceinline__ void tile(State&, const Params&, int, int, int, uint32_t trow, float*, int, int) {
     if (kLoad) {
       uint32_t acc = 0;
