@@ -301,30 +301,43 @@ def run_b200(args, rank, world, local_rank):
     barrier()
 
     # ---- device-timed loop (inputs resident in HBM) -------------------------------------------------------------
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    # Two passes over the SAME K steps.  Pass 1 is the timed region of `value`: only three CUDA events per step.
+    # Pass 2 repeats it with the library's per-launch CUDA events switched on (two event records around each of the
+    # ~138 launches of a step cost ~7 % of the step, so they stay out of pass 1) and feeds `roofline` /
+    # `kernel_ms_per_step`; its own step time is reported as profiled_pass_ms_per_step.
     prof_ms = (ctypes.c_double * 8)()
     prof_n = (ctypes.c_int64 * 8)()
     tot_n0 = (ctypes.c_int64 * 8)()
     tot_n1 = (ctypes.c_int64 * 8)()
+    gclk_c, gclk_ns = ctypes.c_double(), ctypes.c_double()
+
+    def timed_pass():
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        barrier()
+        t_w0 = time.perf_counter()
+        for k in range(args.steps):
+            r = resident[k % len(resident)]
+            ev[k][0].record()
+            enc.encode_packed(r[0], r[1], r[2], B, B * S, S)
+            ev[k][1].record()
+            search_step(queries)
+            ev[k][2].record()
+        barrier()
+        t_w = time.perf_counter() - t_w0
+        e_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
+        s_ms = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps))
+        return e_ms, s_ms, ev[0][0].elapsed_time(ev[-1][2]), t_w
+
     lib.sgpt_profile_read(None, None, tot_n0)
+    lib.sgpt_profile_gemm_clock(ctypes.byref(gclk_c), ctypes.byref(gclk_ns))  # reset
+    enc_ms, sea_ms, tot_ms, t_wall = timed_pass()
+    lib.sgpt_profile_read(None, None, tot_n1)
+    lib.sgpt_profile_gemm_clock(ctypes.byref(gclk_c), ctypes.byref(gclk_ns))
+    launches = sum(int(tot_n1[c] - tot_n0[c]) for c in range(8))
     lib.sgpt_profile_enable(1)
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        r = resident[k % len(resident)]
-        ev[k][0].record()
-        enc.encode_packed(r[0], r[1], r[2], B, B * S, S)
-        ev[k][1].record()
-        search_step(queries)
-        ev[k][2].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
+    _, _, prof_tot_ms, _ = timed_pass()
     lib.sgpt_profile_enable(0)
     lib.sgpt_profile_read(prof_ms, prof_n, tot_n1)
-    enc_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
-    sea_ms = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps))
-    tot_ms = ev[0][0].elapsed_time(ev[-1][2])
-    launches = sum(int(tot_n1[c] - tot_n0[c]) for c in range(8))
 
     # ---- end-to-end loop: public API, HOST buffers in, HOST results out -------------------------------------------
     barrier()
@@ -386,6 +399,7 @@ def run_b200(args, rank, world, local_rank):
                      "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": (gemm_tflops / pk["tf_sustained"]) if gemm_tflops else None, "traffic": None,
                      "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
+                     "timed_in": "pass 2: the same K steps repeated with per-launch CUDA events on the launching stream",
                      "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(1, gemm_n),
                      "algorithmic_flops_per_launch": lin_flops * B / 48},
         "roofline_similarity": {"kernel": "gemm_bf16_tn_kernel<EpiFilterRows> (query x corpus, threshold filter)",
@@ -394,6 +408,8 @@ def run_b200(args, rank, world, local_rank):
                                 "algorithmic_bytes_per_search": sim_bytes, "launches_per_search": sim_n // max(1, K),
                                 "device_ms_per_search": sim_ms / K},
         "kernel_ms_per_step": {c: prof_ms[i] / K for i, c in enumerate(cats)},
+        "profiled_pass_ms_per_step": prof_tot_ms / K,
+        "gemm_sm_clock_mhz": (1e3 * gclk_c.value / gclk_ns.value) if gclk_ns.value > 0 else None,
         "gpu_launches": launches,
         "e2e": {"value": world * B * K / e2e_enc_s, "unit": "embeddings/s", "h2d_bytes_per_step": h2d // K,
                 "d2h_bytes_per_step": d2h // K, "full_step_ms": 1000 * e2e_s / K,

@@ -211,6 +211,11 @@ int sgpt_search(const void* Q, const void* C, const float* q_scale, const float*
 #define SGPT_NUM_LAUNCH_CATEGORIES 8
 int sgpt_profile_enable(int on);
 int sgpt_profile_read(double* ms_by_cat, int64_t* timed_launches_by_cat, int64_t* total_launches_by_cat);
+/* SM clock the tcgen05 GEMM kernels actually ran at: every GEMM launch has one thread read %clock64 and %globaltimer
+ * at its start and end and accumulate both deltas on the device.  Returns the accumulated SM cycles and nanoseconds
+ * since the previous call (cycles / ns = GHz under load, which nvidia-smi sampling cannot resolve) and resets them.
+ * Synchronises the device. */
+int sgpt_profile_gemm_clock(double* sm_cycles, double* nanoseconds);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "sgpt_search_workspace_bytes": (i64, [i32, i64, i32]),
     "sgpt_profile_enable": (i32, [i32]),
     "sgpt_profile_read": (i32, [vp, vp, vp]),
+    "sgpt_profile_gemm_clock": (i32, [vp, vp]),
     "sgpt_search": (i32, [vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, vp, vp, i64, vp]),
 }
 

@@ -91,6 +91,17 @@ int launch_filter_candidates(const void* Q, const void* C, const float* q_scale,
 
 using namespace sgpt;
 
+extern "C" int sgpt_profile_gemm_clock(double* sm_cycles, double* nanoseconds) {
+  SGPT_REQUIRE(sm_cycles != nullptr && nanoseconds != nullptr, "sgpt_profile_gemm_clock: null output");
+  unsigned long long h[2] = {0, 0}, zero[2] = {0, 0};
+  SGPT_CHECK_CUDA(cudaDeviceSynchronize());
+  SGPT_CHECK_CUDA(cudaMemcpyFromSymbol(h, g_gemm_clock, sizeof(h)));
+  SGPT_CHECK_CUDA(cudaMemcpyToSymbol(g_gemm_clock, zero, sizeof(zero)));
+  *sm_cycles = static_cast<double>(h[0]);
+  *nanoseconds = static_cast<double>(h[1]);
+  return SGPT_OK;
+}
+
 extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out,
                            int64_t ldo, const float* resid, int M, int N, int K, int epilogue,
                            sgpt_stream_t stream_) {

@@ -46,6 +46,14 @@ struct GemmCfg {
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
+// [0] SM cycles, [1] nanoseconds spent inside GEMM kernels (sgpt_profile_gemm_clock); one thread per launch adds to it
+__device__ unsigned long long g_gemm_clock[2];
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Optional selection of N-tiles: the similarity search scans a strided sample of corpus tiles first (to establish
 // per-query thresholds) and the remaining tiles afterwards.
 //   mode 0: all tiles;  mode 1: tiles 0, s, 2s, ...;  mode 2: every tile that is NOT a multiple of s   (s >= 2)
@@ -137,6 +145,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const bool clock_probe = (blockIdx.x == 0 && threadIdx.x == 0);
+  const long long probe_c0 = clock_probe ? clock64() : 0;
+  const uint64_t probe_t0 = clock_probe ? global_timer_ns() : 0;
 
   if (warp == kWarpProducer) {
     // ===================== TMA producer =====================
@@ -231,6 +242,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     Epi::finish(st, ep, ew * 32 + lane);
+    if (clock_probe) {
+      atomicAdd(&g_gemm_clock[0], static_cast<unsigned long long>(clock64() - probe_c0));
+      atomicAdd(&g_gemm_clock[1], static_cast<unsigned long long>(global_timer_ns() - probe_t0));
+    }
   }
 
   tc_fence_before();

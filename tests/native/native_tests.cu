@@ -496,7 +496,7 @@ int main(int argc, char** argv) {
   }
   if (!strcmp(only, "nullepi")) {  // timing only: mainloop without / with TMEM loads in the epilogue
     for (int epi = 100; epi <= 105; ++epi)
-      for (int K : {768}) {
+      for (int K : {768, 3072}) {
         const int M = 32768, N = 2304;
         auto x = randn((size_t)M * K, 1.0f), w = randn((size_t)N * K, 0.05f);
         auto xb = to_bf16(x), wb = to_bf16(w);
@@ -513,6 +513,31 @@ int main(int argc, char** argv) {
         printf("INFO epi=%d M=%d N=%d K=%d: %.3f ms  %.1f TFLOP/s\n", epi, M, N, K, ms, 2.0 * M * N * K / (ms * 1e9));
         cudaFree(dx); cudaFree(dw); cudaFree(dout);
       }
+  }
+  if (!strcmp(only, "clockprobe")) {  // what SM clock do the GEMM bursts actually run at?
+    const int M = 32768, N = 2304;
+    for (int launches : {5, 60})
+      for (int K : {768, 3072})
+        for (int epi : {100, 102, (int)SGPT_EPI_BF16}) {
+          auto x = randn((size_t)M * K, 1.0f), w = randn((size_t)N * K, 0.05f);
+          auto xb = to_bf16(x), wb = to_bf16(w);
+          auto *dx = to_dev(xb), *dw = to_dev(wb);
+          auto* dout = dalloc<__nv_bfloat16>((size_t)M * N);
+          SG(sgpt_linear(dx, K, dw, K, nullptr, dout, N, nullptr, M, N, K, epi, 0));
+          double cyc, ns;
+          SG(sgpt_profile_gemm_clock(&cyc, &ns));
+          cudaEvent_t e0, e1;
+          CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+          CK(cudaEventRecord(e0));
+          for (int it = 0; it < launches; ++it) SG(sgpt_linear(dx, K, dw, K, nullptr, dout, N, nullptr, M, N, K, epi, 0));
+          CK(cudaEventRecord(e1));
+          CK(cudaDeviceSynchronize());
+          SG(sgpt_profile_gemm_clock(&cyc, &ns));
+          const double ms = time_ms(e0, e1) / launches;
+          printf("INFO clockprobe launches=%d K=%d epi=%d: %.3f ms/launch %.1f TFLOP/s | in-kernel %.3f ms, SM clock %.0f MHz\n",
+                 launches, K, epi, ms, 2.0 * M * N * K / (ms * 1e9), ns / launches * 1e-6, 1e3 * cyc / ns);
+          cudaFree(dx); cudaFree(dw); cudaFree(dout);
+        }
   }
   if (!strcmp(only, "sweep")) {  // which dimension limits the GEMM rate?
     const int shapes[][3] = {{32768, 2304, 768}, {32768, 2304, 2048}, {16384, 8192, 768},  {16384, 2304, 768},

@@ -69,6 +69,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--models", default="sgpt-1.3b,sgpt-5.8b,sgpt-bloom-7b1")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=0, help="override the batch size (sequences) of every model")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-launch event timing")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peak = 1431.3
@@ -78,6 +80,8 @@ def main():
     for name in args.models.split(","):
         cfg = preset(name)
         B, S = SHAPES[name]
+        if args.batch:
+            B = args.batch
         sd = rand_weights(cfg, dev)
         enc = Encoder(cfg, sd, device=dev, max_tokens=B * S, max_batch=B)
         del sd
@@ -93,7 +97,7 @@ def main():
         lib = _lib.lib()
         ms_cat, n_cat = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
         lib.sgpt_profile_read(None, None, None)
-        lib.sgpt_profile_enable(1)
+        lib.sgpt_profile_enable(0 if args.no_profile else 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
