@@ -77,14 +77,28 @@ static int pick_bn(int M, int N) {
   return (eff(256) * 1.25 >= eff(128)) ? 256 : 128;
 }
 
+FilterGeometry filter_geometry(long long tiles) {
+  const long long sms = sm_count();
+  const long long ctas = tiles < sms ? (tiles > 0 ? tiles : 1) : sms;
+  const long long per_cta = (tiles + ctas - 1) / ctas;
+  FilterGeometry g;
+  g.groups = static_cast<int>(2 * ctas);
+  g.L = static_cast<int>(per_cta * (kSimBN / 2));
+  return g;
+}
+
 int launch_filter_candidates(const void* Q, const void* C, const float* q_scale, const float* c_scale,
-                             const float* tau, uint2* cand, int* count, long long cap, int nq, int n, int D,
-                             int tile_mode, int tile_stride, cudaStream_t stream) {
-  OpFilterCandidates::Params p{q_scale, c_scale, tau, cand, count, cap};
+                             const float* tau, uint2* cand, int* counts, long long stride_q, int L, int group0, int nq,
+                             int n, int D, int tile_mode, int tile_stride, cudaStream_t stream) {
+  SGPT_REQUIRE(nq <= kGemmBM, "filter GEMM: at most %d queries per launch (got %d)", kGemmBM, nq);
   TileMap tm;
   tm.mode = tile_mode;
   tm.stride = tile_stride;
-  return launch_gemm<kSimBN, EpiFilterCandidates>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
+  const FilterGeometry g = filter_geometry(tm.count((n + kSimBN - 1) / kSimBN));
+  SGPT_REQUIRE(L >= g.L && (L % 2) == 0 && (stride_q % 2) == 0, "filter GEMM: candidate lists too small (L=%d < %d)", L,
+               g.L);
+  EpiFilterRows::Params p{q_scale, c_scale, tau, cand, counts, stride_q, L, group0, nq};
+  return launch_gemm<kSimBN, EpiFilterRows>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
 }
 
 }  // namespace sgpt

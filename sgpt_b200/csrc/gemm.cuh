@@ -545,104 +545,53 @@ struct OpScoresF32 {
   }
 };
 
-// Threshold filter: score = fixnan(acc * row_scale[q] * col_scale[doc]); every score > tau[q] is appended as a packed
-// (score bits, local doc index) pair to the query's candidate list.  One warp-aggregated atomicAdd per (query row,
-// 64-column slab); the score matrix itself is never written to HBM.
-struct OpFilterCandidates {
-  struct Params {
-    const float* row_scale;  // per query or null
-    const float* col_scale;  // per doc or null
-    const float* tau;        // per query threshold; null = accept everything (sampling pass)
-    uint2* cand;             // [nq, cap]
-    int* count;              // [nq]
-    long long cap;
-  };
-  static __device__ __forceinline__ void rows(const Params& p, uint32_t slab, int m0, int rows, int col, int N,
-                                              int lane) {
-    const bool ok0 = col < N, ok1 = col + 1 < N;
-    float c0 = 1.f, c1 = 1.f;
-    if (p.col_scale) {
-      if (ok0) c0 = __ldg(p.col_scale + col);
-      if (ok1) c1 = __ldg(p.col_scale + col + 1);
-    }
-    // lane r keeps the scale/threshold of row m0 + r; broadcast per row with a shuffle
-    float my_rs = 1.f, my_tau = -INFINITY;
-    if (lane < rows) {
-      if (p.row_scale) my_rs = __ldg(p.row_scale + m0 + lane);
-      if (p.tau) my_tau = __ldg(p.tau + m0 + lane);
-    }
-    const unsigned lt = (1u << lane) - 1u;
-    // Phase 1: hit counts of all rows of the slab; lane r ends up owning row r's count.
-    int my_total = 0;
-    for (int rb = 0; rb < rows; rb += 8) {
-      float2 ab[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) ab[u] = (rb + u < rows) ? slab_read(slab, rb + u, lane) : make_float2(0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = rb + u;
-        const float rs = __shfl_sync(0xffffffffu, my_rs, r & 31);
-        const float t = __shfl_sync(0xffffffffu, my_tau, r & 31);
-        float x = ab[u].x * rs * c0, y = ab[u].y * rs * c1;
-        x = (x != x) ? -1.f : x;
-        y = (y != y) ? -1.f : y;
-        const bool in = r < rows;
-        const unsigned b0 = __ballot_sync(0xffffffffu, in && ok0 && (x > t));
-        const unsigned b1 = __ballot_sync(0xffffffffu, in && ok1 && (y > t));
-        if (lane == r) my_total = __popc(b0) + __popc(b1);
-      }
-    }
-    if (__ballot_sync(0xffffffffu, my_total != 0) == 0u) return;  // nothing admitted in this slab (warp-uniform)
-    // ONE atomic instruction reserves space in all the slab's query lists (32 different addresses): a single global
-    // round trip per slab instead of one per row.
-    int my_base = 0;
-    if (my_total != 0) my_base = atomicAdd(p.count + m0 + lane, my_total);
-    // Phase 2: rows with hits recompute their scores (smem re-read) and write (score, doc) pairs.
-    for (int r = 0; r < rows; ++r) {
-      const int total = __shfl_sync(0xffffffffu, my_total, r);
-      if (total == 0) continue;  // warp-uniform
-      const int base = __shfl_sync(0xffffffffu, my_base, r);
-      const float rs = __shfl_sync(0xffffffffu, my_rs, r);
-      const float t = __shfl_sync(0xffffffffu, my_tau, r);
-      const float2 a = slab_read(slab, r, lane);
-      float x = a.x * rs * c0, y = a.y * rs * c1;
-      x = (x != x) ? -1.f : x;
-      y = (y != y) ? -1.f : y;
-      const bool h0 = ok0 && (x > t), h1 = ok1 && (y > t);
-      const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
-      uint2* dst = p.cand + static_cast<long long>(m0 + r) * p.cap;
-      if (h0) {
-        const long long s = base + __popc(b0 & lt);
-        if (s < p.cap) dst[s] = make_uint2(__float_as_uint(x), static_cast<uint32_t>(col));
-      }
-      if (h1) {
-        const long long s = base + __popc(b0) + __popc(b1 & lt);
-        if (s < p.cap) dst[s] = make_uint2(__float_as_uint(y), static_cast<uint32_t>(col + 1));
-      }
-    }
-  }
-};
-// Row-native threshold filter (the one the search uses).  In the accumulator's native layout thread r of a warp owns
-// query row r, i.e. ONE admission threshold and ONE candidate list: the compare needs no transpose, no shuffles and no
-// ballots.  Per 32-document chunk: scale, count the admitted scores (branch-free), reserve list space with one
-// atomicAdd per lane (32 different addresses, only when the warp has any hit), then predicated stores.  8 epilogue
-// warps (two per TMEM lane quarter, half the tile's documents each); no shared memory at all.
+// Threshold filter of the fused search (search.cu): score = fixnan(acc * row_scale[q] * col_scale[doc]); every score
+// > tau[q] is appended as a packed (score bits, local doc index) pair to a candidate list; the score matrix itself is
+// never written to HBM.
+//
+// In the accumulator's native layout thread r of a warp owns query row r, i.e. ONE admission threshold: the compare
+// needs no transpose, no shuffles and no ballots.  Each (CTA, column-half) pair is a GROUP with a PRIVATE list per query
+// (cand[q][group][L]); the thread keeps its list length in a register across all tiles of the persistent kernel and
+// writes it out once at the end, so there are NO atomics at all.  (The first version reserved space in one list per
+// query with an atomicAdd per 32-document chunk: ~17 k same-address atomics per counter per search serialised in the
+// L2 and, not the HBM stream, set the kernel's duration.)  L is sized for the worst case (every score of every tile the
+// CTA visits admitted), so there is no overflow path; only the touched prefix of each list generates memory traffic.
+// 8 epilogue warps (two per TMEM lane quarter, half the tile's documents each); no shared memory.
 struct EpiFilterRows {
-  using Params = OpFilterCandidates::Params;
-  using State = EpiNoState;
+  struct Params {
+    const float* row_scale;  // [M] or null
+    const float* col_scale;  // [N] or null
+    const float* tau;        // [M] per-query admission threshold; null -> admit everything (dense, vectorised stores)
+    uint2* cand;             // [M][groups][L]
+    int* counts;             // [groups][M]
+    long long stride_q;      // entries between consecutive queries' list blocks
+    int L;                   // entries per (query, group) list
+    int group0;              // first group index this launch writes (groups below it belong to the caller: seeds)
+    int nq;
+  };
+  struct State {
+    int cnt;
+  };
   static constexpr int kEpiWarps = 8;
-  static __device__ __forceinline__ void init(State&, const Params&, int) {}
-  static __device__ __forceinline__ void finish(State&, const Params&, int) {}
+  static __device__ __forceinline__ int group_of(const Params& p) {
+    return p.group0 + static_cast<int>(blockIdx.x) * 2 + static_cast<int>(threadIdx.x >> 7);
+  }
+  static __device__ __forceinline__ void init(State& st, const Params&, int) { st.cnt = 0; }
+  static __device__ __forceinline__ void finish(State& st, const Params& p, int lane_row) {
+    if (lane_row < p.nq) p.counts[static_cast<long long>(group_of(p)) * p.nq + lane_row] = min(st.cnt, p.L);
+  }
 
   template <int COLS, int kSlabBytes>
-  static __device__ __forceinline__ void tile(State&, const Params& p, int m0, int n0, int lane, uint32_t trow, float*,
-                                              int M, int N) {
+  static __device__ __forceinline__ void tile(State& st, const Params& p, int m0, int n0, int lane, uint32_t trow,
+                                              float*, int M, int N) {
     if (m0 >= M) return;  // warp-uniform
     const int q = m0 + lane;
     const bool qok = q < M;
     const float rs = (qok && p.row_scale) ? __ldg(p.row_scale + q) : 1.f;
-    const float tau = (qok && p.tau) ? __ldg(p.tau + q) : -INFINITY;
-    uint2* dst = p.cand + static_cast<long long>(qok ? q : 0) * p.cap;
+    const bool dense = (p.tau == nullptr);
+    const float tau = (qok && !dense) ? __ldg(p.tau + q) : -INFINITY;
+    uint2* dst = p.cand + static_cast<long long>(qok ? q : 0) * p.stride_q + static_cast<long long>(group_of(p)) * p.L;
+    int cnt = st.cnt;
 #pragma unroll 1
     for (int c = 0; c < COLS; c += 32) {
       const int n = n0 + c;
@@ -650,7 +599,8 @@ struct EpiFilterRows {
       uint32_t v[32];
       tmem_ld_32x32(trow + c, v);
       float cs[32];
-      if (p.col_scale != nullptr && n + 32 <= N) {
+      const bool full = (n + 32 <= N);
+      if (p.col_scale != nullptr && full) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(p.col_scale + n) + i);  // same address in all lanes
@@ -662,26 +612,32 @@ struct EpiFilterRows {
       }
       tmem_ld_wait();
       float x[32];
-      int cnt = 0;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        float s = __uint_as_float(v[i]) * rs * cs[i];
-        s = (s != s) ? -1.f : s;  // XS:99 NaN -> -1
-        x[i] = s;
-        cnt += (qok && n + i < N && s > tau) ? 1 : 0;
+        const float s = __uint_as_float(v[i]) * rs * cs[i];
+        x[i] = (s != s) ? -1.f : s;  // XS:99 NaN -> -1
       }
-      if (__any_sync(0xffffffffu, cnt != 0)) {
-        long long k = 0;
-        if (cnt != 0) k = atomicAdd(p.count + q, cnt);
+      if (dense && full && (cnt & 1) == 0) {
+        // sample pass: every score is kept; 16-byte stores of two consecutive entries (lists are 16-byte aligned)
+        if (qok && cnt + 32 <= p.L) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cnt);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            d4[i] = make_uint4(__float_as_uint(x[2 * i]), static_cast<uint32_t>(n + 2 * i),
+                               __float_as_uint(x[2 * i + 1]), static_cast<uint32_t>(n + 2 * i + 1));
+        }
+        cnt += qok ? 32 : 0;
+      } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (qok && n + i < N && x[i] > tau) {
-            if (k < p.cap) dst[k] = make_uint2(__float_as_uint(x[i]), static_cast<uint32_t>(n + i));
-            ++k;
+            if (cnt < p.L) dst[cnt] = make_uint2(__float_as_uint(x[i]), static_cast<uint32_t>(n + i));
+            ++cnt;
           }
         }
       }
     }
+    st.cnt = cnt;
   }
 };
 using EpiFilterCandidates = EpiFilterRows;

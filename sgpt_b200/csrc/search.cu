@@ -1,15 +1,16 @@
 // S1+S2 for one corpus shard without materialising the [nq, n] score matrix.
 //
 // Two passes of the same tcgen05 similarity GEMM (corpus streamed from HBM exactly once in total):
-//   pass A  scans a strided SAMPLE of the corpus tiles (every s-th 256-document tile, ~one tile per SM) and appends all
-//           of its scores to a per-query list; a radix select turns each list into (i) the query's admission threshold
-//           tau[q] = its k-th best sampled score and (ii) the k sampled winners, which seed the candidate list.
+//   pass A  scans a strided SAMPLE of the corpus tiles (every s-th 256-document tile, ~one tile per SM) and keeps all of
+//           its scores; a radix select turns them into (i) the query's admission threshold tau[q] = its k-th best
+//           sampled score and (ii) the k sampled winners, which seed the candidate lists (group 0).
 //           tau[q] is a valid lower bound of the final k-th best score because k real documents already reach it.
-//   pass B  scans all remaining tiles; the epilogue keeps only scores > tau[q] (warp-aggregated append, expected
-//           k * n / n_sample survivors per query) — the score matrix never reaches HBM.
-//   final   radix select + sort over each query's candidate list -> exact top-k.
-// Candidate lists are sized for the worst case (every score admitted), so no overflow path exists; only the touched
-// prefix of that allocation ever generates memory traffic.  Small shards take the direct path (dense scores + select).
+//   pass B  scans all remaining tiles; the epilogue keeps only scores > tau[q] (expected k * n / n_sample survivors per
+//           query) — the score matrix never reaches HBM.
+//   final   radix select + sort over each query's candidate lists -> exact top-k.
+// Candidates live in per-(query, group) lists, one group per (CTA, tile half) of the GEMM (gemm.cuh EpiFilterRows): no
+// atomics, and every list is sized for the worst case (every score admitted), so no overflow path exists; only the
+// touched prefix of each list ever generates memory traffic.  Small shards take the direct path (dense scores + select).
 #include "../../include/sgpt_b200.h"
 #include "gemm_api.h"
 #include "host_utils.h"
@@ -25,9 +26,9 @@ inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 struct Plan {
   bool two_pass;
   int stride;          // tile stride of the sample
-  int64_t n_sample;    // documents covered by sampled tiles (upper bound)
-  int64_t cap_a;       // pass-A list capacity per query
-  int64_t cap_b;       // candidate list capacity per query
+  FilterGeometry ga;   // pass-A lists: groups x L entries per query
+  FilterGeometry gb;   // pass-B lists (group 0 of the block is the seed list, so gb.groups + 1 lists per query)
+  int64_t stride_a, stride_b;  // entries per query block
 };
 
 Plan make_plan(int nq, int64_t n, int k) {
@@ -39,9 +40,11 @@ Plan make_plan(int nq, int64_t n, int k) {
   if (!p.two_pass) return p;
   p.stride = static_cast<int>(n_tiles / sms);
   const int64_t sampled_tiles = (n_tiles + p.stride - 1) / p.stride;
-  p.n_sample = sampled_tiles * kSimBN;
-  p.cap_a = p.n_sample;
-  p.cap_b = n + k;  // worst case: every non-sampled score admitted, plus the k seeds
+  p.ga = filter_geometry(sampled_tiles);
+  p.gb = filter_geometry(n_tiles - sampled_tiles);
+  if (p.gb.L < k) p.gb.L = (k + 1) & ~1;  // the seed list must hold k entries
+  p.stride_a = static_cast<int64_t>(p.ga.groups) * p.ga.L;
+  p.stride_b = static_cast<int64_t>(p.gb.groups + 1) * p.gb.L;
   return p;
 }
 
@@ -53,8 +56,9 @@ extern "C" int64_t sgpt_search_workspace_bytes(int nq, int64_t n, int k) {
   if (nq > kQueryBlock) nq = kQueryBlock;  // larger batches are processed in blocks that reuse the workspace
   const Plan p = make_plan(nq, n, k);
   if (!p.two_pass) return static_cast<int64_t>(nq) * padded_cols(n) * 4 + 256;
-  return align256(static_cast<int64_t>(nq) * p.cap_a * 8) + align256(static_cast<int64_t>(nq) * p.cap_b * 8) +
-         align256(nq * 4) * 3 + 256;
+  return align256(static_cast<int64_t>(nq) * p.stride_a * 8) + align256(static_cast<int64_t>(nq) * p.stride_b * 8) +
+         align256(static_cast<int64_t>(p.ga.groups) * nq * 4) + align256(static_cast<int64_t>(p.gb.groups + 1) * nq * 4) +
+         align256(nq * 4) + 256;
 }
 
 extern "C" int sgpt_search(const void* Q, const void* Cm, const float* q_scale, const float* c_scale, int nq,
@@ -90,49 +94,54 @@ extern "C" int sgpt_search(const void* Q, const void* Cm, const float* q_scale, 
 
   uint8_t* w = static_cast<uint8_t*>(ws);
   uint2* cand_a = reinterpret_cast<uint2*>(w);
-  w += align256(static_cast<int64_t>(nq) * p.cap_a * 8);
+  w += align256(static_cast<int64_t>(nq) * p.stride_a * 8);
   uint2* cand_b = reinterpret_cast<uint2*>(w);
-  w += align256(static_cast<int64_t>(nq) * p.cap_b * 8);
+  w += align256(static_cast<int64_t>(nq) * p.stride_b * 8);
   int* cnt_a = reinterpret_cast<int*>(w);
-  w += align256(nq * 4);
+  const int64_t cnt_a_bytes = align256(static_cast<int64_t>(p.ga.groups) * nq * 4);
+  w += cnt_a_bytes;
   int* cnt_b = reinterpret_cast<int*>(w);
-  w += align256(nq * 4);
+  const int64_t cnt_b_bytes = align256(static_cast<int64_t>(p.gb.groups + 1) * nq * 4);
+  w += cnt_b_bytes;
   float* tau = reinterpret_cast<float*>(w);
 
-  SGPT_CHECK_CUDA(cudaMemsetAsync(cnt_a, 0, sizeof(int) * nq, stream));
+  // every group of a launch writes its own counts; the memset covers groups of CTAs that do not exist (tiny grids)
+  SGPT_CHECK_CUDA(cudaMemsetAsync(cnt_a, 0, cnt_a_bytes + cnt_b_bytes, stream));
   // pass A: every score of the sampled tiles
-  int rc = launch_filter_candidates(Q, Cm, q_scale, c_scale, nullptr, cand_a, cnt_a, p.cap_a, nq, static_cast<int>(n),
-                                    D, /*tile_mode=*/1, p.stride, stream);
+  int rc = launch_filter_candidates(Q, Cm, q_scale, c_scale, nullptr, cand_a, cnt_a, p.stride_a, p.ga.L, 0, nq,
+                                    static_cast<int>(n), D, /*tile_mode=*/1, p.stride, stream);
   if (rc != SGPT_OK) return rc;
-  // thresholds + seed winners (sorted head of cand_b, cnt_b = number of seeds)
+  // thresholds + seed winners (group 0 of the pass-B lists)
   {
     TopkSrc src{};
     src.packed = cand_a;
     src.counts = cnt_a;
-    src.G = 1;
+    src.G = p.ga.groups;
     src.nq = nq;
-    src.L = p.cap_a;
-    src.stride_q = p.cap_a;
+    src.L = p.ga.L;
+    src.stride_g = p.ga.L;
+    src.stride_q = p.stride_a;
     TopkExtra ex{};
     ex.packed = cand_b;
     ex.count = cnt_b;
-    ex.cap = p.cap_b;
+    ex.cap = p.stride_b;
     ex.tau = tau;
     rc = launch_topk_select(src, nq, k, nullptr, nullptr, stream, ex);
     if (rc != SGPT_OK) return rc;
   }
   // pass B: the rest of the shard, admission threshold tau[q]
-  rc = launch_filter_candidates(Q, Cm, q_scale, c_scale, tau, cand_b, cnt_b, p.cap_b, nq, static_cast<int>(n), D,
-                                /*tile_mode=*/2, p.stride, stream);
+  rc = launch_filter_candidates(Q, Cm, q_scale, c_scale, tau, cand_b, cnt_b, p.stride_b, p.gb.L, 1, nq,
+                                static_cast<int>(n), D, /*tile_mode=*/2, p.stride, stream);
   if (rc != SGPT_OK) return rc;
   // final exact selection over the candidates
   TopkSrc src{};
   src.packed = cand_b;
   src.counts = cnt_b;
   src.id_base = id_base;
-  src.G = 1;
+  src.G = p.gb.groups + 1;
   src.nq = nq;
-  src.L = p.cap_b;
-  src.stride_q = p.cap_b;
+  src.L = p.gb.L;
+  src.stride_g = p.gb.L;
+  src.stride_q = p.stride_b;
   return launch_topk_select(src, nq, k, out_scores, out_ids, stream);
 }

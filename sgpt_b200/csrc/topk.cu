@@ -58,42 +58,116 @@ __device__ __forceinline__ long long list_len(const TopkSrc& s, int q, int g) {
 constexpr int kTopkThreads = 1024;
 constexpr int kBins = 2048;
 
+constexpr int kMaxFlatLists = 1024;
+constexpr int kSubCap = 8192;  // cached mode: keys sharing the k-th key's first radix digit are compacted into smem
+
+// Visit every element of query q's lists: f(g, i, valid).  With at most kMaxFlatLists lists (always, in practice) the
+// lists are laid end to end in a flat index space — each padded to a multiple of 32 so that the 32 lanes of a warp are
+// always inside the same list — and all 1024 threads stride that space; the list of a flat index is found by binary
+// search in the shared prefix array `off`.  This keeps every thread busy for one long list (dense rows), a few
+// (cross-shard merges) or hundreds of short ones (the per-(CTA, half) candidate lists of the fused search).
+// kPad also visits the padding (valid = false) so that warps stay converged for __match_any_sync.
+template <bool kPad, class F>
+__device__ __forceinline__ void for_each_elem(const TopkSrc& s, int q, int tid, const uint32_t* off,
+                                              const uint32_t* len, F&& f) {
+  if (s.G <= kMaxFlatLists) {
+    const uint32_t total = off[s.G];
+    for (uint32_t j = tid; j < total; j += kTopkThreads) {
+      int lo = 0, hi = s.G;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= j) lo = mid; else hi = mid;
+      }
+      const uint32_t i = j - off[lo];
+      const bool valid = i < len[lo];
+      if (kPad || valid) f(lo, static_cast<long long>(i), valid);
+    }
+  } else {
+    for (int g = 0; g < s.G; ++g) {
+      const long long n = list_len(s, q, g);
+      const long long end = kPad ? ((n + 31) & ~31ll) : n;
+      for (long long i = tid; i < end; i += kTopkThreads) f(g, i, i < n);
+    }
+  }
+}
+
 // sorted[] / sorted_id[]: KP (power of two >= k) slots in dynamic smem
-__global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, int k, int KP,
+// ckeys[]: when the flat (padded) index space of the query fits `cache_keys` entries of dynamic smem behind the sort
+// buffers, every key is fetched from global memory ONCE (one warp per list, several loads in flight) and the three
+// histogram passes and the winner scan run out of shared memory; otherwise every pass re-reads global memory.
+__global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc src, int k, int KP, uint32_t cache_keys,
                                                                    float* __restrict__ out_scores,
                                                                    long long* __restrict__ out_ids, TopkExtra extra) {
   extern __shared__ uint8_t dsm[];
   uint32_t* skey = reinterpret_cast<uint32_t*>(dsm);
   long long* sid = reinterpret_cast<long long*>(dsm + static_cast<size_t>(KP) * 4);
+  uint32_t* sub_key = reinterpret_cast<uint32_t*>(dsm + static_cast<size_t>(KP) * 12);  // survivors of the first digit
+  uint32_t* ckeys = sub_key + kSubCap;
+  __shared__ uint32_t s_sub_n;
   __shared__ uint32_t hist[kBins];
   __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t s_off[kMaxFlatLists + 1];  // padded list offsets in the flat index space
+  __shared__ uint32_t s_len[kMaxFlatLists];
   __shared__ uint32_t s_bin, s_need, s_cnt_gt, s_cnt_eq;
-  __shared__ unsigned long long s_total;
+  __shared__ uint32_t s_total;  // < 2^32 (checked by the launcher)
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
+  // flat index space over the lists: s_len[g], s_off[g] = sum of the padded lengths of lists < g (block-wide scan)
+  if (src.G <= kMaxFlatLists) {
+    const uint32_t mylen = (tid < src.G) ? static_cast<uint32_t>(list_len(src, q, tid)) : 0u;
+    const uint32_t mypad = (mylen + 31u) & ~31u;
+    uint32_t incl = mypad;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    if (tid < src.G) {
+      s_len[tid] = mylen;
+      s_off[tid + 1] = base + incl;
+    }
+    if (tid == 0) s_off[0] = 0;
+  }
   // number of valid elements (needed to cap k)
   if (tid == 0) s_total = 0;
   __syncthreads();
-  {
-    unsigned long long local = 0;
-    for (int g = 0; g < src.G; ++g) {
-      const long long len = list_len(src, q, g);
-      if (src.ids == nullptr) {
-        if (tid == 0) local += static_cast<unsigned long long>(len);
-      } else {
-        for (long long i = tid; i < len; i += kTopkThreads) local += (load_elem(src, q, g, i).key != 0);
-      }
+  const bool cached = (src.G <= kMaxFlatLists) && (s_off[src.G <= kMaxFlatLists ? src.G : 0] <= cache_keys);
+  const uint32_t flat_total = cached ? s_off[src.G] : 0u;
+  if (cached) {
+    // one warp per list; the iterations are independent, so the loads of several chunks are in flight together
+    for (int g = warp; g < src.G; g += kTopkThreads / 32) {
+      const uint32_t len = s_len[g], base = s_off[g], end = (len + 31u) & ~31u;
+#pragma unroll 4
+      for (uint32_t i = lane; i < end; i += 32) ckeys[base + i] = (i < len) ? load_elem(src, q, g, i).key : 0u;
     }
-    if (local) atomicAdd(&s_total, local);
+    __syncthreads();
+  }
+  {
+    uint32_t local = 0;
+    if (cached) {
+      for (uint32_t j = tid; j < flat_total; j += kTopkThreads) local += (ckeys[j] != 0);
+    } else if (src.ids == nullptr) {
+      for (int g = tid; g < src.G; g += kTopkThreads) local += static_cast<uint32_t>(list_len(src, q, g));
+    } else {
+      for_each_elem<false>(src, q, tid, s_off, s_len, [&](int g, long long i, bool) { local += (load_elem(src, q, g, i).key != 0); });
+    }
+    local = __reduce_add_sync(0xffffffffu, local);  // 64-bit shared atomics are CAS loops: one 32-bit add per warp
+    if (lane == 0 && local) atomicAdd(&s_total, local);
   }
   __syncthreads();
-  const unsigned long long total = s_total;
-  const uint32_t kk = static_cast<uint32_t>(total < static_cast<unsigned long long>(k) ? total : k);
+  const uint32_t total = s_total;
+  const uint32_t kk = total < static_cast<uint32_t>(k) ? total : static_cast<uint32_t>(k);
 
   uint32_t prefix = 0, mask = 0, need = kk;
+  uint32_t sub_n = 0;
+  bool use_sub = false;  // digits 2 and 3 run over the compacted survivors of digit 1 instead of all keys
   if (kk > 0) {
     const int shifts[3] = {21, 10, 0};
     const uint32_t widths[3] = {11, 11, 10};
@@ -103,20 +177,20 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
       const uint32_t bmask = (1u << widths[pass]) - 1u;
       for (int i = tid; i < kBins; i += kTopkThreads) hist[i] = 0;
       __syncthreads();
-      for (int g = 0; g < src.G; ++g) {
-        const long long len = list_len(src, q, g);
-        const long long len_pad = (len + 31) & ~31ll;  // keep warps converged for match_any
-        for (long long i = tid; i < len_pad; i += kTopkThreads) {
-          uint32_t key = 0;
-          bool ok = false;
-          if (i < len) {
-            key = load_elem(src, q, g, i).key;
-            ok = (key != 0) && ((key & mask) == prefix);
-          }
-          const uint32_t bin = ok ? ((key >> shift) & bmask) : 0xffffffffu;
-          const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-          if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
-        }
+      auto tally = [&](uint32_t key) {  // executed by converged warps
+        const bool ok = (key != 0) && ((key & mask) == prefix);
+        const uint32_t bin = ok ? ((key >> shift) & bmask) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+      };
+      if (use_sub) {
+        for (uint32_t j = tid; j < ((sub_n + 31u) & ~31u); j += kTopkThreads) tally(j < sub_n ? sub_key[j] : 0u);
+      } else if (cached) {
+        for (uint32_t j = tid; j < flat_total; j += kTopkThreads) tally(ckeys[j]);
+      } else {
+        for_each_elem<true>(src, q, tid, s_off, s_len, [&](int g, long long i, bool valid) {
+          tally(valid ? load_elem(src, q, g, i).key : 0u);
+        });
       }
       __syncthreads();
       // suffix scan over bins: thread t owns bins 2t, 2t+1
@@ -145,6 +219,21 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
       prefix |= s_bin << shift;
       mask |= bmask << shift;
       need = s_need;
+      if (pass == 0 && cached) {
+        // compact the keys that share the selected first digit (typically a few hundred to a few thousand)
+        if (tid == 0) s_sub_n = 0;
+        __syncthreads();
+        for (uint32_t j = tid; j < flat_total; j += kTopkThreads) {
+          const uint32_t key = ckeys[j];
+          if (key != 0 && (key & mask) == prefix) {
+            const uint32_t slot = atomicAdd(&s_sub_n, 1u);
+            if (slot < kSubCap) sub_key[slot] = key;
+          }
+        }
+        __syncthreads();
+        sub_n = s_sub_n;
+        use_sub = sub_n <= kSubCap;
+      }
       __syncthreads();
     }
   }
@@ -154,28 +243,40 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
   __syncthreads();
   if (kk > 0) {
     const uint32_t n_gt = kk - need;
-    for (int g = 0; g < src.G; ++g) {
-      const long long len = list_len(src, q, g);
-      for (long long i = tid; i < len; i += kTopkThreads) {
-        const Elem e = load_elem(src, q, g, i);
-        if (e.key == 0) continue;
-        if (e.key > prefix) {
-          const uint32_t slot = atomicAdd(&s_cnt_gt, 1u);
-          skey[slot] = e.key;
-          sid[slot] = e.id;
-        } else if (e.key == prefix) {
-          const uint32_t s = atomicAdd(&s_cnt_eq, 1u);
-          if (s < need) {
-            skey[n_gt + s] = e.key;
-            sid[n_gt + s] = e.id;
-          }
+    auto place = [&](uint32_t key, int g, long long i) {  // winners only: fetch the id
+      if (key > prefix) {
+        const uint32_t slot = atomicAdd(&s_cnt_gt, 1u);
+        skey[slot] = key;
+        sid[slot] = load_elem(src, q, g, i).id;
+      } else {
+        const uint32_t s = atomicAdd(&s_cnt_eq, 1u);
+        if (s < need) {
+          skey[n_gt + s] = key;
+          sid[n_gt + s] = load_elem(src, q, g, i).id;
         }
       }
+    };
+    if (cached) {
+      for (uint32_t j = tid; j < flat_total; j += kTopkThreads) {
+        const uint32_t key = ckeys[j];
+        if (key == 0 || key < prefix) continue;
+        int lo = 0, hi = src.G;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_off[mid] <= j) lo = mid; else hi = mid;
+        }
+        place(key, lo, static_cast<long long>(j - s_off[lo]));
+      }
+    } else {
+      for_each_elem<false>(src, q, tid, s_off, s_len, [&](int g, long long i, bool) {
+        const uint32_t key = load_elem(src, q, g, i).key;
+        if (key != 0 && key >= prefix) place(key, g, i);
+      });
     }
   }
   __syncthreads();
-  // bitonic sort, descending by key then ascending by id
-  for (int size = 2; size <= KP; size <<= 1) {
+  // bitonic sort, descending by key then ascending by id (skipped when only the threshold / unordered seeds are wanted)
+  for (int size = 2; size <= KP && out_scores != nullptr; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = tid; i < KP / 2; i += kTopkThreads) {
         const int lo = 2 * i - (i & (stride - 1));
@@ -209,7 +310,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(TopkSrc src, 
     if (tid == 0) extra.count[q] = static_cast<int>(kk);
   }
   if (extra.tau != nullptr && tid == 0)
-    extra.tau[q] = (kk >= static_cast<uint32_t>(k)) ? key_score(skey[k - 1]) : -INFINITY;
+    extra.tau[q] = (kk >= static_cast<uint32_t>(k)) ? key_score(prefix) : -INFINITY;  // key of the k-th best
 }
 
 int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
@@ -218,17 +319,30 @@ int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int
     set_error("top-k: k=%d outside [1, 4096]", k);
     return SGPT_ERR_INVALID;
   }
+  if (static_cast<long long>(src.G) * ((src.L + 31) & ~31ll) >= (1ll << 32)) {
+    set_error("top-k: %d lists of %lld entries exceed the 2^32-entry selection space", src.G, src.L);
+    return SGPT_ERR_INVALID;
+  }
   int KP = 2;
   while (KP < k) KP <<= 1;
-  const size_t dsm = static_cast<size_t>(KP) * 12;
+  // dynamic smem: sort buffers (KP x 12 B) + as many cached keys as the rest of the SM's shared memory holds
+  constexpr size_t kDynMax = 208 * 1024;  // 227 KB per CTA minus the kernel's static arrays
+  size_t cache_keys = 0;
+  if (src.G <= kMaxFlatLists) {
+    const size_t want = static_cast<size_t>(src.G) * static_cast<size_t>((src.L + 31) & ~31ll);  // padded worst case
+    const size_t room = (kDynMax - static_cast<size_t>(KP) * 12 - kSubCap * 4) / 4;
+    cache_keys = want < room ? want : room;
+  }
+  const size_t dsm = static_cast<size_t>(KP) * 12 + kSubCap * 4 + cache_keys * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    SGPT_CHECK_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));
+    SGPT_CHECK_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kDynMax)));
     attr_set = true;
   }
   LaunchScope _ls(kCatTopk, stream);
-  topk_select_kernel<<<nq, kTopkThreads, dsm, stream>>>(src, k, KP, out_scores, reinterpret_cast<long long*>(out_ids),
-                                                        extra);
+  topk_select_kernel<<<nq, kTopkThreads, dsm, stream>>>(src, k, KP, static_cast<uint32_t>(cache_keys), out_scores,
+                                                        reinterpret_cast<long long*>(out_ids), extra);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }
