@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
 
     // ---- online softmax over this row's 128 scores (pass 1: row maximum) ----
     const int kv0 = j * kAttnTile;
-    float mx = -INFINITY;
+    float mx = -INFINITY, mxa = -INFINITY;  // raw-score maximum (no ALiBi) / scaled+biased maximum (ALiBi)
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
@@ -160,20 +160,37 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
       uint32_t v[32];
       tmem_ld_32x32(tS + lane_off + c * 32, v);
       tmem_ld_wait();
-      if (c_hi <= w_hi_min && c_lo >= w_lo_max && slope2 == 0.f) {
+      const bool unmasked = (c_hi <= w_hi_min && c_lo >= w_lo_max);  // warp-uniform
+      if (slope2 == 0.f) {
+        // no ALiBi: the maximum is taken over the raw scores, the (positive) scale is applied once after the reduction
+        if (unmasked) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));  // scale applied after the reduction
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kp = c_lo + i;
+            if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
       } else {
+        // ALiBi: maximum of the scaled, biased scores s * sl2 + slope2 * key_pos (two FMAs per element)
+        const float ab = slope2 * static_cast<float>(c_lo);
+        if (unmasked) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kp = c_lo + i;
-          const float s = (slope2 == 0.f) ? __uint_as_float(v[i])
-                                          : fmaf(__uint_as_float(v[i]), sl2, slope2 * static_cast<float>(kp)) / sl2;
-          if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, s);
+          for (int i = 0; i < 32; ++i)
+            mxa = fmaxf(mxa, fmaf(__uint_as_float(v[i]), sl2, fmaf(slope2, static_cast<float>(i), ab)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kp = c_lo + i;
+            const float t = fmaf(__uint_as_float(v[i]), sl2, fmaf(slope2, static_cast<float>(i), ab));
+            if (kp <= vis_hi && kp >= vis_lo) mxa = fmaxf(mxa, t);
+          }
         }
       }
     }
-    const float m_new = fmaxf(m_run, mx * sl2);  // sl2 > 0
+    const float m_new = fmaxf(m_run, (slope2 == 0.f) ? mx * sl2 : mxa);  // sl2 > 0
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
     const float alpha = exp2f(m_run - m_use);
     float lsum = 0.f;
@@ -195,24 +212,51 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_off + c * 32, v);
         tmem_ld_wait();
-        if (c_hi <= w_hi_min && c_lo >= w_lo_max && slope2 == 0.f) {
+        const bool unmasked = (c_hi <= w_hi_min && c_lo >= w_lo_max);  // warp-uniform
+        if (slope2 == 0.f) {
+          if (unmasked) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
-            const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
-            lsum += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
+              const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
+              lsum += p0 + p1;
+              pk[i] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int kp = c_lo + 2 * i;
+              float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
+              float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
+              if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
+              if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
+              lsum += p0 + p1;
+              pk[i] = pack_bf16(p0, p1);
+            }
           }
         } else {
+          const float ab = fmaf(slope2, static_cast<float>(c_lo), -m_use);  // slope2 * key_pos - m, position part
+          if (unmasked) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int kp = c_lo + 2 * i;
-            float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, slope2 * static_cast<float>(kp)) - m_use);
-            float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, slope2 * static_cast<float>(kp + 1)) - m_use);
-            if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
-            if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
-            lsum += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, fmaf(slope2, static_cast<float>(2 * i), ab)));
+              const float p1 =
+                  exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, fmaf(slope2, static_cast<float>(2 * i + 1), ab)));
+              lsum += p0 + p1;
+              pk[i] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int kp = c_lo + 2 * i;
+              float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, fmaf(slope2, static_cast<float>(2 * i), ab)));
+              float p1 =
+                  exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, fmaf(slope2, static_cast<float>(2 * i + 1), ab)));
+              if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
+              if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
+              lsum += p0 + p1;
+              pk[i] = pack_bf16(p0, p1);
+            }
           }
         }
       }
