@@ -97,9 +97,20 @@ int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seqlens, int B,
 #define SGPT_POOL_MEAN 0
 #define SGPT_POOL_WEIGHTEDMEAN 1
 #define SGPT_POOL_LASTTOKEN 2
+/* All-hidden-state modes, accepted by sgpt_encode only: the mean over the L+1 hidden states (embedding output, every
+ * block output, ln_f of the last) of the per-state mean / last-token embedding — BDR:243-257 (meanmean: the mask sum is
+ * the same for every layer, so sum/sum == mean of means) and BDR:284-301 (lasttokenmean).  layer_idx is ignored, as in
+ * the reference. */
+#define SGPT_POOL_MEANMEAN 3
+#define SGPT_POOL_LASTTOKENMEAN 4
 int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma, const float* beta,
               float eps, float* out, float* row_stats_ws /* fp32[2*T] scratch */, int B, int T, int d, int mode,
               int clamp_denominator, int normalize, sgpt_stream_t stream);
+/* Building block of the all-hidden-state modes: out = (accumulate ? out : 0) + out_scale * pool(x); mode is one of
+ * MEAN / WEIGHTEDMEAN / LASTTOKEN; normalize (if set) acts on the accumulated rows, so pass it with the last state. */
+int sgpt_pool_accumulate(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                         const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d, int mode,
+                         int clamp_denominator, int normalize, int accumulate, float out_scale, sgpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Whole-encoder handle (F1..F7 + P1 in one call).

@@ -55,6 +55,26 @@ def last_token(hidden: torch.Tensor, attention_mask: torch.Tensor, st_variant: b
     return hidden[torch.arange(B), idx]
 
 
+def mean_mean(all_hidden, attention_mask: torch.Tensor) -> torch.Tensor:
+    """meanmean, BDR:243-257: sum over ALL L+1 hidden states and all tokens of h * mask, divided by the equally expanded
+    mask sum — i.e. the average over the hidden states of the per-state masked mean."""
+    hs = torch.stack(list(all_hidden))  # BDR:246  [L+1, B, S, d]
+    m = attention_mask.unsqueeze(-1).expand(hs.shape[1:]).float().unsqueeze(0).expand(hs.size())  # BDR:248
+    num = torch.sum(torch.sum(hs * m, dim=2), dim=0)  # BDR:252-254
+    den = m.sum(dim=2).sum(dim=0)  # BDR:255
+    return num / den  # BDR:257
+
+
+def last_token_mean(all_hidden, attention_mask: torch.Tensor) -> torch.Tensor:
+    """lasttokenmean, BDR:284-301: the last attended token (index len-1, BDR:198) gathered from every hidden state,
+    averaged over the L+1 states."""
+    hs = torch.stack(list(all_hidden))  # BDR:288
+    B = hs.shape[1]
+    idx = torch.clamp(attention_mask.long().sum(dim=1) - 1, min=0)
+    emb = hs[:, torch.arange(B), idx]  # BDR:291-298  [L+1, B, d]
+    return torch.mean(emb, 0)  # BDR:301
+
+
 def normalize(x: torch.Tensor) -> torch.Tensor:
     """models/Normalize.py:13-14: F.normalize(p=2, dim=1) == x / max(||x||, 1e-12)."""
     return x / torch.clamp(torch.linalg.vector_norm(x, dim=1, keepdim=True), min=1e-12)

@@ -13,7 +13,7 @@ using it without the library raises.
 from .config import ModelConfig, preset  # noqa: F401
 
 __all__ = ["ModelConfig", "preset", "Encoder", "CustomEmbedder", "SentenceEncoder", "SentenceBERTBOSEOS",
-           "DenseRetrievalExactSearch", "CorpusShard", "merge_topk", "sharded_search"]
+           "DenseRetrievalExactSearch", "CorpusShard", "merge_topk", "semantic_search", "sharded_search"]
 
 
 def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
@@ -26,7 +26,7 @@ def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
     if name == "DenseRetrievalExactSearch":
         from .exact_search import DenseRetrievalExactSearch
         return DenseRetrievalExactSearch
-    if name in ("CorpusShard", "merge_topk"):
+    if name in ("CorpusShard", "merge_topk", "semantic_search"):
         from . import index
         return getattr(index, name)
     if name == "sharded_search":

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libsgpt_b200.so")
 
 SGPT_OK = 0
 EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32 = 0, 1, 2
-POOL_MEAN, POOL_WEIGHTEDMEAN, POOL_LASTTOKEN = 0, 1, 2
+POOL_MEAN, POOL_WEIGHTEDMEAN, POOL_LASTTOKEN, POOL_MEANMEAN, POOL_LASTTOKENMEAN = 0, 1, 2, 3, 4
 ARCH_GPT_NEO, ARCH_GPTJ, ARCH_BLOOM = 0, 1, 2
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -46,6 +46,7 @@ _SIGNATURES = {
     "sgpt_linear": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp]),
     "sgpt_attention": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp, i32, vp]),
     "sgpt_pool": (i32, [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "sgpt_pool_accumulate": (i32, [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
     "sgpt_model_create": (i32, [C.POINTER(ModelConfigC), C.POINTER(ModelWeightsC), C.POINTER(vp)]),
     "sgpt_model_destroy": (None, [vp]),
     "sgpt_encode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x,
                                                    const int32_t* __restrict__ cu, const float2* __restrict__ stats,
                                                    const float4* __restrict__ g, const float4* __restrict__ bta,
                                                    float4* __restrict__ out, float* __restrict__ sumsq, int d4,
-                                                   int mode, int clamp_den) {
+                                                   int mode, int clamp_den, int accumulate, float out_scale) {
   __shared__ float4 part[4][32];
   __shared__ float wpart[4];
   const int b = blockIdx.x;
@@ -233,6 +233,12 @@ __global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x,
       o.z = (gg.z * a.z + bb.z * W) / den; o.w = (gg.w * a.w + bb.w * W) / den;
     } else {
       o.x = a.x / den; o.y = a.y / den; o.z = a.z / den; o.w = a.w / den;
+    }
+    // all-layer modes (meanmean / lasttokenmean): out = [out +] out_scale * pooled(this hidden state)
+    o.x *= out_scale; o.y *= out_scale; o.z *= out_scale; o.w *= out_scale;
+    if (accumulate && col_ok) {
+      const float4 prev = out[static_cast<size_t>(b) * d4 + col];
+      o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
     }
     if (col_ok) out[static_cast<size_t>(b) * d4 + col] = o;
     if (sumsq != nullptr) {
@@ -341,12 +347,14 @@ extern "C" int sgpt_layernorm_f32_inplace(float* x, const float* gamma, const fl
   return SGPT_OK;
 }
 
-extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
-                         const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d, int mode,
-                         int clamp_denominator, int normalize, sgpt_stream_t stream_) {
+extern "C" int sgpt_pool_accumulate(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                                    const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d,
+                                    int mode, int clamp_denominator, int normalize, int accumulate, float out_scale,
+                                    sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(d > 0 && d % 4 == 0, "sgpt_pool: d=%d must be a positive multiple of 4", d);
-  SGPT_REQUIRE(mode >= 0 && mode <= 2, "sgpt_pool: unknown mode %d", mode);
+  SGPT_REQUIRE(mode >= SGPT_POOL_MEAN && mode <= SGPT_POOL_LASTTOKEN,
+               "sgpt_pool: mode %d is not a single-hidden-state pooling mode", mode);
   SGPT_REQUIRE(mode != SGPT_POOL_WEIGHTEDMEAN || pos != nullptr, "sgpt_pool: weightedmean needs pos");
   SGPT_REQUIRE((gamma == nullptr) == (beta == nullptr), "sgpt_pool: gamma and beta must be given together");
   SGPT_REQUIRE(gamma == nullptr || row_stats_ws != nullptr, "sgpt_pool: ln_f fusion needs row_stats_ws");
@@ -370,7 +378,8 @@ extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_s
   dim3 grid(B, (d4 + 31) / 32);
   pool_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float4*>(x), pos, cu_seqlens, stats,
                                         reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
-                                        reinterpret_cast<float4*>(out), sumsq, d4, mode, clamp_denominator);
+                                        reinterpret_cast<float4*>(out), sumsq, d4, mode, clamp_denominator, accumulate,
+                                        out_scale);
   SGPT_CHECK_CUDA(cudaGetLastError());
   if (normalize) {
     l2_scale_rows_kernel<<<grid_for(static_cast<long long>(B) * d4, 256), 256, 0, stream>>>(
@@ -378,6 +387,13 @@ extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_s
     SGPT_CHECK_CUDA(cudaGetLastError());
   }
   return SGPT_OK;
+}
+
+extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                         const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d, int mode,
+                         int clamp_denominator, int normalize, sgpt_stream_t stream_) {
+  return sgpt_pool_accumulate(x, pos, cu_seqlens, gamma, beta, eps, out, row_stats_ws, B, T, d, mode, clamp_denominator,
+                              normalize, /*accumulate=*/0, /*out_scale=*/1.0f, stream_);
 }
 
 extern "C" int sgpt_row_inv_norms(const void* x, float* inv_norm, int64_t n, int D, sgpt_stream_t stream_) {

@@ -153,6 +153,12 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
                B, T, c.max_batch, c.max_tokens);
   SGPT_REQUIRE(c.arch == SGPT_ARCH_BLOOM || max_seqlen <= c.max_pos,
                "sgpt_encode: max_seqlen %d exceeds max_position_embeddings %d", max_seqlen, c.max_pos);
+  // meanmean / lasttokenmean (BDR:243-257, 284-301) average the mean / last-token embedding of ALL L+1 hidden states
+  const bool all_layers = (pool_mode == SGPT_POOL_MEANMEAN || pool_mode == SGPT_POOL_LASTTOKENMEAN);
+  const int base_mode = pool_mode == SGPT_POOL_MEANMEAN ? SGPT_POOL_MEAN
+                        : pool_mode == SGPT_POOL_LASTTOKENMEAN ? SGPT_POOL_LASTTOKEN : pool_mode;
+  const float layer_scale = all_layers ? 1.0f / static_cast<float>(c.n_layer + 1) : 1.0f;
+  if (all_layers) layer_idx = c.n_layer;  // the reference ignores layeridx for these modes
   if (layer_idx < 0) layer_idx += c.n_layer + 1;
   SGPT_REQUIRE(layer_idx >= 0 && layer_idx <= c.n_layer, "sgpt_encode: layer index out of range for %d hidden states",
                c.n_layer + 1);
@@ -168,6 +174,9 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
   const int n_run = layer_idx;  // hidden_states[i] is the input of block i; hidden_states[L] is ln_f(output of block L-1)
   for (int l = 0; l < n_run && l < c.n_layer; ++l) {
     const sgpt_layer_weights& lw = m->layers[l];
+    if (all_layers)  // hidden_states[l] = the residual stream entering block l (no ln_f)
+      SGPT_TRY(sgpt_pool_accumulate(m->resid, pos, cu_seqlens, nullptr, nullptr, c.ln_eps, out, m->stats, B, T, d,
+                                    base_mode, clamp_denominator, 0, /*accumulate=*/l > 0, layer_scale, stream));
     SGPT_TRY(sgpt_layernorm(m->resid, lw.ln1_g, lw.ln1_b, m->xn, T, d, c.ln_eps, stream));
     if (c.arch == SGPT_ARCH_GPT_NEO) {
       SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
@@ -199,8 +208,10 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
     }
   }
   const bool final_ln = (layer_idx == c.n_layer);
-  SGPT_TRY(sgpt_pool(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr,
-                     c.ln_eps, out, m->stats, B, T, d, pool_mode, clamp_denominator, normalize, stream));
+  SGPT_TRY(sgpt_pool_accumulate(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr,
+                                final_ln ? m->w.lnf_b : nullptr, c.ln_eps, out, m->stats, B, T, d, base_mode,
+                                clamp_denominator, normalize, /*accumulate=*/all_layers && c.n_layer > 0, layer_scale,
+                                stream));
   return SGPT_OK;
 }
 

@@ -26,7 +26,8 @@ logger = logging.getLogger(__name__)
 SPECB_QUE_BOS, SPECB_QUE_EOS = "[", "]"   # beir_dense_retriever.py:100-101
 SPECB_DOC_BOS, SPECB_DOC_EOS = "{", "}"   # beir_dense_retriever.py:103-104
 
-METHODS = ("mean", "weightedmean", "lasttoken")
+METHODS = ("mean", "weightedmean", "lasttoken", "meanmean", "lasttokenmean")  # BDR:238-301
+ST_POOLING = ("mean", "weightedmean", "lasttoken")  # single-hidden-state modes of ST/models/Pooling.py
 
 
 def _pad_batch(seqs: Sequence[Sequence[int]], pad_id: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -50,8 +51,8 @@ class CustomEmbedder:
         caller hand the model over directly (no hub access offline); otherwise they are loaded with HF
         ``AutoConfig``/``AutoModel``/``AutoTokenizer`` from ``model_name`` exactly like BDR:123,138."""
         if method not in METHODS:
-            raise NotImplementedError(f"pooling method {method!r}: built so far: {METHODS} "
-                                      "(meanmean / lasttokenmean / poolout are next, SURVEY.md §8f)")
+            raise NotImplementedError(f"pooling method {method!r}: built: {METHODS} (poolout needs a pooler head the "
+                                      "GPT models of the reference do not have, BDR:303-304)")
         if save_emb:
             logger.warning("save_emb pickle cache (BDR:311-323) is not implemented; embeddings are recomputed")
         if state_dict is None:
@@ -154,8 +155,8 @@ class SentenceEncoder:
     def __init__(self, config: ModelConfig, state_dict: Dict[str, torch.Tensor], tokenizer, device: str = "cuda:0",
                  pooling: str = "weightedmean", max_seq_length: int = 300, batch_capacity: int = 256,
                  max_tokens: Optional[int] = None):
-        if pooling not in METHODS:
-            raise NotImplementedError(f"pooling mode {pooling!r} not in {METHODS}")
+        if pooling not in ST_POOLING:
+            raise NotImplementedError(f"pooling mode {pooling!r} not in {ST_POOLING}")
         self.config, self.tokenizer, self.pooling = config, tokenizer, pooling
         self.max_seq_length = max_seq_length
         self.encoder = Encoder(config, state_dict, device=device,

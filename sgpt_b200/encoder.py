@@ -16,7 +16,8 @@ import torch
 from . import _lib
 from .config import ModelConfig
 
-POOL_MODES = {"mean": _lib.POOL_MEAN, "weightedmean": _lib.POOL_WEIGHTEDMEAN, "lasttoken": _lib.POOL_LASTTOKEN}
+POOL_MODES = {"mean": _lib.POOL_MEAN, "weightedmean": _lib.POOL_WEIGHTEDMEAN, "lasttoken": _lib.POOL_LASTTOKEN,
+              "meanmean": _lib.POOL_MEANMEAN, "lasttokenmean": _lib.POOL_LASTTOKENMEAN}
 
 
 def pack_ragged(input_ids, attention_mask) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:

@@ -6,8 +6,11 @@ HBM speed) plus fp32 1/||row|| of the STORED rows, so cosine scores are exactly 
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import json
+import os
+from typing import Dict, List, Optional, Tuple, Union
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -75,6 +78,35 @@ class CorpusShard:
     def stored(self) -> torch.Tensor:
         return self.vectors[:self.n]
 
+    # ---- persistence (replaces the pickle-per-chunk embedding cache of BDR:311-323, 336-342) ----------------------
+    def save(self, path: str) -> None:
+        """Write the shard as ``path/{vectors.npy (bf16 bit patterns as uint16), inv_norms.npy, meta.json}``; one
+        directory per rank for a sharded corpus."""
+        os.makedirs(path, exist_ok=True)
+        np.save(os.path.join(path, "vectors.npy"), self.stored().view(torch.int16).cpu().numpy().view(np.uint16))
+        np.save(os.path.join(path, "inv_norms.npy"), self.inv_norms[:self.n].cpu().numpy())
+        with open(os.path.join(path, "meta.json"), "w") as f:
+            json.dump({"format": "sgpt_b200.CorpusShard/1", "dtype": "bf16", "dim": self.dim, "n": self.n,
+                       "id_base": self.id_base}, f)
+
+    @classmethod
+    def load(cls, path: str, device="cuda:0", capacity: Optional[int] = None) -> "CorpusShard":
+        """Reload a shard written by ``save`` (bit-identical vectors and norms, so identical search results)."""
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != "sgpt_b200.CorpusShard/1" or meta.get("dtype") != "bf16":
+            raise ValueError(f"{path}: not a CorpusShard directory ({meta})")
+        vec = np.load(os.path.join(path, "vectors.npy"), mmap_mode="r")
+        inv = np.load(os.path.join(path, "inv_norms.npy"))
+        n, dim = int(meta["n"]), int(meta["dim"])
+        if vec.shape != (n, dim) or vec.dtype != np.uint16 or inv.shape != (n,):
+            raise ValueError(f"{path}: array shapes {vec.shape}/{inv.shape} do not match meta {meta}")
+        shard = cls(dim, max(n, capacity or n), device=device, id_base=int(meta["id_base"]))
+        shard.vectors[:n].copy_(torch.from_numpy(np.array(vec).view(np.int16)).view(torch.bfloat16))
+        shard.inv_norms[:n].copy_(torch.from_numpy(inv))
+        shard.n = n
+        return shard
+
     def search(self, queries: torch.Tensor, k: int, score_function: str = "cos_sim") -> Tuple[torch.Tensor, torch.Tensor]:
         """Exact top-k of this shard for fp32/bf16 queries [Q, D] (device).
 
@@ -116,3 +148,27 @@ def merge_topk(scores: torch.Tensor, ids: torch.Tensor, exclude_ids: Optional[to
                                         _lib.ptr(exclude_ids), None, _lib.current_stream())
     _lib.check(rc, "sgpt_topk_merge")
     return out_s, out_i
+
+
+def semantic_search(query_embeddings: torch.Tensor, corpus_embeddings: Union[torch.Tensor, CorpusShard],
+                    query_chunk_size: int = 100, corpus_chunk_size: int = 500000, top_k: int = 10,
+                    score_function="cos_sim", device="cuda:0") -> List[List[Dict[str, Union[int, float]]]]:
+    """``sentence_transformers.util.semantic_search`` (ST/util.py:197-258) on the fused exact search: for every query
+    the ``top_k`` corpus entries as ``{"corpus_id", "score"}`` dicts, best first.  ``score_function`` is "cos_sim" /
+    "dot" or the reference's ``cos_sim`` / ``dot_score`` callables (recognised by name); the chunk sizes of the reference
+    are accepted and ignored — the kernel streams the whole shard once and needs no score-matrix chunks."""
+    del query_chunk_size, corpus_chunk_size
+    if callable(score_function):
+        score_function = {"cos_sim": "cos_sim", "pytorch_cos_sim": "cos_sim", "dot_score": "dot"}.get(
+            getattr(score_function, "__name__", ""), None)
+    _check_score_function(score_function)
+    q = torch.as_tensor(query_embeddings)
+    if q.dim() == 1:
+        q = q.unsqueeze(0)  # ST/util.py:214-217
+    shard = corpus_embeddings if isinstance(corpus_embeddings, CorpusShard) else CorpusShard.from_embeddings(
+        torch.as_tensor(corpus_embeddings).to(device))
+    k = min(int(top_k), shard.n)
+    scores, ids = shard.search(q.to(shard.device), k, score_function)
+    scores, ids = scores.cpu().tolist(), ids.cpu().tolist()
+    return [[{"corpus_id": int(i), "score": float(s)} for s, i in zip(srow, irow) if i >= 0]
+            for srow, irow in zip(scores, ids)]

@@ -61,6 +61,14 @@ def test_tiny_model_all_pooling_modes_vs_reference_fixture(tiny_encoder):
     mid = int(z["mid_layer"])
     got = enc.encode_tokens(ids, mask, method="weightedmean", layer_idx=mid).cpu()
     assert min_row_cosine(got, z["pooled_weightedmean_mid"]) > 1 - COS_TOL
+    # all-hidden-state modes and script lasttoken vs the EXECUTED reference pooling block (make_script_pooling.py)
+    sp = np.load(os.path.join(os.path.dirname(__file__), "golden", "script_pooling_neo_tiny.npz"))
+    for method in ("meanmean", "lasttokenmean", "lasttoken", "mean", "weightedmean"):
+        got = enc.encode_tokens(ids, mask, method=method).cpu()
+        assert min_row_cosine(got, sp["pooled_" + method]) > 1 - COS_TOL, method
+    got = enc.encode_tokens(ids, mask, method="meanmean", normalize=True).cpu()
+    assert torch.allclose(got.norm(dim=1), torch.ones(len(got)), atol=1e-5)
+    assert min_row_cosine(got, sp["pooled_meanmean"]) > 1 - COS_TOL
     # normalize + clamp flags (ST path)
     got = enc.encode_tokens(ids, mask, method="weightedmean", clamp=True, normalize=True).cpu()
     assert torch.allclose(got.norm(dim=1), torch.ones(len(got)), atol=1e-5)
@@ -306,6 +314,11 @@ def test_gptj_bloom_pooled_embeddings_vs_reference_fixture(golden_dir, name):
     assert min_row_cosine(got, z["pooled_weightedmean"]) > 1 - COS_TOL
     got = enc.encode_tokens(ids, mask, method="mean").cpu()
     assert min_row_cosine(got, z["pooled_mean"]) > 1 - COS_TOL
+    # all-hidden-state modes (BDR:243-257, 284-301) vs the executed reference pooling block
+    sp = np.load(os.path.join(golden_dir, f"script_pooling_{name}.npz"))
+    for method in ("meanmean", "lasttokenmean", "lasttoken"):
+        got = enc.encode_tokens(ids, mask, method=method).cpu()
+        assert min_row_cosine(got, sp["pooled_" + method]) > 1 - COS_TOL, method
     # per-token residual stream -> ln_f on the host vs HF's last hidden state
     enc.encode_tokens(ids, mask)
     resid = enc.last_residual().cpu()
@@ -364,3 +377,32 @@ def test_wide_gptj_hd256_and_bloom_hd128_vs_oracle():
     got = enc.encode_tokens(ids.numpy(), mask.numpy()).cpu()
     assert min_row_cosine(got, want) > 1 - COS_TOL
     enc.close()
+
+
+def test_semantic_search_matches_reference_util_and_shard_roundtrip(golden_dir, tmp_path):
+    """`semantic_search` vs the hits the reference's own util.semantic_search produced for the scoring fixture
+    (tests/golden/make_golden.py: run_scoring, chunk sizes 5/17, top_k 10), and CorpusShard.save/load reproduce the
+    search bit for bit."""
+    from sgpt_b200 import CorpusShard, semantic_search
+
+    z = np.load(os.path.join(golden_dir, "scoring.npz"))
+    q, c = torch.from_numpy(z["queries"]), torch.from_numpy(z["corpus"])
+    # D = 100 is not a multiple of 8: pad with zero columns (changes neither dot products nor norms)
+    pad = lambda x: torch.nn.functional.pad(x, (0, 4))  # noqa: E731
+    hits = semantic_search(pad(q), pad(c), query_chunk_size=5, corpus_chunk_size=17, top_k=10)
+    got_ids = np.array([[h["corpus_id"] for h in row] for row in hits])
+    got_scores = np.array([[h["score"] for h in row] for row in hits], dtype=np.float32)
+    # bf16 storage perturbs scores by ~1e-3: compare as sets with a tie band at the cut, scores within 5e-3
+    for r in range(len(hits)):
+        want = {int(i): float(s) for i, s in zip(z["hit_ids"][r], z["hit_scores"][r])}
+        cut = min(want.values())
+        for i, s in zip(got_ids[r], got_scores[r]):
+            assert (int(i) in want and abs(want[int(i)] - s) < 5e-3) or abs(s - cut) < 5e-3, (r, i, s, cut)
+        assert np.all(np.diff(got_scores[r]) <= 1e-7)  # best first
+    shard = CorpusShard.from_embeddings(pad(c).cuda(), id_base=1000)
+    s0, i0 = shard.search(pad(q).cuda(), 25, "dot")
+    shard.save(str(tmp_path / "shard0"))
+    again = CorpusShard.load(str(tmp_path / "shard0"), device="cuda:0")
+    assert again.n == shard.n and again.id_base == 1000
+    s1, i1 = again.search(pad(q).cuda(), 25, "dot")
+    assert torch.equal(s0, s1) and torch.equal(i0, i1)

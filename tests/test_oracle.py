@@ -181,3 +181,24 @@ def test_gptj_bloom_oracle_matches_hf(golden_dir, name):
         assert (hs[i] - ref[i]).abs()[mask.bool()].max().item() < 2e-5, i
     np.testing.assert_allclose(pooling.weighted_mean(hs[-1], mask).numpy(), z["pooled_weightedmean"], atol=2e-5)
     np.testing.assert_allclose(pooling.mean(hs[-1], mask).numpy(), z["pooled_mean"], atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["neo_tiny", "gptj_tiny", "bloom_tiny"])
+def test_script_pooling_modes_match_executed_reference_block(golden_dir, name):
+    """All five script-path pooling modes (BDR:238-301) of the oracle vs fixtures produced by EXECUTING the reference's
+    own pooling block on the HF hidden states (tests/golden/make_script_pooling.py)."""
+    from oracle import pooling
+
+    fx = np.load(os.path.join(golden_dir, name + ".npz"))
+    ref = np.load(os.path.join(golden_dir, f"script_pooling_{name}.npz"))
+    hs = [torch.from_numpy(h) for h in fx["hidden_states"]]
+    mask = torch.from_numpy(fx["attention_mask"].astype(np.int64))
+    got = {
+        "mean": pooling.mean(hs[-1], mask),
+        "weightedmean": pooling.weighted_mean(hs[-1], mask),
+        "lasttoken": pooling.last_token(hs[-1], mask),
+        "meanmean": pooling.mean_mean(hs, mask),
+        "lasttokenmean": pooling.last_token_mean(hs, mask),
+    }
+    for mode, val in got.items():
+        np.testing.assert_allclose(val.numpy(), ref["pooled_" + mode], rtol=1e-5, atol=1e-6, err_msg=mode)
