@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   const uint32_t tO = kSingle ? tmem_base : tmem_base + 128;
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
 
+  // barrier init and TMEM allocation above overlapped the previous kernel's tail (cu_seqlens is written by a copy, never
+  // by a kernel, so reading it earlier is safe); qkv is touched only from here on
+  pdl_sync();
   if (tid == 0) {
     mbar_expect_tx(bar_q, Cfg::kQBytes);
     for (int s = 0; s < Cfg::kSub; ++s) tma_load_2d(sQ + s * kSubBytes, &tma_qkv, bar_q, h * HD + 64 * s, seq0 + qp0);
@@ -355,6 +358,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const __nv_bfloat16
                                                              __nv_bfloat16* __restrict__ out,
                                                              const int32_t* __restrict__ cu, int B, int T, int H,
                                                              float scale, int window, const float* __restrict__ alibi) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   constexpr int E = HD / 32;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int h = blockIdx.y;
@@ -410,8 +414,8 @@ static int launch_attention_tc_impl(const CUtensorMap& map, void* out, const int
   dim3 grid((max_seqlen + kAttnTile - 1) / kAttnTile, B, H);
   const float sl2 = scale * 1.4426950408889634f;
   LaunchScope _ls(kCatAttention, stream);
-  kern<<<grid, 128, Cfg::kSmemBytes, stream>>>(map, static_cast<__nv_bfloat16*>(out), cu, H, sl2, window, alibi);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(launch_kernel(kern, grid, dim3(128), Cfg::kSmemBytes, stream, map, static_cast<__nv_bfloat16*>(out), cu,
+                                H, sl2, window, alibi));
   return SGPT_OK;
 }
 
@@ -431,9 +435,9 @@ static int launch_attention_simt(const void* qkv, void* out, const int32_t* cu, 
                                  int window, const float* alibi, cudaStream_t stream) {
   dim3 grid((T + 7) / 8, H);
   LaunchScope _ls(kCatAttention, stream);
-  attention_simt_kernel<HD><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                      static_cast<__nv_bfloat16*>(out), cu, B, T, H, scale, window, alibi);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(launch_kernel(attention_simt_kernel<HD>, grid, dim3(256), 0, stream,
+                                static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), cu, B, T, H,
+                                scale, window, alibi));
   return SGPT_OK;
 }
 

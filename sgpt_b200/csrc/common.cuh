@@ -48,6 +48,22 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (host_utils.h: launch_kernel): its CTAs may become resident while the
+// previous kernel of the stream is still draining.  pdl_wait() blocks until every prerequisite grid has completed and
+// its memory is visible — it must precede the FIRST global-memory access of the kernel; what sits before it (barrier
+// init, TMEM allocation, descriptor prefetch, index arithmetic) overlaps the predecessor's tail.
+// pdl_launch_dependents() lets the NEXT kernel of the stream start the same way once all CTAs of this grid have
+// executed it (or exited).  Both are no-ops when the launch carried no such attribute.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
                                                     const uint4* __restrict__ wte, const uint4* __restrict__ wpe,
                                                     float4* __restrict__ resid, int T, int d8, int vocab,
                                                     int max_pos) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   // d8 = d / 8: number of 16-B bf16 vectors per row.  Grid-stride over (token, vector).
   const long long total = static_cast<long long>(T) * d8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -115,6 +116,7 @@ template <int TPR, int V>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ g,
                                                         const float4* __restrict__ b, uint2* __restrict__ y, int T,
                                                         int d4, float eps) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   layernorm_body<TPR, V>(x, g, b, y, T, d4, eps);
 }
 
@@ -123,6 +125,7 @@ template <int TPR, int V>
 __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float4* x, const float4* __restrict__ g,
                                                             const float4* __restrict__ b, float4* y, int T, int d4,
                                                             float eps) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   layernorm_body<TPR, V>(x, g, b, y, T, d4, eps);
 }
 
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float4* x, con
 template <int TPR, int V>
 __global__ void __launch_bounds__(256) row_stats_kernel(const float4* __restrict__ x, float2* __restrict__ stats,
                                                         int T, int d4, float eps) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   constexpr int ROWS = 256 / TPR;
   __shared__ float scratch[ROWS * (TPR / 32) + 1];
   const int row_in_cta = threadIdx.x / TPR;
@@ -164,12 +168,12 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float4* __restrict
   do {                                                                                              \
     if (d4 <= 32 * 8) {                                                                             \
       const int rows = 8;                                                                           \
-      KERNEL<32, 8><<<(T + rows - 1) / rows, 256, 0, stream>>>(__VA_ARGS__);                        \
+      SGPT_CHECK_CUDA(launch_kernel(KERNEL<32, 8>, dim3((T + rows - 1) / rows), dim3(256), 0, stream, __VA_ARGS__)); \
     } else if (d4 <= 128 * 8) {                                                                     \
       const int rows = 2;                                                                           \
-      KERNEL<128, 8><<<(T + rows - 1) / rows, 256, 0, stream>>>(__VA_ARGS__);                       \
+      SGPT_CHECK_CUDA(launch_kernel(KERNEL<128, 8>, dim3((T + rows - 1) / rows), dim3(256), 0, stream, __VA_ARGS__)); \
     } else if (d4 <= 256 * 16) {                                                                    \
-      KERNEL<256, 16><<<T, 256, 0, stream>>>(__VA_ARGS__);                                          \
+      SGPT_CHECK_CUDA(launch_kernel(KERNEL<256, 16>, dim3(T), dim3(256), 0, stream, __VA_ARGS__));  \
     } else {                                                                                        \
       set_error("hidden size %d too large for the row kernels", d4 * 4);                            \
       return SGPT_ERR_UNSUPPORTED;                                                                  \
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x,
                                                    const float4* __restrict__ g, const float4* __restrict__ bta,
                                                    float4* __restrict__ out, float* __restrict__ sumsq, int d4,
                                                    int mode, int clamp_den, int accumulate, float out_scale) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   __shared__ float4 part[4][32];
   __shared__ float wpart[4];
   const int b = blockIdx.x;
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x,
 // P2: x[b,:] /= max(sqrt(sumsq[b]), 1e-12)      (F.normalize(p=2, dim=1))
 __global__ void __launch_bounds__(256) l2_scale_rows_kernel(float4* __restrict__ x, const float* __restrict__ sumsq,
                                                             int B, int d4) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   const long long total = static_cast<long long>(B) * d4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -268,6 +274,7 @@ __global__ void __launch_bounds__(256) l2_scale_rows_kernel(float4* __restrict__
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y,
                                                           long long n4) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = x[i];
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restri
 // one warp per row; D % 8 == 0
 __global__ void __launch_bounds__(256) row_inv_norm_kernel(const uint4* __restrict__ x, float* __restrict__ inv,
                                                            long long n, int d8) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (row >= n) return;
   const int lane = threadIdx.x & 31;
@@ -312,10 +320,9 @@ extern "C" int sgpt_embed_tokens(const int32_t* ids, const int32_t* pos, const v
   if (T == 0) return SGPT_OK;
   const int d8 = d / 8;
   LaunchScope _ls(kCatEmbed, stream);
-  embed_kernel<<<grid_for(static_cast<long long>(T) * d8, 256), 256, 0, stream>>>(
-      ids, pos, static_cast<const uint4*>(wte), static_cast<const uint4*>(wpe), reinterpret_cast<float4*>(resid), T,
-      d8, vocab, max_pos);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(launch_kernel(embed_kernel, dim3(grid_for(static_cast<long long>(T) * d8, 256)), dim3(256), 0, stream,
+                                ids, pos, static_cast<const uint4*>(wte), static_cast<const uint4*>(wpe),
+                                reinterpret_cast<float4*>(resid), T, d8, vocab, max_pos));
   return SGPT_OK;
 }
 
@@ -376,15 +383,13 @@ extern "C" int sgpt_pool_accumulate(const float* x, const int32_t* pos, const in
     SGPT_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * B, stream));
   }
   dim3 grid(B, (d4 + 31) / 32);
-  pool_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float4*>(x), pos, cu_seqlens, stats,
-                                        reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
-                                        reinterpret_cast<float4*>(out), sumsq, d4, mode, clamp_denominator, accumulate,
-                                        out_scale);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(launch_kernel(pool_kernel, grid, dim3(128), 0, stream, reinterpret_cast<const float4*>(x), pos,
+                                cu_seqlens, stats, reinterpret_cast<const float4*>(gamma),
+                                reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(out), sumsq, d4, mode,
+                                clamp_denominator, accumulate, out_scale));
   if (normalize) {
-    l2_scale_rows_kernel<<<grid_for(static_cast<long long>(B) * d4, 256), 256, 0, stream>>>(
-        reinterpret_cast<float4*>(out), sumsq, B, d4);
-    SGPT_CHECK_CUDA(cudaGetLastError());
+    SGPT_CHECK_CUDA(launch_kernel(l2_scale_rows_kernel, dim3(grid_for(static_cast<long long>(B) * d4, 256)), dim3(256),
+                                  0, stream, reinterpret_cast<float4*>(out), sumsq, B, d4));
   }
   return SGPT_OK;
 }
@@ -403,9 +408,8 @@ extern "C" int sgpt_row_inv_norms(const void* x, float* inv_norm, int64_t n, int
   const long long blocks = (n + 7) / 8;
   SGPT_REQUIRE(blocks < (1ll << 31), "sgpt_row_inv_norms: too many rows");
   LaunchScope _ls(kCatMisc, stream);
-  row_inv_norm_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint4*>(x), inv_norm, n,
-                                                                          D / 8);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(launch_kernel(row_inv_norm_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream,
+                                static_cast<const uint4*>(x), inv_norm, n, D / 8));
   return SGPT_OK;
 }
 
@@ -414,8 +418,7 @@ extern "C" int sgpt_f32_to_bf16(const float* x, void* y, int64_t count, sgpt_str
   SGPT_REQUIRE(count >= 0 && count % 4 == 0, "sgpt_f32_to_bf16: count must be a multiple of 4");
   if (count == 0) return SGPT_OK;
   LaunchScope _ls(kCatMisc, stream);
-  f32_to_bf16_kernel<<<grid_for(count / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
-                                                                    static_cast<uint2*>(y), count / 4);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(launch_kernel(f32_to_bf16_kernel, dim3(grid_for(count / 4, 256)), dim3(256), 0, stream,
+                                reinterpret_cast<const float4*>(x), static_cast<uint2*>(y), count / 4));
   return SGPT_OK;
 }

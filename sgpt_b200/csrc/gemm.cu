@@ -38,13 +38,22 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   cfg.blockDim = dim3(128 + 32 * Epi::kEpiWarps);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CL > 1) ? 1 : 0;
+  cfg.numAttrs = na;
   LaunchScope _ls(cat, stream);
   SGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep, tmap));
   return SGPT_OK;

@@ -145,6 +145,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   const bool clock_probe = (blockIdx.x == 0 && threadIdx.x == 0);
   const long long probe_c0 = clock_probe ? clock64() : 0;
   const uint64_t probe_t0 = clock_probe ? global_timer_ns() : 0;

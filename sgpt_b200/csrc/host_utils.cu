@@ -1,5 +1,7 @@
 #include "host_utils.h"
 
+#include <stdlib.h>
+
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -68,6 +70,14 @@ static int make_tma_2d(CUtensorMap* map, CUtensorMapDataType dt, uint64_t esz, c
     return SGPT_ERR_CUDA;
   }
   return SGPT_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SGPT_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int sm_count() {

@@ -38,6 +38,26 @@ int make_tma_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 int sm_count();
 
+// Programmatic dependent launch is on unless SGPT_PDL=0 is set in the environment (A/B measurements).
+bool pdl_enabled();
+
+// Launch with the programmatic-stream-serialization attribute (common.cuh: pdl_wait / pdl_launch_dependents).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace sgpt
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
+  pdl_sync();  // programmatic dependent launch: see common.cuh
   // flat index space over the lists: s_len[g], s_off[g] = sum of the padded lengths of lists < g (block-wide scan)
   if (src.G <= kMaxFlatLists) {
     const uint32_t mylen = (tid < src.G) ? static_cast<uint32_t>(list_len(src, q, tid)) : 0u;
@@ -341,9 +342,9 @@ int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int
     attr_set = true;
   }
   LaunchScope _ls(kCatTopk, stream);
-  topk_select_kernel<<<nq, kTopkThreads, dsm, stream>>>(src, k, KP, static_cast<uint32_t>(cache_keys), out_scores,
-                                                        reinterpret_cast<long long*>(out_ids), extra);
-  SGPT_CHECK_CUDA(cudaGetLastError());
+  SGPT_CHECK_CUDA(launch_kernel(topk_select_kernel, dim3(nq), dim3(kTopkThreads), dsm, stream, src, k, KP,
+                                static_cast<uint32_t>(cache_keys), out_scores, reinterpret_cast<long long*>(out_ids),
+                                extra));
   return SGPT_OK;
 }
 
