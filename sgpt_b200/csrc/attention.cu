@@ -25,6 +25,149 @@ namespace sgpt {
 constexpr int kAttnTile = 128;
 constexpr int kSubBytes = kAttnTile * 128;  // one [128 rows x 64 bf16] sub-tile
 
+// Visibility of the 128 query rows of a tile.  vis_*: this THREAD's row (causal / window / ragged length bounds on the
+// key position); w_*: bounds over the 32 rows of its WARP — a 32-key chunk entirely inside [w_lo_max, w_hi_min] needs no
+// per-element mask, a chunk entirely outside [w_lo_min, w_hi_max] contributes nothing (causal: half of the diagonal tile
+// on average).
+struct RowVis {
+  int vis_hi, vis_lo, w_hi_min, w_hi_max, w_lo_max, w_lo_min;
+};
+__device__ __forceinline__ RowVis make_row_vis(int qp0, int tid, int len, int window) {
+  RowVis r;
+  const int qpos = qp0 + tid;
+  r.vis_hi = min(qpos, len - 1);
+  r.vis_lo = (window > 0) ? (qpos - window + 1) : 0;
+  const int wq0 = qp0 + (tid >> 5) * 32;
+  r.w_hi_min = min(wq0, len - 1);
+  r.w_hi_max = min(wq0 + 31, len - 1);
+  r.w_lo_max = (window > 0) ? (wq0 + 31 - window + 1) : 0;
+  r.w_lo_min = (window > 0) ? (wq0 - window + 1) : 0;
+  return r;
+}
+
+// Softmax pass 1 over one 128-key tile whose scores sit in TMEM (thread = query row): the row maximum in the exp2
+// domain, i.e. of s * sl2 (+ slope2 * key_pos with ALiBi), -inf when no key of the tile is visible.
+__device__ __forceinline__ float softmax_tile_max(uint32_t tS_row, int kv0, const RowVis& rv, float sl2, float slope2) {
+  const int vis_hi = rv.vis_hi, vis_lo = rv.vis_lo, w_hi_min = rv.w_hi_min, w_hi_max = rv.w_hi_max,
+            w_lo_max = rv.w_lo_max, w_lo_min = rv.w_lo_min;
+  float mx = -INFINITY, mxa = -INFINITY;  // raw-score maximum (no ALiBi) / scaled+biased maximum (ALiBi)
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
+    if (c_lo > w_hi_max || c_hi < w_lo_min) continue;  // nothing visible for any row of this warp (warp-uniform)
+    uint32_t v[32];
+    tmem_ld_32x32(tS_row + c * 32, v);
+    tmem_ld_wait();
+    const bool unmasked = (c_hi <= w_hi_min && c_lo >= w_lo_max);  // warp-uniform
+    if (slope2 == 0.f) {
+      // no ALiBi: the maximum is taken over the raw scores, the (positive) scale is applied once after the reduction
+      if (unmasked) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kp = c_lo + i;
+          if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+    } else {
+      // ALiBi: maximum of the scaled, biased scores s * sl2 + slope2 * key_pos (two FMAs per element)
+      const float ab = slope2 * static_cast<float>(c_lo);
+      if (unmasked) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          mxa = fmaxf(mxa, fmaf(__uint_as_float(v[i]), sl2, fmaf(slope2, static_cast<float>(i), ab)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kp = c_lo + i;
+          const float t = fmaf(__uint_as_float(v[i]), sl2, fmaf(slope2, static_cast<float>(i), ab));
+          if (kp <= vis_hi && kp >= vis_lo) mxa = fmaxf(mxa, t);
+        }
+      }
+    }
+  }
+  return (slope2 == 0.f) ? mx * sl2 : mxa;  // sl2 > 0
+}
+
+// Softmax pass 2: p = exp2(s * sl2 (+ ALiBi) - m_use) for the same tile, P -> bf16 -> the thread's row of the swizzled
+// [128 x 128] smem operand (two 64-key sub-tiles); returns the row sum of p.
+__device__ __forceinline__ float softmax_tile_exp(uint32_t tS_row, int kv0, const RowVis& rv, float sl2, float slope2,
+                                                  float m_use, uint32_t sP_addr, int tid) {
+  const int vis_hi = rv.vis_hi, vis_lo = rv.vis_lo, w_hi_min = rv.w_hi_min, w_hi_max = rv.w_hi_max,
+            w_lo_max = rv.w_lo_max, w_lo_min = rv.w_lo_min;
+  float lsum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
+    uint32_t pk[16];
+    if (c_lo > w_hi_max || c_hi < w_lo_min) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    } else {
+      uint32_t v[32];
+      tmem_ld_32x32(tS_row + c * 32, v);
+      tmem_ld_wait();
+      const bool unmasked = (c_hi <= w_hi_min && c_lo >= w_lo_max);  // warp-uniform
+      if (slope2 == 0.f) {
+        if (unmasked) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
+            const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int kp = c_lo + 2 * i;
+            float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
+            float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
+            if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
+            if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        }
+      } else {
+        const float ab = fmaf(slope2, static_cast<float>(c_lo), -m_use);  // slope2 * key_pos - m, position part
+        if (unmasked) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, fmaf(slope2, static_cast<float>(2 * i), ab)));
+            const float p1 =
+                exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, fmaf(slope2, static_cast<float>(2 * i + 1), ab)));
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int kp = c_lo + 2 * i;
+            float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, fmaf(slope2, static_cast<float>(2 * i), ab)));
+            float p1 =
+                exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, fmaf(slope2, static_cast<float>(2 * i + 1), ab)));
+            if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
+            if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        }
+      }
+    }
+    // P[row, kv 32c .. 32c+31] -> sub-tile (c >> 1), 16-B chunks 4*(c&1) .. +3, XOR-swizzled with (row & 7)
+    const uint32_t prow = sP_addr + (c >> 1) * kSubBytes + tid * 128;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int chunk = ((c & 1) * 4 + q4) ^ (tid & 7);
+      sts_v4(prow + chunk * 16, pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+    }
+  }
+  return lsum;
+}
+
 // kSingle: every sequence of the batch fits one 128-key tile (max_seqlen <= 128 — all of the reference's NLI models
 // and BASELINE configs 1-2).  Then Q and K are dead once S = Q K^T has been read, so P reuses their smem, and O
 // reuses S's TMEM columns: 48 KB smem / 128 TMEM columns per CTA at hd = 64, i.e. FOUR co-resident CTAs per SM whose
@@ -116,14 +259,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   // by log2(e) because the softmax runs in the exp2 domain
   const float slope2 = (alibi != nullptr) ? __ldg(alibi + h) * 1.4426950408889634f : 0.f;
   const int qpos = qp0 + tid;
-  const int vis_hi = min(qpos, len - 1);
-  const int vis_lo = (window > 0) ? (qpos - window + 1) : 0;
-  // visibility bounds of this WARP's 32 query rows: a 32-key chunk entirely inside [w_lo_max, w_hi_min] needs no
-  // per-element mask, a chunk entirely outside [w_lo_min, w_hi_max] contributes nothing (causal: half of the diagonal
-  // tile on average)
-  const int wq0 = qp0 + warp * 32;
-  const int w_hi_min = min(wq0, len - 1), w_hi_max = min(wq0 + 31, len - 1);
-  const int w_lo_max = (window > 0) ? (wq0 + 31 - window + 1) : 0, w_lo_min = (window > 0) ? (wq0 - window + 1) : 0;
+  const RowVis rv = make_row_vis(qp0, tid, len, window);
   float m_run = -INFINITY, l_run = 0.f;
 
   for (int j = j_lo; j <= j_hi; ++j) {
@@ -155,48 +291,9 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
 
     // ---- online softmax over this row's 128 scores (pass 1: row maximum) ----
     const int kv0 = j * kAttnTile;
-    float mx = -INFINITY, mxa = -INFINITY;  // raw-score maximum (no ALiBi) / scaled+biased maximum (ALiBi)
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
-      if (c_lo > w_hi_max || c_hi < w_lo_min) continue;  // nothing visible for any row of this warp (warp-uniform)
-      uint32_t v[32];
-      tmem_ld_32x32(tS + lane_off + c * 32, v);
-      tmem_ld_wait();
-      const bool unmasked = (c_hi <= w_hi_min && c_lo >= w_lo_max);  // warp-uniform
-      if (slope2 == 0.f) {
-        // no ALiBi: the maximum is taken over the raw scores, the (positive) scale is applied once after the reduction
-        if (unmasked) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kp = c_lo + i;
-            if (kp <= vis_hi && kp >= vis_lo) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
-        }
-      } else {
-        // ALiBi: maximum of the scaled, biased scores s * sl2 + slope2 * key_pos (two FMAs per element)
-        const float ab = slope2 * static_cast<float>(c_lo);
-        if (unmasked) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            mxa = fmaxf(mxa, fmaf(__uint_as_float(v[i]), sl2, fmaf(slope2, static_cast<float>(i), ab)));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kp = c_lo + i;
-            const float t = fmaf(__uint_as_float(v[i]), sl2, fmaf(slope2, static_cast<float>(i), ab));
-            if (kp <= vis_hi && kp >= vis_lo) mxa = fmaxf(mxa, t);
-          }
-        }
-      }
-    }
-    const float m_new = fmaxf(m_run, (slope2 == 0.f) ? mx * sl2 : mxa);  // sl2 > 0
+    const float m_new = fmaxf(m_run, softmax_tile_max(tS + lane_off, kv0, rv, sl2, slope2));
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
     const float alpha = exp2f(m_run - m_use);
-    float lsum = 0.f;
     // The P buffer (and O) still belong to the previous tile's P V MMA until it has completed.
     if (j > j_lo) {
       mbar_wait(bar_o, ph ^ 1u);
@@ -204,73 +301,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
       __syncwarp();
     }
     // ---- pass 2: p = exp2(s * sl2 (+ alibi) - m), P -> bf16 -> swizzled smem ----
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
-      uint32_t pk[16];
-      if (c_lo > w_hi_max || c_hi < w_lo_min) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      } else {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_off + c * 32, v);
-        tmem_ld_wait();
-        const bool unmasked = (c_hi <= w_hi_min && c_lo >= w_lo_max);  // warp-uniform
-        if (slope2 == 0.f) {
-          if (unmasked) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
-              const float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
-              lsum += p0 + p1;
-              pk[i] = pack_bf16(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int kp = c_lo + 2 * i;
-              float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_use));
-              float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_use));
-              if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
-              if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
-              lsum += p0 + p1;
-              pk[i] = pack_bf16(p0, p1);
-            }
-          }
-        } else {
-          const float ab = fmaf(slope2, static_cast<float>(c_lo), -m_use);  // slope2 * key_pos - m, position part
-          if (unmasked) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, fmaf(slope2, static_cast<float>(2 * i), ab)));
-              const float p1 =
-                  exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, fmaf(slope2, static_cast<float>(2 * i + 1), ab)));
-              lsum += p0 + p1;
-              pk[i] = pack_bf16(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int kp = c_lo + 2 * i;
-              float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, fmaf(slope2, static_cast<float>(2 * i), ab)));
-              float p1 =
-                  exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, fmaf(slope2, static_cast<float>(2 * i + 1), ab)));
-              if (!(kp <= vis_hi && kp >= vis_lo)) p0 = 0.f;
-              if (!(kp + 1 <= vis_hi && kp + 1 >= vis_lo)) p1 = 0.f;
-              lsum += p0 + p1;
-              pk[i] = pack_bf16(p0, p1);
-            }
-          }
-        }
-      }
-      // P[row, kv 32c .. 32c+31] -> sub-tile (c >> 1), 16-B chunks 4*(c&1) .. +3, XOR-swizzled with (row & 7)
-      const uint32_t prow = smem_u32(sP) + (c >> 1) * kSubBytes + tid * 128;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const int chunk = ((c & 1) * 4 + q4) ^ (tid & 7);
-        sts_v4(prow + chunk * 16, pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-      }
-    }
+    const float lsum = softmax_tile_exp(tS + lane_off, kv0, rv, sl2, slope2, m_use, smem_u32(sP), tid);
     l_run = l_run * alpha + lsum;
     m_run = m_new;
 

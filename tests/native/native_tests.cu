@@ -554,6 +554,28 @@ int main(int argc, char** argv) {
                              {32768, 2048, 768}, {32768, 2048, 1024}};
     for (auto& sh : shapes) test_linear(sh[0], sh[1], sh[2], SGPT_EPI_BF16, 2);
   }
+  if (!strcmp(only, "attnperf")) {  // the bench shape: 256 sequences x 128 tokens, 12 heads x 64 (timing only)
+    const int B = 256, S = 128, H = 12, hd = 64, T = B * S, d = H * hd;
+    auto qkv = randn((size_t)T * 3 * d, 0.3f);
+    auto qb = to_bf16(qkv);
+    auto* dq = to_dev(qb);
+    auto* dout = dalloc<__nv_bfloat16>((size_t)T * d);
+    std::vector<int> cu(B + 1);
+    for (int b = 0; b <= B; ++b) cu[b] = b * S;
+    int* dcu = to_dev(cu);
+    for (int impl : {0, 0}) {
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      SG(sgpt_attention(dq, dout, dcu, B, T, H, hd, 1.0f, 0, S, nullptr, impl, 0));
+      CK(cudaEventRecord(e0));
+      for (int it = 0; it < 20; ++it) SG(sgpt_attention(dq, dout, dcu, B, T, H, hd, 1.0f, 0, S, nullptr, impl, 0));
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      const double ms = time_ms(e0, e1) / 20;
+      printf("INFO attention impl=%d: %.1f us, %.0f GB/s of qkv+out\n", impl, ms * 1e3,
+             (double)T * d * 2 * 4 / (ms * 1e6));
+    }
+  }
   if (want("attention")) {
     test_attention({128}, 1, 64, 1.0f, 0, 0.3f);
     test_attention({1, 37, 128, 5, 64, 100}, 3, 64, 1.0f, 0, 0.3f);

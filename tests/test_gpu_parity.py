@@ -202,7 +202,10 @@ def _assert_same_topk(scores_dev, ids_dev, full, k, id_base=0):
 
 
 @pytest.mark.parametrize("nq,n,D,k,fn", [(128, 20000, 768, 1001, "cos_sim"), (16, 5003, 2048, 1001, "dot"),
-                                         (1, 3000, 768, 1001, "cos_sim"), (7, 600, 64, 1001, "cos_sim")])
+                                         (1, 3000, 768, 1001, "cos_sim"), (7, 600, 64, 1001, "cos_sim"),
+                                         # >= 8 x 148 corpus tiles: the two-pass threshold-filter path; 130 queries =
+                                         # two query blocks; ragged last tile (n % 256 != 0)
+                                         (130, 320001, 64, 1001, "cos_sim"), (5, 310000, 128, 10, "dot")])
 def test_search_identical_topk_ids(nq, n, D, k, fn):
     from sgpt_b200 import CorpusShard
 
@@ -406,3 +409,72 @@ def test_semantic_search_matches_reference_util_and_shard_roundtrip(golden_dir, 
     assert again.n == shard.n and again.id_base == 1000
     s1, i1 = again.search(pad(q).cuda(), 25, "dot")
     assert torch.equal(s0, s1) and torch.equal(i0, i1)
+
+
+def test_search_two_pass_with_massive_ties():
+    """Two-pass filter path on a corpus with only 40 distinct vectors (every score value is shared by ~7750 documents):
+    the admission threshold sits inside a tie group, which must not lose candidates."""
+    from sgpt_b200 import CorpusShard
+
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(40, 64, generator=g)
+    n = 310000
+    c = base[torch.randint(0, 40, (n,), generator=g)]
+    q = torch.randn(9, 64, generator=g)
+    shard = CorpusShard.from_embeddings(c.cuda(), device="cuda:0")
+    k = 1001
+    s, i = shard.search(q.cuda(), k, "cos_sim")
+    full = _oracle_topk_on_stored(q, c, k, "cos_sim")
+    _assert_same_topk(s, i, full, k)
+    for r in range(len(q)):
+        assert len(set(i[r].tolist())) == k  # no document twice
+
+
+def test_search_full_size_1m_docs_properties():
+    """BASELINE size (128 queries x 1 M docs x 768, top-1001) through size-independent properties; torch on the GPU is
+    used only as the checker: (a) descending scores, unique ids; (b) returned scores == cos_sim of the stored vectors;
+    (c) exactness: fewer than k documents score above the returned k-th score; (d) planted near-duplicates rank first;
+    (e) searching two half shards and merging == searching the whole shard."""
+    from sgpt_b200 import CorpusShard
+    from sgpt_b200.index import merge_topk
+
+    dev, n, D, nq, k = torch.device("cuda:0"), 1_000_000, 768, 128, 1001
+    g = torch.Generator(device=dev).manual_seed(99)
+    q = torch.randn(nq, D, generator=g, device=dev)
+    whole = CorpusShard(D, n, device=dev)
+    for s0 in range(0, n, 100_000):
+        c = torch.randn(100_000, D, generator=g, device=dev)
+        idx = torch.arange(0, 100_000, 1000, device=dev)
+        c[idx] = q[((s0 + idx) // 1000) % nq] + 0.3 * c[idx]  # doc 1000*j is a near-duplicate of query j % 128
+        whole.add(c)
+    del c
+    s, i = whole.search(q, k, "cos_sim")
+    assert torch.all(s[:, :-1] >= s[:, 1:])
+    assert all(len(set(r)) == k for r in i.tolist())
+    stored = whole.stored()
+    qb = q.to(torch.bfloat16).float()
+    qn = qb / qb.norm(dim=1, keepdim=True)
+    # (b) recompute the returned scores from the stored rows
+    rows = stored[i.reshape(-1)].float().reshape(nq, k, D)
+    want = torch.einsum("qd,qkd->qk", qn, rows / rows.norm(dim=2, keepdim=True))
+    assert (want - s).abs().max().item() < 2e-5
+    # (c) exactness: count documents above the k-th returned score
+    above = torch.zeros(nq, dtype=torch.int64, device=dev)
+    for s0 in range(0, n, 100_000):
+        blk = stored[s0:s0 + 100_000].float()
+        sc = qn @ (blk / blk.norm(dim=1, keepdim=True)).T
+        above += (sc > (s[:, -1:] + 2e-5)).sum(dim=1)
+    assert int(above.max()) < k
+    # (d) the planted near-duplicates of query j are documents 1000*m with m % 128 == j; the best hit must be one of them
+    top1 = i[:, 0]
+    assert torch.all(top1 % 1000 == 0) and torch.all((top1 // 1000) % nq == torch.arange(nq, device=dev))
+    # (e) two half shards + merge
+    half = n // 2
+    a = CorpusShard.from_embeddings(stored[:half], device=dev, id_base=0)
+    b = CorpusShard.from_embeddings(stored[half:], device=dev, id_base=half)
+    sa, ia = a.search(q, k, "cos_sim")
+    sb, ib = b.search(q, k, "cos_sim")
+    sm, im = merge_topk(torch.stack([sa, sb]), torch.stack([ia, ib]))
+    assert (sm - s).abs().max().item() < 1e-6
+    agree = sum(len(set(x) & set(y)) for x, y in zip(im.tolist(), i.tolist())) / (nq * k)
+    assert agree > 0.999  # identical up to ties at the cut
