@@ -112,6 +112,26 @@ int sgpt_pool_accumulate(const float* x, const int32_t* pos, const int32_t* cu_s
                          const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d, int mode,
                          int clamp_denominator, int normalize, int accumulate, float out_scale, sgpt_stream_t stream);
 
+/* General form: pos_weights fp32[n_pos_weights] or NULL.  With a table (mode must be WEIGHTEDMEAN) the weight of token t
+ * is pos_weights[pos[t]] instead of pos[t]+1 — the learnt per-position weights of
+ * ST/models/WeightedMeanPooling.py:21-37 (`position_weights[:positions]`, indexed by the position in the padded row;
+ * that module always clamps the denominator, :34).  pos[t] >= n_pos_weights is the caller's error (the reference
+ * asserts, :30); the kernel clamps the index instead of reading out of bounds. */
+int sgpt_pool_ex(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma, const float* beta,
+                 float eps, const float* pos_weights, int n_pos_weights, float* out, float* row_stats_ws, int B, int T,
+                 int d, int mode, int clamp_denominator, int normalize, int accumulate, float out_scale,
+                 sgpt_stream_t stream);
+
+/* Sentence-embedding head applied after pooling: y = act(x @ w^T + bias), all fp32 (ST/models/Dense.py:40-43 with
+ * key_name "sentence_embedding"; nn.Linear weight layout).  x fp32[B,in], w fp32[out,in], bias fp32[out] or NULL,
+ * y fp32[B,out] (must not alias x). */
+#define SGPT_ACT_IDENTITY 0
+#define SGPT_ACT_TANH 1
+#define SGPT_ACT_RELU 2
+#define SGPT_ACT_SIGMOID 3
+int sgpt_dense(const float* x, const float* w, const float* bias, float* y, int B, int in_features, int out_features,
+               int activation, sgpt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Whole-encoder handle (F1..F7 + P1 in one call).
  * ------------------------------------------------------------------------------------------------------------------ */
@@ -169,6 +189,11 @@ void sgpt_model_destroy(sgpt_model_t m);
 int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const int32_t* cu_seqlens, int B, int T,
                 int max_seqlen, int layer_idx, int pool_mode, int clamp_denominator, int normalize, float* out,
                 sgpt_stream_t stream);
+
+/* Installs (w != NULL) or removes (w == NULL) a learnt position-weight table for pool_mode WEIGHTEDMEAN in sgpt_encode
+ * (ST/models/WeightedMeanPooling.py).  w is a DEVICE fp32[n] buffer borrowed by the handle; sgpt_encode then fails with
+ * SGPT_ERR_INVALID when max_seqlen > n, like the reference's shape assert (:30). */
+int sgpt_model_set_position_weights(sgpt_model_t m, const float* w, int n);
 
 /* Debug/parity tap: copies the fp32 residual stream (hidden_states[layer] before ln_f) left by the LAST sgpt_encode
  * into dst (device, capacity_elems floats) and reports its shape. */

@@ -13,14 +13,24 @@ using it without the library raises.
 from .config import ModelConfig, preset  # noqa: F401
 
 __all__ = ["ModelConfig", "preset", "Encoder", "CustomEmbedder", "SentenceEncoder", "SentenceBERTBOSEOS",
-           "DenseRetrievalExactSearch", "CorpusShard", "merge_topk", "semantic_search", "sharded_search"]
+           "SentenceBERTAsym", "DenseRetrievalExactSearch", "CorpusShard", "merge_topk", "semantic_search",
+           "sharded_search", "DenseHead", "AsymHeads", "load_st_directory", "GenericDataLoader", "EvaluateRetrieval"]
 
 
 def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
     if name == "Encoder":
         from .encoder import Encoder
         return Encoder
-    if name in ("CustomEmbedder", "SentenceEncoder", "SentenceBERTBOSEOS"):
+    if name in ("DenseHead", "AsymHeads"):
+        from . import heads
+        return getattr(heads, name)
+    if name == "load_st_directory":
+        from .st_loader import load_st_directory
+        return load_st_directory
+    if name in ("GenericDataLoader", "EvaluateRetrieval"):
+        from . import beir_compat
+        return getattr(beir_compat, name)
+    if name in ("CustomEmbedder", "SentenceEncoder", "SentenceBERTBOSEOS", "SentenceBERTAsym"):
         from . import embedder
         return getattr(embedder, name)
     if name == "DenseRetrievalExactSearch":

@@ -15,6 +15,7 @@ SGPT_OK = 0
 EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32 = 0, 1, 2
 POOL_MEAN, POOL_WEIGHTEDMEAN, POOL_LASTTOKEN, POOL_MEANMEAN, POOL_LASTTOKENMEAN = 0, 1, 2, 3, 4
 ARCH_GPT_NEO, ARCH_GPTJ, ARCH_BLOOM = 0, 1, 2
+ACT_IDENTITY, ACT_TANH, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -47,6 +48,9 @@ _SIGNATURES = {
     "sgpt_attention": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp, i32, vp]),
     "sgpt_pool": (i32, [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sgpt_pool_accumulate": (i32, [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "sgpt_pool_ex": (i32, [vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "sgpt_dense": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "sgpt_model_set_position_weights": (i32, [vp, vp, i32]),
     "sgpt_model_create": (i32, [C.POINTER(ModelConfigC), C.POINTER(ModelWeightsC), C.POINTER(vp)]),
     "sgpt_model_destroy": (None, [vp]),
     "sgpt_encode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),

@@ -185,8 +185,10 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float4* __restrict
 //   grid = (B, d / 128); 128 threads = 4 warps; each warp strides over the tokens of the sequence, each lane owns one
 //   float4 column group (coalesced 512-B row segments); fp32 accumulators; cross-warp combine through smem.
 //   With ln_f:  sum_t w_t ((x_t - mu_t) r_t g + b) = g * sum_t w_t r_t (x_t - mu_t) + b * W.
+//   w_t = pos_t + 1 (weightedmean), pw[pos_t] (learnt WeightedMeanPooling), 1 (mean) or [t is last] (lasttoken).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x, const int32_t* __restrict__ pos,
+                                                   const float* __restrict__ pw, int n_pw,
                                                    const int32_t* __restrict__ cu, const float2* __restrict__ stats,
                                                    const float4* __restrict__ g, const float4* __restrict__ bta,
                                                    float4* __restrict__ out, float* __restrict__ sumsq, int d4,
@@ -203,7 +205,11 @@ __global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x,
   const bool col_ok = col < d4;
   for (int t = t0 + warp; t < t1; t += 4) {
     float w;
-    if (mode == SGPT_POOL_WEIGHTEDMEAN) w = static_cast<float>(__ldg(pos + t) + 1);
+    if (mode == SGPT_POOL_WEIGHTEDMEAN) {
+      // fixed weights i+1 (BDR:259-265), or the learnt table of ST/models/WeightedMeanPooling.py:29 indexed by position
+      const int p = __ldg(pos + t);
+      w = pw != nullptr ? __ldg(pw + min(p, n_pw - 1)) : static_cast<float>(p + 1);
+    }
     else if (mode == SGPT_POOL_LASTTOKEN) w = (t == t1 - 1) ? 1.f : 0.f;
     else w = 1.f;
     wsum += w;
@@ -300,6 +306,55 @@ __global__ void __launch_bounds__(256) row_inv_norm_kernel(const uint4* __restri
   if (lane == 0) inv[row] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sentence-embedding head: y[b,o] = act(sum_k x[b,k] * w[o,k] + bias[o]) in fp32 (ST/models/Dense.py:40-43 applied to
+// the pooled embedding).  B x in x out is tiny (<= a few hundred MFLOP), so this is a plain smem-tiled SIMT kernel kept
+// in fp32 end to end: 32 x 32 output tile per CTA, 256 threads x (2 x 2) outputs, K in steps of 32, fixed summation
+// order (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, float* __restrict__ y, int B,
+                                                    int K, int N, int act) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
+  __shared__ float xs[32][33];
+  __shared__ float ws[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int o0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + i * 256;  // 0..1023
+      const int r = e >> 5, c = e & 31;
+      const int k = k0 + c;
+      xs[r][c] = (b0 + r < B && k < K) ? x[static_cast<size_t>(b0 + r) * K + k] : 0.f;
+      ws[r][c] = (o0 + r < N && k < K) ? __ldg(w + static_cast<size_t>(o0 + r) * K + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float x0 = xs[ty][c], x1 = xs[ty + 16][c];
+      const float w0 = ws[tx][c], w1 = ws[tx + 16][c];
+      acc[0][0] = fmaf(x0, w0, acc[0][0]); acc[0][1] = fmaf(x0, w1, acc[0][1]);
+      acc[1][0] = fmaf(x1, w0, acc[1][0]); acc[1][1] = fmaf(x1, w1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = b0 + ty + 16 * i, o = o0 + tx + 16 * j;
+      if (b < B && o < N) {
+        float v = acc[i][j] + (bias != nullptr ? __ldg(bias + o) : 0.f);
+        if (act == SGPT_ACT_TANH) v = tanhf(v);
+        else if (act == SGPT_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == SGPT_ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+        y[static_cast<size_t>(b) * N + o] = v;
+      }
+    }
+}
+
 static inline int grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(sm_count()) * 16;
@@ -354,15 +409,17 @@ extern "C" int sgpt_layernorm_f32_inplace(float* x, const float* gamma, const fl
   return SGPT_OK;
 }
 
-extern "C" int sgpt_pool_accumulate(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
-                                    const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d,
-                                    int mode, int clamp_denominator, int normalize, int accumulate, float out_scale,
-                                    sgpt_stream_t stream_) {
+extern "C" int sgpt_pool_ex(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                            const float* beta, float eps, const float* pos_weights, int n_pos_weights, float* out,
+                            float* row_stats_ws, int B, int T, int d, int mode, int clamp_denominator, int normalize,
+                            int accumulate, float out_scale, sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(d > 0 && d % 4 == 0, "sgpt_pool: d=%d must be a positive multiple of 4", d);
   SGPT_REQUIRE(mode >= SGPT_POOL_MEAN && mode <= SGPT_POOL_LASTTOKEN,
                "sgpt_pool: mode %d is not a single-hidden-state pooling mode", mode);
   SGPT_REQUIRE(mode != SGPT_POOL_WEIGHTEDMEAN || pos != nullptr, "sgpt_pool: weightedmean needs pos");
+  SGPT_REQUIRE(pos_weights == nullptr || (mode == SGPT_POOL_WEIGHTEDMEAN && n_pos_weights > 0),
+               "sgpt_pool: a position-weight table needs mode WEIGHTEDMEAN and n_pos_weights > 0");
   SGPT_REQUIRE((gamma == nullptr) == (beta == nullptr), "sgpt_pool: gamma and beta must be given together");
   SGPT_REQUIRE(gamma == nullptr || row_stats_ws != nullptr, "sgpt_pool: ln_f fusion needs row_stats_ws");
   if (B == 0) return SGPT_OK;
@@ -384,7 +441,7 @@ extern "C" int sgpt_pool_accumulate(const float* x, const int32_t* pos, const in
   }
   dim3 grid(B, (d4 + 31) / 32);
   SGPT_CHECK_CUDA(launch_kernel(pool_kernel, grid, dim3(128), 0, stream, reinterpret_cast<const float4*>(x), pos,
-                                cu_seqlens, stats, reinterpret_cast<const float4*>(gamma),
+                                pos_weights, n_pos_weights, cu_seqlens, stats, reinterpret_cast<const float4*>(gamma),
                                 reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(out), sumsq, d4, mode,
                                 clamp_denominator, accumulate, out_scale));
   if (normalize) {
@@ -394,11 +451,34 @@ extern "C" int sgpt_pool_accumulate(const float* x, const int32_t* pos, const in
   return SGPT_OK;
 }
 
+extern "C" int sgpt_pool_accumulate(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                                    const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d,
+                                    int mode, int clamp_denominator, int normalize, int accumulate, float out_scale,
+                                    sgpt_stream_t stream_) {
+  return sgpt_pool_ex(x, pos, cu_seqlens, gamma, beta, eps, nullptr, 0, out, row_stats_ws, B, T, d, mode,
+                      clamp_denominator, normalize, accumulate, out_scale, stream_);
+}
+
 extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
                          const float* beta, float eps, float* out, float* row_stats_ws, int B, int T, int d, int mode,
                          int clamp_denominator, int normalize, sgpt_stream_t stream_) {
-  return sgpt_pool_accumulate(x, pos, cu_seqlens, gamma, beta, eps, out, row_stats_ws, B, T, d, mode, clamp_denominator,
-                              normalize, /*accumulate=*/0, /*out_scale=*/1.0f, stream_);
+  return sgpt_pool_ex(x, pos, cu_seqlens, gamma, beta, eps, nullptr, 0, out, row_stats_ws, B, T, d, mode,
+                      clamp_denominator, normalize, /*accumulate=*/0, /*out_scale=*/1.0f, stream_);
+}
+
+extern "C" int sgpt_dense(const float* x, const float* w, const float* bias, float* y, int B, int in_features,
+                          int out_features, int activation, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(B >= 0 && in_features > 0 && out_features > 0, "sgpt_dense: bad sizes");
+  SGPT_REQUIRE(activation >= SGPT_ACT_IDENTITY && activation <= SGPT_ACT_SIGMOID, "sgpt_dense: unknown activation %d",
+               activation);
+  SGPT_REQUIRE(x != y, "sgpt_dense: x and y must not alias");
+  if (B == 0) return SGPT_OK;
+  LaunchScope _ls(kCatPool, stream);
+  dim3 grid((out_features + 31) / 32, (B + 31) / 32);
+  SGPT_CHECK_CUDA(launch_kernel(dense_kernel, grid, dim3(256), 0, stream, x, w, bias, y, B, in_features, out_features,
+                                activation));
+  return SGPT_OK;
 }
 
 extern "C" int sgpt_row_inv_norms(const void* x, float* inv_norm, int64_t n, int D, sgpt_stream_t stream_) {

@@ -32,6 +32,8 @@ struct sgpt_model {
   float* stats = nullptr;
   float* rotary = nullptr;  // GPT-J: (cos, sin)[max_pos, rotary_dim/2]
   float* alibi = nullptr;   // BLOOM: slopes[n_head]
+  const float* pool_w = nullptr;  // learnt position weights (borrowed), see sgpt_model_set_position_weights
+  int n_pool_w = 0;
   int last_T = 0;
 };
 
@@ -162,6 +164,9 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
   if (layer_idx < 0) layer_idx += c.n_layer + 1;
   SGPT_REQUIRE(layer_idx >= 0 && layer_idx <= c.n_layer, "sgpt_encode: layer index out of range for %d hidden states",
                c.n_layer + 1);
+  const float* pool_w = (pool_mode == SGPT_POOL_WEIGHTEDMEAN) ? m->pool_w : nullptr;
+  SGPT_REQUIRE(pool_w == nullptr || max_seqlen <= m->n_pool_w,
+               "sgpt_encode: max_seqlen %d exceeds the %d learnt position weights", max_seqlen, m->n_pool_w);
   if (B == 0) return SGPT_OK;
   const int d = c.d_model, H = c.n_head, hd = d / H, ff = c.d_ff;
   const float inv_sqrt_hd = 1.0f / sqrtf(static_cast<float>(hd));
@@ -208,10 +213,17 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
     }
   }
   const bool final_ln = (layer_idx == c.n_layer);
-  SGPT_TRY(sgpt_pool_accumulate(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr,
-                                final_ln ? m->w.lnf_b : nullptr, c.ln_eps, out, m->stats, B, T, d, base_mode,
-                                clamp_denominator, normalize, /*accumulate=*/all_layers && c.n_layer > 0, layer_scale,
-                                stream));
+  SGPT_TRY(sgpt_pool_ex(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr,
+                        c.ln_eps, pool_w, pool_w ? m->n_pool_w : 0, out, m->stats, B, T, d, base_mode, clamp_denominator,
+                        normalize, /*accumulate=*/all_layers && c.n_layer > 0, layer_scale, stream));
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_model_set_position_weights(sgpt_model_t m, const float* w, int n) {
+  SGPT_REQUIRE(m != nullptr, "sgpt_model_set_position_weights: null model");
+  SGPT_REQUIRE(w == nullptr || n > 0, "sgpt_model_set_position_weights: n must be positive");
+  m->pool_w = w;
+  m->n_pool_w = w ? n : 0;
   return SGPT_OK;
 }
 

@@ -13,6 +13,9 @@ deterministic tokenizer in where no pretrained files are reachable.
 from __future__ import annotations
 
 import logging
+import os
+import pathlib
+import pickle
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -27,6 +30,7 @@ SPECB_QUE_BOS, SPECB_QUE_EOS = "[", "]"   # beir_dense_retriever.py:100-101
 SPECB_DOC_BOS, SPECB_DOC_EOS = "{", "}"   # beir_dense_retriever.py:103-104
 
 METHODS = ("mean", "weightedmean", "lasttoken", "meanmean", "lasttokenmean")  # BDR:238-301
+USEB_METHODS = METHODS + ("learntmean",)  # biencoder/useb/useb_dense_retriever.py:218-305
 ST_POOLING = ("mean", "weightedmean", "lasttoken")  # single-hidden-state modes of ST/models/Pooling.py
 
 
@@ -53,8 +57,12 @@ class CustomEmbedder:
         if method not in METHODS:
             raise NotImplementedError(f"pooling method {method!r}: built: {METHODS} (poolout needs a pooler head the "
                                       "GPT models of the reference do not have, BDR:303-304)")
+        self.model_name = model_name
+        self.save_emb = save_emb
+        # BDR:155-156 (the reference creates the directory unconditionally; here only when something will be written)
+        self.base_path = f"embeddings/{model_name.split('/')[-1]}/{method}/{dataset}"
         if save_emb:
-            logger.warning("save_emb pickle cache (BDR:311-323) is not implemented; embeddings are recomputed")
+            pathlib.Path(self.base_path).mkdir(parents=True, exist_ok=True)
         if state_dict is None:
             from transformers import AutoModel  # real checkpoint path
 
@@ -128,40 +136,120 @@ class CustomEmbedder:
         return out
 
     def embed_batcher(self, texts: List[Tuple[str, str]], is_query: bool, out_name=None, **kwargs) -> Dict[str, np.ndarray]:
-        """{id: embedding} like BDR:225-314 (one D2H copy for the whole list instead of per-row .numpy())."""
+        """{id: embedding} like BDR:225-314 (one D2H copy for the whole list instead of per-row .numpy()); with
+        save_emb the dict is pickled to `out_name` (BDR:311-312)."""
         ids, sentences = zip(*texts) if texts else ((), ())
         emb = self.embed_texts(list(sentences), is_query).cpu().numpy()
-        return {i: e for i, e in zip(ids, emb)}
+        all_embeddings = {i: e for i, e in zip(ids, emb)}
+        assert len(texts) == len(all_embeddings)  # BDR:309 (duplicate ids collapse, exactly as upstream)
+        if self.save_emb and out_name:
+            with open(out_name, "wb") as f:
+                pickle.dump(all_embeddings, f)
+        return all_embeddings
+
+    def _cached(self, path: str, ids: Sequence[str]) -> Optional[np.ndarray]:
+        """The pickle-per-chunk embedding cache (BDR:319-323, 336-339): a {id: embedding} dict written by an earlier
+        save_emb run is used whenever the file exists, whatever save_emb says now — like upstream."""
+        if not os.path.exists(path):
+            return None
+        with open(path, "rb") as f:
+            embeddings = pickle.load(f)
+        return np.array([embeddings[i] for i in ids])  # order given, BDR:326 / :344
 
     def encode_queries(self, queries: List[Tuple[str, str]], batch_size: int = None, convert_to_tensor: bool = False,
                        **kwargs) -> Union[np.ndarray, torch.Tensor]:
         """BDR:316-330: rows in the order given.  convert_to_tensor=True keeps the result on the device."""
-        emb = self.embed_texts([t for (_, t) in queries], is_query=True)
+        path = f"{self.base_path}_queries.pickle"
+        cached = self._cached(path, [qid for (qid, _) in queries])
+        if cached is not None:
+            emb = torch.from_numpy(cached).to(self.device) if convert_to_tensor else cached
+        elif self.save_emb:
+            d = self.embed_batcher(queries, is_query=True, out_name=path)
+            emb = np.array([d[qid] for (qid, _) in queries])
+            emb = torch.from_numpy(emb).to(self.device) if convert_to_tensor else emb
+        else:
+            emb = self.embed_texts([t for (_, t) in queries], is_query=True)
+            emb = emb if convert_to_tensor else emb.cpu().numpy()
         logger.info(f"Produced embeddings of shape {tuple(emb.shape)}")
-        return emb if convert_to_tensor else emb.cpu().numpy()
+        return emb
 
     def encode_corpus(self, corpus: List[Tuple[str, Dict[str, str]]], batch_size: int = None, batch_num="",
                       convert_to_tensor: bool = False, **kwargs) -> Union[np.ndarray, torch.Tensor]:
         """BDR:332-348: text = (title + " " + text).strip() when a title key exists (BDR:341)."""
-        texts = [((d["title"] + " " + d["text"]).strip() if "title" in d else d["text"].strip()) for (_, d) in corpus]
-        emb = self.embed_texts(texts, is_query=False)
+        path = f"{self.base_path}_corpus{batch_num}.pickle"
+        cached = self._cached(path, [cid for (cid, _) in corpus])
+        if cached is not None:
+            emb = torch.from_numpy(cached).to(self.device) if convert_to_tensor else cached
+        else:
+            texts = [((d["title"] + " " + d["text"]).strip() if "title" in d else d["text"].strip()) for (_, d) in corpus]
+            if self.save_emb:
+                dd = self.embed_batcher(list(zip([cid for (cid, _) in corpus], texts)), is_query=False, out_name=path)
+                emb = np.array([dd[cid] for (cid, _) in corpus])
+                emb = torch.from_numpy(emb).to(self.device) if convert_to_tensor else emb
+            else:
+                emb = self.embed_texts(texts, is_query=False)
+                emb = emb if convert_to_tensor else emb.cpu().numpy()
         logger.info(f"Produced embeddings of shape {tuple(emb.shape)}")
-        return emb if convert_to_tensor else emb.cpu().numpy()
+        return emb
+
+    # ---- USEB flavour (biencoder/useb/useb_dense_retriever.py:76-309) ---------------------------------------------
+    def encode(self, sentences: Sequence[str], method: str = "mean", show_progress_bar: bool = False,
+               dataset_name=None, add_name: str = "", idx=None, **kwargs) -> List[List[float]]:
+        """``CustomEmbedder.encode`` of the USEB script: plain sentences (no brackets), the pooling ``method`` chosen
+        per call, result as a list of Python float lists (UDR:307).  ``learntmean`` (UDR:252-268) reads the learnt
+        position weights from ``{model_name}/1_WeightedMeanPooling/pytorch_model.bin``.  The per-batch pickle of ALL
+        hidden states (UDR:189-211) is not written: nothing downstream of this call ever needs them again."""
+        if method not in USEB_METHODS:
+            raise NotImplementedError(f"pooling method {method!r}: built: {USEB_METHODS}")
+        if method == "learntmean":
+            if getattr(self, "_learnt_weights", None) is None:
+                from .st_loader import load_torch_weights
+
+                self._learnt_weights = load_torch_weights(
+                    os.path.join(self.model_name, "1_WeightedMeanPooling"))["position_weights"].float()
+            self.encoder.set_position_weights(self._learnt_weights)
+        out: List[List[float]] = []
+        specb, self.specb = self.specb, False  # the USEB script has no bracket mode
+        try:
+            for i in range(0, len(sentences), self.batch_size):
+                ids, mask = self.tokenize_batch(sentences[i:i + self.batch_size], is_query=True)
+                emb = self.encoder.encode_tokens(ids, mask, method="weightedmean" if method == "learntmean" else method,
+                                                 layer_idx=self.layeridx)
+                out.extend(emb.cpu().numpy().tolist())
+        finally:
+            self.specb = specb
+            if method == "learntmean":
+                self.encoder.set_position_weights(None)
+        assert len(sentences) == len(out)
+        return out
 
 
 class SentenceEncoder:
-    """``SentenceTransformer.encode`` for a [Transformer -> Pooling(-> Normalize)] SGPT model on the B200 encoder."""
+    """``SentenceTransformer.encode`` for a [Transformer -> Pooling | WeightedMeanPooling (-> Dense | Asym)* (-> Normalize)]
+    SGPT model on the B200 encoder (module pipeline of sentence_transformers/SentenceTransformer.py:98, run as one
+    ``sgpt_encode`` call + ``sgpt_dense`` per head)."""
 
     def __init__(self, config: ModelConfig, state_dict: Dict[str, torch.Tensor], tokenizer, device: str = "cuda:0",
                  pooling: str = "weightedmean", max_seq_length: int = 300, batch_capacity: int = 256,
-                 max_tokens: Optional[int] = None):
+                 max_tokens: Optional[int] = None, position_weights: Optional[torch.Tensor] = None,
+                 heads: Optional[Sequence] = None, asym=None, normalize: bool = False, do_lower_case: bool = False):
         if pooling not in ST_POOLING:
             raise NotImplementedError(f"pooling mode {pooling!r} not in {ST_POOLING}")
+        if position_weights is not None and pooling != "weightedmean":
+            raise ValueError("position_weights need pooling='weightedmean'")
         self.config, self.tokenizer, self.pooling = config, tokenizer, pooling
         self.max_seq_length = max_seq_length
+        self.do_lower_case = do_lower_case
         self.encoder = Encoder(config, state_dict, device=device,
                                max_tokens=max_tokens or batch_capacity * max_seq_length, max_batch=batch_capacity)
         self.device = self.encoder.device
+        if position_weights is not None:
+            if position_weights.numel() < max_seq_length:
+                raise ValueError(f"{position_weights.numel()} position weights < max_seq_length {max_seq_length}")
+            self.encoder.set_position_weights(position_weights)
+        self.heads = list(heads or [])   # DenseHead stack applied to every input (models/Dense.py)
+        self.asym = asym                 # AsymHeads: stack chosen by the input dict key (models/Asym.py)
+        self.normalize = bool(normalize)  # trailing models/Normalize.py module
         pad = getattr(tokenizer, "pad_token_id", None)
         self.pad_id = int(pad) if pad is not None else 0
         # specb/speca state installed by SentenceBERTBOSEOS (models/Transformer.py attributes of the same names)
@@ -169,12 +257,71 @@ class SentenceEncoder:
         self.bos_spec_token_q_rep = self.bos_spec_token_d_rep = None
         self.replace_bos = False
 
-    def _text_length(self, text) -> int:
-        return len(text)  # SentenceTransformer.py:600-614 for plain strings
+    # ---- construction from a saved sentence-transformers directory -----------------------------------------------
+    @classmethod
+    def from_spec(cls, spec, tokenizer=None, device: str = "cuda:0", batch_capacity: int = 256,
+                  max_seq_length: Optional[int] = None, max_tokens: Optional[int] = None) -> "SentenceEncoder":
+        """Build from ``st_loader.load_st_directory(path)``; the tokenizer defaults to ``AutoTokenizer`` of the model
+        directory (models/Transformer.py:40)."""
+        from .heads import AsymHeads, DenseHead
 
-    def tokenize(self, texts: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
-        """models/Transformer.py:90-153: strip, tokenize with truncation, bracket rules, right-pad."""
+        if spec.state_dict is None:
+            raise ValueError("spec has no transformer weights (load_weights=False?)")
+        if tokenizer is None:
+            from transformers import AutoTokenizer
+
+            tokenizer = AutoTokenizer.from_pretrained(spec.hf_dir)
+        msl = max_seq_length or spec.max_seq_length
+        if msl is None:  # Transformer.py:43-46
+            msl = min(spec.config.max_pos, getattr(tokenizer, "model_max_length", spec.config.max_pos))
+        mk = lambda d: DenseHead(d.weight, d.bias, d.activation, device=device)  # noqa: E731
+        heads = [mk(d) for d in spec.dense]
+        asym = AsymHeads({k: [mk(d) for d in v] for k, v in spec.asym.items()}) if spec.asym else None
+        return cls(spec.config, spec.state_dict, tokenizer, device=device, pooling=spec.pooling, max_seq_length=msl,
+                   batch_capacity=batch_capacity, max_tokens=max_tokens, position_weights=spec.position_weights,
+                   heads=heads, asym=asym, normalize=spec.normalize, do_lower_case=spec.do_lower_case)
+
+    @classmethod
+    def from_pretrained(cls, model_path: str, device: str = "cuda:0", **kwargs) -> "SentenceEncoder":
+        """``SentenceTransformer(model_path)`` for a local model directory (SentenceTransformer.py:90-93): a
+        ``modules.json`` directory is read module by module; a plain HF directory becomes Transformer + mean Pooling
+        (``_load_auto_model``, :893-900)."""
+        import os
+
+        from . import st_loader
+
+        if os.path.exists(os.path.join(model_path, "modules.json")):
+            spec = st_loader.load_st_directory(model_path)
+        else:
+            from transformers import AutoConfig
+
+            spec = st_loader.STModelSpec(hf_dir=model_path, pooling="mean",
+                                         config=ModelConfig.from_hf(AutoConfig.from_pretrained(model_path)),
+                                         state_dict=st_loader.load_torch_weights(model_path))
+        return cls.from_spec(spec, device=device, **kwargs)
+
+    def get_sentence_embedding_dimension(self) -> int:
+        if self.heads:
+            return self.heads[-1].out_features
+        return self.config.d_model
+
+    def _text_length(self, text) -> int:
+        """SentenceTransformer.py:600-614: dict -> length of its first value; str -> len; list -> summed lengths."""
+        if isinstance(text, dict):
+            return len(next(iter(text.values())))
+        if not hasattr(text, "__len__"):
+            return 1
+        if len(text) == 0 or isinstance(text, str) or isinstance(text[0], int):
+            return len(text)
+        return sum(len(t) for t in text)
+
+    def tokenize(self, texts: Sequence) -> Tuple[np.ndarray, np.ndarray]:
+        """models/Transformer.py:90-153: strip, (lower-case), tokenize with truncation, bracket rules, right-pad.
+        ``{key: text}`` inputs contribute their text (the key selects the Asym stack in ``encode``)."""
+        texts = [next(iter(t.values())) if isinstance(t, dict) else t for t in texts]
         texts = [str(s).strip() for s in texts]
+        if self.do_lower_case:
+            texts = [s.lower() for s in texts]  # :116-118
         spec = None not in (self.bos_spec_token_q, self.eos_spec_token_q, self.bos_spec_token_d, self.eos_spec_token_d)
         limit = self.max_seq_length - 2 if spec else self.max_seq_length  # :135
         seqs = []
@@ -194,6 +341,10 @@ class SentenceEncoder:
             seqs.append(ids)
         return _pad_batch(seqs, self.pad_id)
 
+    @staticmethod
+    def _text_key(sentence) -> Optional[str]:
+        return next(iter(sentence.keys())) if isinstance(sentence, dict) else None
+
     def encode(self, sentences: Union[str, List[str]], batch_size: int = 32, show_progress_bar: bool = None,
                output_value: str = "sentence_embedding", convert_to_numpy: bool = True, convert_to_tensor: bool = False,
                device: str = None, normalize_embeddings: bool = False, num_proc=None):
@@ -202,16 +353,38 @@ class SentenceEncoder:
             raise NotImplementedError("only output_value='sentence_embedding' is built")
         if convert_to_tensor:
             convert_to_numpy = False
-        input_was_string = isinstance(sentences, str) or not hasattr(sentences, "__len__")
+        input_was_string = isinstance(sentences, (str, dict)) or not hasattr(sentences, "__len__")
         if input_was_string:
             sentences = [sentences]
+        post = bool(self.heads) or self.asym is not None
+        # Normalize is the last module of the pipeline: it can only be fused into the pooling kernel when no head follows
+        fuse_norm = (self.normalize or normalize_embeddings) and not post
         order = np.argsort([-self._text_length(s) for s in sentences], kind="stable")
-        out = torch.empty((len(sentences), self.config.d_model), dtype=torch.float32, device=self.device)
+        out = None
         for start in range(0, len(sentences), batch_size):
             idx = order[start:start + batch_size]
-            ids, mask = self.tokenize([sentences[i] for i in idx])
-            emb = self.encoder.encode_tokens(ids, mask, method=self.pooling, clamp=True, normalize=normalize_embeddings)
+            batch = [sentences[i] for i in idx]
+            ids, mask = self.tokenize(batch)
+            # the learnt WeightedMeanPooling always clamps its denominator (:34), like Pooling.py:122
+            emb = self.encoder.encode_tokens(ids, mask, method=self.pooling, clamp=True, normalize=fuse_norm)
+            if post:
+                from .heads import apply_heads
+
+                emb = apply_heads(emb, self.heads)
+                if self.asym is not None:
+                    key = self._text_key(batch[0])  # Asym.py:50-52: text_keys[0] selects the stack for the batch
+                    if key is not None:
+                        emb = self.asym.apply(emb, key)
+                if self.normalize or normalize_embeddings:
+                    emb = torch.nn.functional.normalize(emb, p=2, dim=1)  # SentenceTransformer.py:248-249
+            if out is None:
+                out = torch.empty((len(sentences), emb.shape[1]), dtype=torch.float32, device=self.device)
+            elif out.shape[1] != emb.shape[1]:
+                raise ValueError("inputs with different Asym text keys produce different embedding sizes; "
+                                 "encode them in separate calls (Asym.py: mixed types cannot be encoded)")
             out[torch.as_tensor(idx, device=self.device)] = emb
+        if out is None:
+            out = torch.empty((0, self.get_sentence_embedding_dimension()), dtype=torch.float32, device=self.device)
         if convert_to_tensor:
             res = out
         elif convert_to_numpy:
@@ -221,29 +394,54 @@ class SentenceEncoder:
         return res[0] if input_was_string else res
 
 
-class SentenceBERTBOSEOS:
-    """custommodels/sentence_bert_asym.py:21-79 on top of SentenceEncoder (specb only: '[SOS]'/'{SOS}' markers are
-    replaced by the bracket ids and the closing bracket is appended)."""
+class SentenceBERTAsym:
+    """custommodels/sentence_bert_asym.py:8-19: queries are passed as ``{'QRY': text}``, documents as
+    ``{'DOCPOS': text}`` so that the model's Asym module applies the matching Dense stack."""
 
-    def __init__(self, model: SentenceEncoder, sep: str = " ", specb: bool = False, sos_q: int = None, sos_d: int = None):
-        self.model, self.sep, self.specb = model, sep, specb
-        if specb:
-            tok = model.tokenizer
-            model.bos_spec_token_q = sos_q if sos_q is not None else tok.encode("[SOS]")[0]
-            model.bos_spec_token_d = sos_d if sos_d is not None else tok.encode("{SOS}")[0]
-            model.bos_spec_token_q_rep = tok.encode("[")[0]
-            model.eos_spec_token_q = tok.encode("]")[0]
-            model.bos_spec_token_d_rep = tok.encode("{")[0]
-            model.eos_spec_token_d = tok.encode("}")[0]
-            model.replace_bos = True
+    def __init__(self, model: SentenceEncoder, sep: str = " "):
+        self.model, self.sep = model, sep
 
     def encode_queries(self, queries: List[str], batch_size: int = 16, **kwargs):
-        if self.specb:
+        return self.model.encode([{"QRY": q} for q in queries], batch_size=batch_size, **kwargs)
+
+    def encode_corpus(self, corpus: List[Dict[str, str]], batch_size: int = 8, **kwargs):
+        # (the reference leaves title-less documents as bare strings, :18 — i.e. without a head; kept as is)
+        sentences = [{"DOCPOS": (doc["title"] + self.sep + doc["text"]).strip()} if "title" in doc else doc["text"].strip()
+                     for doc in corpus]
+        return self.model.encode(sentences, batch_size=batch_size, **kwargs)
+
+
+class SentenceBERTBOSEOS:
+    """custommodels/sentence_bert_asym.py:21-79 on top of SentenceEncoder.  specb: the '[SOS]'/'{SOS}' markers are
+    replaced by the bracket ids and the closing bracket is appended; speca: the markers are kept and '[EOS]'/'{EOS}'
+    are appended (the four added tokens must exist in the tokenizer and the checkpoint's embedding matrix, :56-58)."""
+
+    def __init__(self, model: SentenceEncoder, sep: str = " ", specb: bool = False, sos_q: int = None, sos_d: int = None,
+                 speca: bool = False):
+        self.model, self.sep, self.specb, self.speca = model, sep, specb, speca
+        tok = model.tokenizer
+        first = lambda text: tok.encode(text)[0]  # noqa: E731
+        if specb:
+            model.bos_spec_token_q = sos_q if sos_q is not None else first("[SOS]")
+            model.bos_spec_token_d = sos_d if sos_d is not None else first("{SOS}")
+            model.bos_spec_token_q_rep = first("[")
+            model.eos_spec_token_q = first("]")
+            model.bos_spec_token_d_rep = first("{")
+            model.eos_spec_token_d = first("}")
+            model.replace_bos = True
+        elif speca:
+            model.bos_spec_token_q = sos_q if sos_q is not None else first("[SOS]")
+            model.eos_spec_token_q = first("[EOS]")
+            model.bos_spec_token_d = sos_d if sos_d is not None else first("{SOS}")
+            model.eos_spec_token_d = first("{EOS}")
+
+    def encode_queries(self, queries: List[str], batch_size: int = 16, **kwargs):
+        if self.specb or self.speca:
             queries = ["[SOS]" + q for q in queries]
         return self.model.encode(queries, batch_size=batch_size, **kwargs)
 
     def encode_corpus(self, corpus: List[Dict[str, str]], batch_size: int = 8, **kwargs):
-        pre = "{SOS}" if self.specb else ""
+        pre = "{SOS}" if (self.specb or self.speca) else ""
         sentences = [(pre + doc["title"] + self.sep + doc["text"]).strip() if "title" in doc else pre + doc["text"].strip()
                      for doc in corpus]
         return self.model.encode(sentences, batch_size=batch_size, **kwargs)

@@ -147,6 +147,7 @@ class Encoder:
         self._stage_evt = [torch.cuda.Event() for _ in range(2)]
         self._stage_idx = 0
         self.h2d_bytes_last = 0
+        self._pos_weights: Optional[torch.Tensor] = None
 
     def close(self):
         if getattr(self, "_handle", None):
@@ -158,6 +159,20 @@ class Encoder:
             self.close()
         except Exception:
             pass
+
+    def set_position_weights(self, weights: Optional[torch.Tensor]) -> None:
+        """Install (or, with None, remove) a learnt position-weight table for method="weightedmean": token at padded
+        position i gets weight ``weights[i]`` instead of ``i+1`` (ST/models/WeightedMeanPooling.py:21-37)."""
+        if weights is None:
+            self._pos_weights = None
+            _lib.check(self._lib.sgpt_model_set_position_weights(self._handle, None, 0))
+            return
+        w = weights.detach().to(self.device, torch.float32).contiguous().view(-1)
+        if w.numel() == 0:
+            raise ValueError("empty position-weight table")
+        self._pos_weights = w  # borrowed by the C handle
+        _lib.check(self._lib.sgpt_model_set_position_weights(self._handle, w.data_ptr(), w.numel()),
+                   "sgpt_model_set_position_weights")
 
     @property
     def embedding_dim(self) -> int:

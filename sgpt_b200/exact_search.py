@@ -19,9 +19,15 @@ logger = logging.getLogger(__name__)
 
 
 class DenseRetrievalExactSearch:
-    def __init__(self, model, batch_size: int = 128, corpus_chunk_size: int = 50000, **kwargs):
-        # model is any class that provides encode_corpus() and encode_queries() (XS:24)
+    def __init__(self, model, batch_size: int = 128, corpus_chunk_size: int = 50000, plain_lists: bool = False,
+                 **kwargs):
+        """model is any class that provides encode_corpus() and encode_queries() (XS:24).  ``plain_lists=False`` is the
+        reference's custom convention — ``[(id, text)]`` / ``[(id, {title, text})]`` tuples and a ``batch_num`` keyword
+        (XS:56-62, 87-93); ``plain_lists=True`` is upstream beir's DRES convention — ``List[str]`` /
+        ``List[{title, text}]`` — which the ST-path wrappers (SentenceBERTBOSEOS / SentenceBERTAsym, used with
+        ``beir.retrieval.search.dense.DenseRetrievalExactSearch`` at BDR:405-412) expect."""
         self.model = model
+        self.plain_lists = plain_lists
         self.batch_size = batch_size
         self.score_functions = {"cos_sim": "cos_sim", "dot": "dot"}
         self.score_function_desc = {"cos_sim": "Cosine Similarity", "dot": "Dot Product"}
@@ -42,7 +48,7 @@ class DenseRetrievalExactSearch:
         logger.info("Encoding Queries...")
         query_ids = list(queries.keys())
         self.results = {qid: {} for qid in query_ids}
-        query_list = [(qid, queries[qid]) for qid in queries]  # XS:56
+        query_list = [queries[qid] if self.plain_lists else (qid, queries[qid]) for qid in queries]  # XS:56
         q_emb = self._as_device(self.model.encode_queries(
             query_list, batch_size=self.batch_size, show_progress_bar=self.show_progress_bar,
             convert_to_tensor=self.convert_to_tensor))
@@ -50,7 +56,7 @@ class DenseRetrievalExactSearch:
         logger.info("Sorting Corpus by document length (Longest first)...")
         corpus_ids = sorted(corpus, key=lambda k: len(corpus[k].get("title", "") + corpus[k].get("text", "")),
                             reverse=True)  # XS:66-70
-        corpus_list = [(cid, corpus[cid]) for cid in corpus_ids]
+        corpus_list = [corpus[cid] if self.plain_lists else (cid, corpus[cid]) for cid in corpus_ids]
         # XS:118 drops corpus_id == query_id: as a per-query global row index (or -1) so the GPU merge can apply it
         row_of = {cid: i for i, cid in enumerate(corpus_ids)}
         exclude = torch.tensor([row_of.get(qid, -1) for qid in query_ids], dtype=torch.int64, device=self.device)
@@ -65,9 +71,10 @@ class DenseRetrievalExactSearch:
         for batch_num, start in enumerate(starts):
             logger.info("Encoding Batch {}/{}...".format(batch_num + 1, len(starts)))
             end = min(start + self.corpus_chunk_size, len(corpus_list))
+            extra = {} if self.plain_lists else {"batch_num": batch_num}
             sub = self._as_device(self.model.encode_corpus(
                 corpus_list[start:end], batch_size=self.batch_size, show_progress_bar=self.show_progress_bar,
-                convert_to_tensor=self.convert_to_tensor, batch_num=batch_num))
+                convert_to_tensor=self.convert_to_tensor, **extra))
             shard = CorpusShard.from_embeddings(sub, device=self.device, id_base=start)
             # XS:96-108: scores, NaN -> -1, top-(k+1) of this chunk
             s, i = shard.search(q_emb, kk, score_function)

@@ -1,0 +1,170 @@
+"""CPU-only checks of the harness-side rows of SURVEY.md §8f: the sentence-transformers directory loader (against
+directories written by the reference's own module classes, tests/golden/make_st_model.py), the BEIR loader/evaluator
+stand-ins, the retrieval CLI flow with a stub retriever, and the pickle embedding cache logic."""
+import json
+import math
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+
+
+def test_st_directory_loader_reads_reference_written_modules():
+    from sgpt_b200.st_loader import load_st_directory
+
+    ref = np.load(os.path.join(GOLDEN, "st_tiny.npz"))
+    spec = load_st_directory(os.path.join(GOLDEN, "st_tiny"))
+    assert spec.config.arch == "gpt_neo" and spec.config.d_model == 128 and spec.config.n_layer == 2
+    assert spec.config.attention_layers == ["global", "local"] and spec.config.window == 8
+    assert spec.max_seq_length == 32 and spec.do_lower_case is False
+    assert spec.pooling == "weightedmean" and spec.normalize is True and not spec.asym
+    assert torch.equal(spec.position_weights, torch.from_numpy(ref["position_weights"]))
+    assert len(spec.dense) == 1
+    d = spec.dense[0]
+    assert d.activation == "torch.nn.modules.activation.Tanh" and d.key_name == "sentence_embedding"
+    assert torch.equal(d.weight, torch.from_numpy(ref["dense_w"])) and torch.equal(d.bias, torch.from_numpy(ref["dense_b"]))
+    assert "wte.weight" in spec.state_dict and spec.state_dict["h.1.mlp.c_fc.weight"].shape == (256, 128)
+    assert [t.rsplit(".", 1)[-1] for t, _ in spec.modules] == ["Transformer", "WeightedMeanPooling", "Dense", "Normalize"]
+
+
+def test_st_directory_loader_asym_and_pooling_flags():
+    from sgpt_b200.heads import activation_id
+    from sgpt_b200.st_loader import load_st_directory, pooling_mode_from_config
+
+    spec = load_st_directory(os.path.join(GOLDEN, "st_tiny_asym"), load_weights=False)
+    assert spec.state_dict is None and spec.pooling == "weightedmean" and spec.position_weights is None
+    assert sorted(spec.asym) == ["DOCPOS", "QRY"] and not spec.dense and not spec.normalize
+    q, d = spec.asym["QRY"][0], spec.asym["DOCPOS"][0]
+    assert q.bias is None and q.weight.shape == (32, 128) and activation_id(q.activation) == 0
+    assert d.bias is not None and activation_id(d.activation) == 1
+    assert pooling_mode_from_config({"pooling_mode_mean_tokens": True}) == "mean"
+    assert pooling_mode_from_config({"pooling_mode_mean_tokens": False, "pooling_mode_lasttoken": True}) == "lasttoken"
+    with pytest.raises(NotImplementedError):
+        pooling_mode_from_config({"pooling_mode_cls_token": True, "pooling_mode_mean_tokens": False})
+    with pytest.raises(NotImplementedError):
+        pooling_mode_from_config({"pooling_mode_mean_tokens": True, "pooling_mode_max_tokens": True})
+    with pytest.raises(NotImplementedError):
+        activation_id("torch.nn.modules.activation.GELU")
+    with pytest.raises(FileNotFoundError):
+        load_st_directory(GOLDEN)
+
+
+def test_heads_refuse_cpu():
+    from sgpt_b200.heads import DenseHead
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DenseHead(torch.zeros(4, 4), device="cpu")
+
+
+def _write_beir_dataset(root):
+    os.makedirs(os.path.join(root, "qrels"))
+    docs = [{"_id": f"d{i}", "title": f"T{i}", "text": f"text {i}"} for i in range(6)] + [{"_id": "empty", "title": "", "text": ""}]
+    with open(os.path.join(root, "corpus.jsonl"), "w") as f:
+        f.writelines(json.dumps(d) + "\n" for d in docs)
+    with open(os.path.join(root, "queries.jsonl"), "w") as f:
+        f.writelines(json.dumps({"_id": q, "text": f"query {q}"}) + "\n" for q in ("q1", "q2", "q_unjudged"))
+    with open(os.path.join(root, "qrels", "test.tsv"), "w") as f:
+        f.write("query-id\tcorpus-id\tscore\n")
+        f.write("q1\td0\t2\nq1\td3\t1\nq1\td5\t0\nq2\td1\t1\n")
+
+
+def test_generic_data_loader(tmp_path):
+    from sgpt_b200.beir_compat import GenericDataLoader
+
+    root = str(tmp_path / "toy")
+    _write_beir_dataset(root)
+    corpus, queries, qrels = GenericDataLoader(root).load(split="test")
+    assert len(corpus) == 7 and corpus["d2"] == {"text": "text 2", "title": "T2"}
+    assert queries == {"q1": "query q1", "q2": "query q2"}  # only judged queries survive
+    assert qrels == {"q1": {"d0": 2, "d3": 1, "d5": 0}, "q2": {"d1": 1}}
+    with pytest.raises(ValueError, match="not present"):
+        GenericDataLoader(str(tmp_path / "nope")).load()
+
+
+def test_evaluate_retrieval_matches_hand_computed_trec_eval_values():
+    from sgpt_b200.beir_compat import EvaluateRetrieval
+
+    qrels = {"q1": {"d0": 2, "d3": 1, "d5": 0}, "q2": {"d1": 1}}
+    results = {"q1": {"d3": 0.9, "d5": 0.8, "d0": 0.7, "d4": 0.1, "q1": 5.0},  # the self id is dropped before scoring
+               "q2": {"d2": 0.5, "d1": 0.5},                                  # tie: larger doc id ranks first
+               "q3": {"d0": 1.0}}                                             # no qrels: not evaluated
+    ndcg, _map, recall, prec = EvaluateRetrieval.evaluate(qrels, results, [1, 3])
+    idcg3 = 2 / math.log2(2) + 1 / math.log2(3)
+    ndcg3_q1 = (1 / math.log2(2) + 2 / math.log2(4)) / idcg3
+    ndcg3_q2 = (1 / math.log2(3)) / 1.0
+    assert ndcg["NDCG@1"] == round(((1 / 2) + 0.0) / 2, 5)
+    assert ndcg["NDCG@3"] == round((ndcg3_q1 + ndcg3_q2) / 2, 5)
+    assert _map["MAP@3"] == round((((1 / 1) + (2 / 3)) / 2 + (1 / 2) / 1) / 2, 5)
+    assert recall["Recall@1"] == round((1 / 2 + 0) / 2, 5) and recall["Recall@3"] == 1.0
+    assert prec["P@1"] == 0.5 and prec["P@3"] == round((2 / 3 + 1 / 3) / 2, 5)
+
+
+def test_retrieve_cli_flow_with_stub_retriever(tmp_path, monkeypatch):
+    from sgpt_b200 import retrieve
+
+    data = tmp_path / "datasets"
+    _write_beir_dataset(str(data / "toy"))
+
+    class StubRetriever:
+        def search(self, corpus, queries, top_k, score_function, **kw):
+            assert "empty" not in corpus and top_k == 1000 and score_function == "cos_sim"
+            return {"q1": {"d0": 0.9, "d1": 0.2}, "q2": {"d1": 0.8}}
+
+    monkeypatch.setattr(retrieve, "build_retriever", lambda args: StubRetriever())
+    args = retrieve.parse_args(["--dataset", "toy", "--modelname", "org/model", "--method", "weightedmean", "--datapath",
+                                str(data), "--outdir", str(tmp_path)])
+    out = retrieve.main(args)
+    assert out["ndcg"]["NDCG@1"] == 1.0 and out["recall"]["Recall@10"] == 0.75
+    with open(tmp_path / "results_org_model_weightedmean_toy.json") as f:
+        assert json.load(f)["q2"] == {"d1": 0.8}
+    with open(tmp_path / "beir_embeddings_ndcgs.json") as f:
+        js = json.load(f)
+    assert js["ndcgs"]["org_model"]["toy"]["NDCG@1"] == 1.0 and "toy" in js["precisions"]["org_model"]
+    assert retrieve.main(args) == {}  # result file exists and --overwrite not given: skipped (BDR:435-437)
+    # CQADupStack average appears once all twelve sub-datasets are present (BDR:484-493)
+    path = str(tmp_path / "cqa.json")
+    for i, d in enumerate(retrieve.CQADUPSTACK_DATASETS):
+        js = retrieve.update_scores_json(path, "m", f"cqadupstack_{d}", {"NDCG@10": float(i)}, {}, {}, {})
+        assert ("cqadupstack" in js["ndcgs"]["m"]) == (i == 11)
+    assert abs(js["ndcgs"]["m"]["cqadupstack"]["NDCG@10"] - 5.5) < 1e-9
+    with pytest.raises(ValueError, match="speca"):
+        monkeypatch.undo()
+        retrieve.build_retriever(retrieve.parse_args(["--speca"]))
+
+
+def test_pickle_embedding_cache_logic(tmp_path, monkeypatch):
+    """save_emb writes {id: embedding} pickles per query set / corpus chunk and later calls read them back in the
+    order given (BDR:311-348) — exercised with the encoder stubbed out (the GPU round trip is in the -m gpu suite)."""
+    from sgpt_b200.embedder import CustomEmbedder
+
+    monkeypatch.chdir(tmp_path)
+    emb = object.__new__(CustomEmbedder)
+    emb.save_emb, emb.device = True, torch.device("cpu")
+    emb.base_path = "embeddings/model/weightedmean/toy"
+    os.makedirs("embeddings/model/weightedmean")
+    calls = []
+
+    def fake_embed_texts(sentences, is_query):
+        calls.append((list(sentences), is_query))
+        return torch.tensor([[float(len(s)), 1.0 if is_query else 0.0] for s in sentences])
+
+    emb.embed_texts = fake_embed_texts
+    queries = [("q2", "bb"), ("q1", "a")]
+    corpus = [("c1", {"title": "T", "text": " x "}), ("c2", {"text": " yy "})]
+    q = emb.encode_queries(queries, batch_size=4)
+    c = emb.encode_corpus(corpus, batch_size=4, batch_num=3)
+    assert q.tolist() == [[2.0, 1.0], [1.0, 1.0]] and c.tolist() == [[4.0, 0.0], [2.0, 0.0]]
+    assert calls == [(["bb", "a"], True), (["T  x", "yy"], False)]
+    with open("embeddings/model/weightedmean/toy_corpus3.pickle", "rb") as f:
+        assert sorted(pickle.load(f)) == ["c1", "c2"]
+    calls.clear()
+    emb.save_emb = False  # an existing pickle is used regardless of save_emb, as upstream
+    assert emb.encode_queries(list(reversed(queries)), batch_size=4).tolist() == [[1.0, 1.0], [2.0, 1.0]]
+    assert emb.encode_corpus(corpus, batch_size=4, batch_num=3).tolist() == c.tolist()
+    assert calls == []
+    assert emb.encode_corpus(corpus[:1], batch_size=4, batch_num=4).tolist() == [[4.0, 0.0]]  # other chunk: recomputed
+    assert len(calls) == 1 and not os.path.exists("embeddings/model/weightedmean/toy_corpus4.pickle")
