@@ -62,6 +62,11 @@ int sgpt_layernorm(const float* x, const float* gamma, const float* beta, void* 
 int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out, int64_t ldo,
                 const float* resid, int M, int N, int K, int epilogue, sgpt_stream_t stream);
 
+/* F7'. y[m,:] = LayerNorm(x[rows[m],:]) for a gathered subset of rows (bf16 out): the LM-head input of
+ *      sgpt_lm_logprobs.  x fp32[T,d]; rows int32[M] (values in [0,T)); y bf16[M,d]. */
+int sgpt_layernorm_gather(const float* x, const int32_t* rows, const float* gamma, const float* beta, void* y, int M,
+                          int d, float eps, sgpt_stream_t stream);
+
 /* F2'. In-place fp32 LayerNorm (BLOOM word_embeddings_layernorm, HF:bloom/modeling_bloom.py:496): x fp32[T,d]. */
 int sgpt_layernorm_f32_inplace(float* x, const float* gamma, const float* beta, int T, int d, float eps,
                                sgpt_stream_t stream);
@@ -132,6 +137,10 @@ int sgpt_pool_ex(const float* x, const int32_t* pos, const int32_t* cu_seqlens, 
 int sgpt_dense(const float* x, const float* w, const float* bias, float* y, int B, int in_features, int out_features,
                int activation, sgpt_stream_t stream);
 
+/* P2 stand-alone: x[b,:] /= max(||x[b,:]||_2, 1e-12) in place (ST/models/Normalize.py:13-14;
+ * SentenceTransformer.py:248-249) for embeddings that passed through a head after pooling.  x fp32[B,d]. */
+int sgpt_normalize_rows(float* x, int B, int d, sgpt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Whole-encoder handle (F1..F7 + P1 in one call).
  * ------------------------------------------------------------------------------------------------------------------ */
@@ -189,6 +198,34 @@ void sgpt_model_destroy(sgpt_model_t m);
 int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const int32_t* cu_seqlens, int B, int T,
                 int max_seqlen, int layer_idx, int pool_mode, int clamp_denominator, int normalize, float* out,
                 sgpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Continuation log-likelihoods with the same encoder (the SGPT cross-encoder scorer,
+ * crossencoder/beir/sgptce.py:150-262 `_loglikelihood_tokens`).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* The GPT forward pass alone (F1..F6 of every block): replaces `model(inps)` at sgptce.py:76-83 up to the final
+ * LayerNorm.  Leaves the fp32 residual stream [T,d] in the handle for sgpt_lm_logprobs / sgpt_model_read_residual. */
+int sgpt_forward(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const int32_t* cu_seqlens, int B, int T,
+                 int max_seqlen, sgpt_stream_t stream);
+
+/* token_logprobs[i] = log_softmax(LN_f(resid[rows[i]]) @ lm_head_w^T + lm_head_bias)[targets[i]]
+ *     == F.log_softmax(logits, -1) (sgptce.py:221) gathered at the continuation tokens (:247), for the packed token
+ *     rows `rows` of the batch the last sgpt_forward ran.  lm_head_w bf16[vocab,d] (the tied wte for GPT-Neo / BLOOM,
+ *     lm_head.weight for GPT-J), lm_head_bias fp32[vocab] or NULL (GPT-J has one); rows,targets int32[M];
+ *     greedy int32[M] or NULL receives argmax(logits) (:229, lowest index on ties).  The [M,vocab] logits exist only in
+ *     `ws`, rows_per_chunk rows at a time (ws >= sgpt_lm_logprobs_workspace_bytes(d_model, vocab, rows_per_chunk)). */
+int64_t sgpt_lm_logprobs_workspace_bytes(int d_model, int vocab, int rows_per_chunk);
+int sgpt_lm_logprobs(sgpt_model_t m, const void* lm_head_w, const float* lm_head_bias, int vocab, const int32_t* rows,
+                     const int32_t* targets, int M, float* token_logprobs, int32_t* greedy, void* ws, int64_t ws_bytes,
+                     int rows_per_chunk, sgpt_stream_t stream);
+
+/* Building blocks of the above.  sgpt_token_logprobs: logits fp32[M,lds] (vocab valid columns) -> log-softmax value of
+ * the target column per row (+ optional argmax).  sgpt_segment_sum: out[r] = sum(x[offsets[r]..offsets[r+1])) in index
+ * order — the per-request `float(logits.sum())` of sgptce.py:250; offsets int32[R+1]. */
+int sgpt_token_logprobs(const float* logits, int64_t lds, int M, int vocab, const float* bias, const int32_t* targets,
+                        float* logprob, int32_t* greedy, sgpt_stream_t stream);
+int sgpt_segment_sum(const float* x, const int32_t* offsets, int R, float* out, sgpt_stream_t stream);
 
 /* Installs (w != NULL) or removes (w == NULL) a learnt position-weight table for pool_mode WEIGHTEDMEAN in sgpt_encode
  * (ST/models/WeightedMeanPooling.py).  w is a DEVICE fp32[n] buffer borrowed by the handle; sgpt_encode then fails with

@@ -49,8 +49,15 @@ _SIGNATURES = {
     "sgpt_pool": (i32, [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sgpt_pool_accumulate": (i32, [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
     "sgpt_pool_ex": (i32, [vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "sgpt_normalize_rows": (i32, [vp, i32, i32, vp]),
     "sgpt_dense": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "sgpt_model_set_position_weights": (i32, [vp, vp, i32]),
+    "sgpt_layernorm_gather": (i32, [vp, vp, vp, vp, vp, i32, i32, f32, vp]),
+    "sgpt_forward": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "sgpt_lm_logprobs_workspace_bytes": (i64, [i32, i32, i32]),
+    "sgpt_lm_logprobs": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i64, i32, vp]),
+    "sgpt_token_logprobs": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp]),
+    "sgpt_segment_sum": (i32, [vp, vp, i32, vp, vp]),
     "sgpt_model_create": (i32, [C.POINTER(ModelConfigC), C.POINTER(ModelWeightsC), C.POINTER(vp)]),
     "sgpt_model_destroy": (None, [vp]),
     "sgpt_encode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),

@@ -69,19 +69,22 @@ __device__ __forceinline__ void ln_store(float4* y, size_t idx, float o0, float 
 
 template <int TPR, int V, class OutT>
 __device__ __forceinline__ void layernorm_body(const float4* x, const float4* __restrict__ g,
-                                               const float4* __restrict__ b, OutT* y, int T, int d4, float eps) {
+                                               const float4* __restrict__ b, OutT* y, int T, int d4, float eps,
+                                               const int32_t* __restrict__ src_rows = nullptr) {
   constexpr int ROWS = 256 / TPR;
   __shared__ float scratch[ROWS * (TPR / 32) + 1];
   const int row_in_cta = threadIdx.x / TPR;
   const int l = threadIdx.x % TPR;
   const int row = blockIdx.x * ROWS + row_in_cta;
   const bool active = row < T;
+  // gather variant: output row `row` is the LayerNorm of input row src_rows[row]
+  const int src = (src_rows != nullptr && active) ? __ldg(src_rows + row) : row;
   float4 v[V];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = l + i * TPR;
-    v[i] = (active && c < d4) ? x[static_cast<size_t>(row) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = (active && c < d4) ? x[static_cast<size_t>(src) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float inv_d = 1.0f / static_cast<float>(d4 * 4);
@@ -118,6 +121,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float4* __restrict
                                                         int d4, float eps) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
   layernorm_body<TPR, V>(x, g, b, y, T, d4, eps);
+}
+
+// LayerNorm of a gathered subset of rows: y[m,:] = LN(x[rows[m],:]) (the LM-head input of the cross-encoder scorer)
+template <int TPR, int V>
+__global__ void __launch_bounds__(256) layernorm_gather_kernel(const float4* __restrict__ x,
+                                                               const float4* __restrict__ g,
+                                                               const float4* __restrict__ b, uint2* __restrict__ y,
+                                                               int M, int d4, float eps,
+                                                               const int32_t* __restrict__ rows) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
+  layernorm_body<TPR, V>(x, g, b, y, M, d4, eps, rows);
 }
 
 // fp32 output, may run in place (each thread rewrites exactly the elements it read)
@@ -275,6 +289,20 @@ __global__ void __launch_bounds__(256) l2_scale_rows_kernel(float4* __restrict__
   }
 }
 
+// Stand-alone P2 for embeddings that went through a head after pooling: one warp per row, any d.
+__global__ void __launch_bounds__(256) l2_normalize_rows_kernel(float* __restrict__ x, int B, int d) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  float* r = x + static_cast<size_t>(row) * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s = fmaf(r[c], r[c], s);
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int c = lane; c < d; c += 32) r[c] *= inv;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Shard maintenance: fp32 -> bf16 rows, and 1 / max(||row||, 1e-12) of the *stored* bf16 rows.
 // ---------------------------------------------------------------------------------------------------------------
@@ -395,6 +423,21 @@ extern "C" int sgpt_layernorm(const float* x, const float* gamma, const float* b
   return SGPT_OK;
 }
 
+extern "C" int sgpt_layernorm_gather(const float* x, const int32_t* row_idx, const float* gamma, const float* beta, void* y,
+                                     int M, int d, float eps, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(M >= 0 && d > 0 && d % 4 == 0, "sgpt_layernorm_gather: d=%d must be a positive multiple of 4", d);
+  SGPT_REQUIRE(row_idx != nullptr, "sgpt_layernorm_gather: rows required");  // (`rows` is a local of the macro below)
+  if (M == 0) return SGPT_OK;
+  const int d4 = d / 4;
+  LaunchScope _ls(kCatLayerNorm, stream);
+  SGPT_ROW_DISPATCH(layernorm_gather_kernel, d4, M, stream, reinterpret_cast<const float4*>(x),
+                    reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
+                    static_cast<uint2*>(y), M, d4, eps, row_idx);
+  SGPT_CHECK_CUDA(cudaGetLastError());
+  return SGPT_OK;
+}
+
 extern "C" int sgpt_layernorm_f32_inplace(float* x, const float* gamma, const float* beta, int T, int d, float eps,
                                           sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -464,6 +507,15 @@ extern "C" int sgpt_pool(const float* x, const int32_t* pos, const int32_t* cu_s
                          int clamp_denominator, int normalize, sgpt_stream_t stream_) {
   return sgpt_pool_ex(x, pos, cu_seqlens, gamma, beta, eps, nullptr, 0, out, row_stats_ws, B, T, d, mode,
                       clamp_denominator, normalize, /*accumulate=*/0, /*out_scale=*/1.0f, stream_);
+}
+
+extern "C" int sgpt_normalize_rows(float* x, int B, int d, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(B >= 0 && d > 0, "sgpt_normalize_rows: bad sizes");
+  if (B == 0) return SGPT_OK;
+  LaunchScope _ls(kCatPool, stream);
+  SGPT_CHECK_CUDA(launch_kernel(l2_normalize_rows_kernel, dim3((B + 7) / 8), dim3(256), 0, stream, x, B, d));
+  return SGPT_OK;
 }
 
 extern "C" int sgpt_dense(const float* x, const float* w, const float* bias, float* y, int B, int in_features,

@@ -145,10 +145,15 @@ extern "C" void sgpt_model_destroy(sgpt_model_t m) {
     if (_rc != SGPT_OK) return _rc; \
   } while (0)
 
+constexpr int kNoPooling = -1;  // internal pool_mode of sgpt_forward: run the blocks, leave the residual stream
+
 extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const int32_t* cu_seqlens, int B,
                            int T, int max_seqlen, int layer_idx, int pool_mode, int clamp_denominator, int normalize,
                            float* out, sgpt_stream_t stream) {
   SGPT_REQUIRE(m != nullptr, "sgpt_encode: null model");
+  SGPT_REQUIRE(pool_mode == kNoPooling || (pool_mode >= SGPT_POOL_MEAN && pool_mode <= SGPT_POOL_LASTTOKENMEAN),
+               "sgpt_encode: unknown pooling mode %d", pool_mode);
+  SGPT_REQUIRE(pool_mode == kNoPooling || out != nullptr, "sgpt_encode: null output");
   const sgpt_model_config& c = m->cfg;
   SGPT_REQUIRE(B >= 0 && T >= 0, "sgpt_encode: negative sizes");
   SGPT_REQUIRE(T <= c.max_tokens && B <= c.max_batch, "sgpt_encode: batch (B=%d, T=%d) exceeds workspace (B<=%d, T<=%d)",
@@ -212,10 +217,51 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
                            stream));
     }
   }
+  if (pool_mode == kNoPooling) return SGPT_OK;
   const bool final_ln = (layer_idx == c.n_layer);
   SGPT_TRY(sgpt_pool_ex(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr,
                         c.ln_eps, pool_w, pool_w ? m->n_pool_w : 0, out, m->stats, B, T, d, base_mode, clamp_denominator,
                         normalize, /*accumulate=*/all_layers && c.n_layer > 0, layer_scale, stream));
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_forward(sgpt_model_t m, const int32_t* ids, const int32_t* pos, const int32_t* cu_seqlens, int B, int T,
+                            int max_seqlen, sgpt_stream_t stream) {
+  return sgpt_encode(m, ids, pos, cu_seqlens, B, T, max_seqlen, /*layer_idx=*/-1, kNoPooling, 0, 0, nullptr, stream);
+}
+
+static inline int64_t lm_lds(int vocab) { return (static_cast<int64_t>(vocab) + 3) & ~int64_t(3); }
+static inline int64_t lm_align(int64_t x) { return (x + 255) & ~int64_t(255); }
+
+extern "C" int64_t sgpt_lm_logprobs_workspace_bytes(int d_model, int vocab, int rows_per_chunk) {
+  if (d_model <= 0 || vocab <= 0 || rows_per_chunk <= 0) return 0;
+  return lm_align(static_cast<int64_t>(rows_per_chunk) * d_model * 2) +
+         lm_align(static_cast<int64_t>(rows_per_chunk) * lm_lds(vocab) * 4) + 256;
+}
+
+extern "C" int sgpt_lm_logprobs(sgpt_model_t m, const void* lm_head_w, const float* lm_head_bias, int vocab,
+                                const int32_t* rows, const int32_t* targets, int M, float* token_logprobs,
+                                int32_t* greedy, void* ws, int64_t ws_bytes, int rows_per_chunk, sgpt_stream_t stream) {
+  SGPT_REQUIRE(m != nullptr && lm_head_w != nullptr, "sgpt_lm_logprobs: null model or LM head");
+  SGPT_REQUIRE(M >= 0 && vocab > 0 && rows_per_chunk > 0, "sgpt_lm_logprobs: bad sizes");
+  SGPT_REQUIRE(M == 0 || (rows != nullptr && targets != nullptr && token_logprobs != nullptr),
+               "sgpt_lm_logprobs: null argument");
+  const int d = m->cfg.d_model;
+  SGPT_REQUIRE(ws != nullptr && ws_bytes >= sgpt_lm_logprobs_workspace_bytes(d, vocab, rows_per_chunk),
+               "sgpt_lm_logprobs: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
+               (long long)sgpt_lm_logprobs_workspace_bytes(d, vocab, rows_per_chunk));
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  void* xsel = w;
+  float* logits = reinterpret_cast<float*>(w + lm_align(static_cast<int64_t>(rows_per_chunk) * d * 2));
+  const int64_t lds = lm_lds(vocab);
+  for (int m0 = 0; m0 < M; m0 += rows_per_chunk) {
+    const int mc = (M - m0 < rows_per_chunk) ? M - m0 : rows_per_chunk;
+    // hidden_states[-1] of the selected positions: ln_f of the residual stream the last sgpt_forward left behind
+    SGPT_TRY(sgpt_layernorm_gather(m->resid, rows + m0, m->w.lnf_g, m->w.lnf_b, xsel, mc, d, m->cfg.ln_eps, stream));
+    SGPT_TRY(sgpt_scores(xsel, lm_head_w, nullptr, nullptr, logits, lds, mc, vocab, d, stream));
+    SGPT_TRY(sgpt_token_logprobs(logits, lds, mc, vocab, lm_head_bias, targets + m0, token_logprobs + m0,
+                                 greedy ? greedy + m0 : nullptr, stream));
+  }
   return SGPT_OK;
 }
 

@@ -368,7 +368,7 @@ class SentenceEncoder:
             # the learnt WeightedMeanPooling always clamps its denominator (:34), like Pooling.py:122
             emb = self.encoder.encode_tokens(ids, mask, method=self.pooling, clamp=True, normalize=fuse_norm)
             if post:
-                from .heads import apply_heads
+                from .heads import apply_heads, normalize_rows_
 
                 emb = apply_heads(emb, self.heads)
                 if self.asym is not None:
@@ -376,7 +376,7 @@ class SentenceEncoder:
                     if key is not None:
                         emb = self.asym.apply(emb, key)
                 if self.normalize or normalize_embeddings:
-                    emb = torch.nn.functional.normalize(emb, p=2, dim=1)  # SentenceTransformer.py:248-249
+                    emb = normalize_rows_(emb.contiguous())  # SentenceTransformer.py:248-249
             if out is None:
                 out = torch.empty((len(sentences), emb.shape[1]), dtype=torch.float32, device=self.device)
             elif out.shape[1] != emb.shape[1]:

@@ -76,6 +76,16 @@ class AsymHeads:
         return emb
 
 
+def normalize_rows_(emb: torch.Tensor) -> torch.Tensor:
+    """In-place L2 normalisation of fp32 [B, d] rows on the device (models/Normalize.py) with the library's kernel."""
+    if emb.dtype != torch.float32 or not emb.is_cuda or not emb.is_contiguous():
+        raise ValueError("normalize_rows_ expects a contiguous fp32 CUDA tensor")
+    with torch.cuda.device(emb.device):
+        _lib.check(_lib.lib().sgpt_normalize_rows(emb.data_ptr(), emb.shape[0], emb.shape[1], _lib.current_stream()),
+                   "sgpt_normalize_rows")
+    return emb
+
+
 def apply_heads(emb: torch.Tensor, heads: Optional[List[DenseHead]]) -> torch.Tensor:
     for h in heads or ():
         emb = h(emb)

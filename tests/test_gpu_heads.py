@@ -54,7 +54,8 @@ def test_pool_ex_learnt_position_weights_bit_level(ref):
     pw = torch.from_numpy(ref["position_weights"]).cuda()
     out = torch.empty((B, d), dtype=torch.float32, device="cuda")
     ws = torch.empty(2 * T + B, dtype=torch.float32, device="cuda")
-    rc = _lib.lib().sgpt_pool_ex(x.data_ptr(), torch.from_numpy(pos).cuda().data_ptr(), torch.from_numpy(cu).cuda().data_ptr(),
+    pos_d, cu_d = torch.from_numpy(pos).cuda(), torch.from_numpy(cu).cuda()  # keep alive: raw pointers below
+    rc = _lib.lib().sgpt_pool_ex(x.data_ptr(), pos_d.data_ptr(), cu_d.data_ptr(),
                                  None, None, 1e-5, pw.data_ptr(), pw.numel(), out.data_ptr(), ws.data_ptr(), B, T, d,
                                  _lib.POOL_WEIGHTEDMEAN, 1, 0, 0, 1.0, _lib.current_stream())
     _lib.check(rc, "sgpt_pool_ex")
