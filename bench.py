@@ -12,6 +12,7 @@ all-gather of the per-shard top-1001 and a merge).  Prints ONE JSON line (rank 0
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -364,27 +365,63 @@ def run_b200(args, rank, world, local_rank):
     i_host = [torch.empty((NQ, kk), dtype=torch.int64).pin_memory() for _ in range(2)]
     slot_evt = [torch.cuda.Event() for _ in range(2)]
 
+    trace = os.environ.get("SGPT_BENCH_E2E_TRACE") == "1"  # per-step host/GPU timestamps of the e2e loop to stderr
+
     def e2e_pass(with_search, steps):
         nonlocal_h2d = nonlocal_d2h = 0
+        tr_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)] if trace else None
+        tr_host, tr_calls = [], []
+        gc_was_on = gc.isenabled()
+        if os.environ.get("SGPT_BENCH_GC", "off") == "off":
+            gc.collect()
+            gc.disable()  # keep the collector's pauses out of the timed loop
         barrier()
         t0 = time.perf_counter()
         for k in range(steps):
             slot = k % 2
             slot_evt[slot].synchronize()  # the consumer of this slot's previous results is done with them
+            if trace:
+                tr_host.append(time.perf_counter() - t0)
+                tr_ev[k][0].record()
             emb = enc.encode_tokens(batches[k % 4].numpy(), mask)
+            if trace:
+                tr_ev[k][1].record()
             nonlocal_h2d += enc.h2d_bytes_last
             emb_host[slot].copy_(emb, non_blocking=True)
             nonlocal_d2h += emb_host[slot].numel() * 4
             if with_search:
+                h0 = time.perf_counter()
                 qd = q_host.to(dev, non_blocking=True)
+                h1 = time.perf_counter()
                 nonlocal_h2d += q_host.numel() * 4
                 s, i = search_step(qd)
+                h2 = time.perf_counter()
                 s_host[slot].copy_(s, non_blocking=True)
                 i_host[slot].copy_(i, non_blocking=True)
+                h3 = time.perf_counter()
+                if trace:
+                    tr_calls.append((h1 - h0, h2 - h1, h3 - h2))
                 nonlocal_d2h += s_host[slot].numel() * 4 + i_host[slot].numel() * 8
+            if trace:
+                tr_ev[k][2].record()
             slot_evt[slot].record()
         barrier()
-        return time.perf_counter() - t0, nonlocal_h2d, nonlocal_d2h
+        t_total = time.perf_counter() - t0
+        if gc_was_on:
+            gc.enable()
+        if trace:
+            print(f"[e2e trace] with_search={with_search} steps={steps} total {1e3 * t_total:.2f} ms", file=sys.stderr)
+            if tr_calls:
+                worst = [max(range(len(tr_calls)), key=lambda j: tr_calls[j][c]) for c in range(3)]
+                print("[e2e trace] slowest host call (ms, step): q.to(dev) %.2f @%d | shard.search %.2f @%d | D2H copy_ x2 "
+                      "%.2f @%d" % (1e3 * tr_calls[worst[0]][0], worst[0], 1e3 * tr_calls[worst[1]][1], worst[1],
+                                    1e3 * tr_calls[worst[2]][2], worst[2]), file=sys.stderr)
+            for k in range(steps):
+                gap = tr_ev[k - 1][2].elapsed_time(tr_ev[k][0]) if k else 0.0
+                print(f"[e2e trace] step {k:2d} host_start {1e3 * tr_host[k]:8.2f} ms | gpu encode "
+                      f"{tr_ev[k][0].elapsed_time(tr_ev[k][1]):6.2f} rest {tr_ev[k][1].elapsed_time(tr_ev[k][2]):6.2f} "
+                      f"gap_before {gap:6.2f}", file=sys.stderr)
+        return t_total, nonlocal_h2d, nonlocal_d2h
 
     # W untimed warm-up steps of exactly this loop first: the warm-up at the top never runs the host->device query copy
     # or the copies into the pinned result buffers.  (Without it the search leg measured 2.7 ms per step here against

@@ -168,3 +168,36 @@ def test_pickle_embedding_cache_logic(tmp_path, monkeypatch):
     assert calls == []
     assert emb.encode_corpus(corpus[:1], batch_size=4, batch_num=4).tolist() == [[4.0, 0.0]]  # other chunk: recomputed
     assert len(calls) == 1 and not os.path.exists("embeddings/model/weightedmean/toy_corpus4.pickle")
+
+
+def test_gpt_ranker_prompting_and_rerank_with_stub_scorer():
+    """Host logic of the cross-encoder surface (sgptce.py:76-90, 265-330; beir Rerank): prompt formatting, instruction
+    length, (continuation, context) order, top_k cut — with the device scorer stubbed out."""
+    from sgpt_b200.cross_encoder import GPTRanker, Rerank, encode
+    from tests.helpers import ToyTokenizer
+
+    tok = ToyTokenizer(vocab=300)
+    tok.eos_token_id = 298
+    reqs = encode([("my query", "some doc text"), ("q2", "")], tok)
+    assert reqs[0][0] == ("some doc text", "my query") and len(reqs[0][1]) == 3 and len(reqs[0][2]) == 2
+    assert reqs[1][1] == [298]  # empty context -> eos (sgptce.py:80-82)
+
+    class StubScorer:
+        class cfg:
+            max_pos = 64
+
+        def loglikelihood_tokens(self, requests, max_length, batch_size=64, instruction_len=0):
+            self.seen = (requests, max_length, instruction_len)
+            return [-float(len(ctx)) for _, ctx, _ in requests]
+
+    stub = StubScorer()
+    ranker = GPTRanker(stub, tok, prompt_doc='Doc "{}" matches "', fewshots=("fdoc", "fquery"), prompt_doc_start="{} -> {}\n")
+    assert ranker.max_length == 64
+    assert ranker.instruction_len == len(tok.tokenize('Doc "')) + len(tok.tokenize("fdoc -> fquery\n"))
+    scores = ranker.predict([("query one", "short"), ("query one", "a much longer document")], batch_size=2)
+    assert scores[0] > scores[1]
+    (ctx_text, cont_text), _, cont = stub.seen[0][0]
+    assert ctx_text == 'fdoc -> fquery\nDoc "short" matches "' and cont_text == "query one" and len(cont) == 2
+    corpus = {"a": {"title": "T", "text": "x"}, "b": {"text": "y y y"}, "c": {"title": "", "text": "z z"}}
+    res = Rerank(ranker).rerank(corpus, {"q": "query"}, {"q": {"a": 0.1, "b": 0.9, "c": 0.5}}, top_k=2)
+    assert sorted(res["q"]) == ["b", "c"]  # only the two best first-stage hits are re-scored

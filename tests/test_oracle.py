@@ -202,3 +202,27 @@ def test_script_pooling_modes_match_executed_reference_block(golden_dir, name):
     }
     for mode, val in got.items():
         np.testing.assert_allclose(val.numpy(), ref["pooled_" + mode], rtol=1e-5, atol=1e-6, err_msg=mode)
+
+
+def _ce_requests(z):
+    co, qo = z["ctx_off"], z["cont_off"]
+    return [(i, z["ctx_flat"][co[i]:co[i + 1]].tolist(), z["cont_flat"][qo[i]:qo[i + 1]].tolist())
+            for i in range(len(co) - 1)]
+
+
+def test_lm_score_oracle_matches_executed_reference_functions(golden_dir):
+    """oracle.lm_score vs the output of the reference's own _loglikelihood_tokens (crossencoder/beir/sgptce.py:150-262,
+    executed by tests/golden/make_ce.py on HF GPTNeoForCausalLM with the st_tiny weights): left truncation after the
+    instruction, the duplicate request, a 1-token context and a 1-token continuation are all in the fixture."""
+    from oracle import lm_score
+    from sgpt_b200.st_loader import load_torch_weights
+
+    z = np.load(os.path.join(golden_dir, "ce_tiny.npz"))
+    w = load_torch_weights(os.path.join(golden_dir, "st_tiny"))
+    spec = gpt_neo.NeoSpec(n_layer=2, d_model=128, n_head=2, d_ff=256, vocab=300, max_pos=64, window=8)
+    reqs = _ce_requests(z)
+    assert any(len(c) + len(q) > int(z["max_length"]) + 1 for _, c, q in reqs)  # truncation is exercised
+    got = lm_score.loglikelihood(spec, w, reqs, int(z["max_length"]), int(z["instruction_len"]))
+    np.testing.assert_allclose(got, z["loglik"], atol=2e-4)
+    assert got[0] == got[-1]  # the duplicated request
+    assert lm_score.model_input([1, 2, 3, 4, 5, 6], [7, 8], max_length=4, instruction_len=2) == [1, 2, 6, 7]
