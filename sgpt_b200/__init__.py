@@ -14,7 +14,7 @@ from .config import ModelConfig, preset  # noqa: F401
 
 __all__ = ["ModelConfig", "preset", "Encoder", "CustomEmbedder", "SentenceEncoder", "SentenceBERTBOSEOS",
            "SentenceBERTAsym", "DenseRetrievalExactSearch", "CorpusShard", "merge_topk", "semantic_search",
-           "sharded_search", "DenseHead", "AsymHeads", "load_st_directory", "GenericDataLoader", "EvaluateRetrieval"]
+           "sharded_search", "ShardedDenseRetrievalExactSearch", "DenseHead", "AsymHeads", "load_st_directory", "GenericDataLoader", "EvaluateRetrieval"]
 
 
 def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
@@ -39,7 +39,7 @@ def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
     if name in ("CorpusShard", "merge_topk", "semantic_search"):
         from . import index
         return getattr(index, name)
-    if name == "sharded_search":
-        from .dist import sharded_search
-        return sharded_search
+    if name in ("sharded_search", "ShardedDenseRetrievalExactSearch"):
+        from . import dist
+        return getattr(dist, name)
     raise AttributeError(name)

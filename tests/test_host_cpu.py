@@ -168,3 +168,128 @@ def test_sharded_search_two_ranks_gloo():
     [p.join(60) for p in procs]
     for rank, same_ids, err in res:
         assert same_ids and err < 1e-6, (rank, same_ids, err)
+
+
+def _toy_embed(text, dim=16):
+    """Deterministic text -> vector (stands in for the GPU encoder in the CPU tests)."""
+    import zlib
+
+    g = torch.Generator().manual_seed(zlib.crc32(text.encode()))
+    return torch.randn(dim, generator=g)
+
+
+class _StubEmbedder:
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.corpus_calls = []
+
+    def encode_queries(self, queries, batch_size, **kw):
+        return torch.stack([_toy_embed(t) for _, t in queries])
+
+    def encode_corpus(self, corpus, batch_size, batch_num="", **kw):
+        self.corpus_calls.append((batch_num, [cid for cid, _ in corpus]))
+        return torch.stack([_toy_embed((d["title"] + " " + d["text"]).strip()) for _, d in corpus])
+
+
+def _toy_corpus(n=57):
+    corpus = {f"d{i}": {"title": f"t{i}", "text": "w " * (1 + (i * 7) % 23)} for i in range(n)}
+    queries = {"q0": "t3 " + "w " * 22, "d5": "some query", "q2": "another"}
+    queries["q0"] = (corpus["d3"]["title"] + " " + corpus["d3"]["text"]).strip()  # exact duplicate of d3 -> top hit
+    return corpus, queries
+
+
+class _CpuShard:  # CorpusShard contract on CPU tensors with the oracle's arithmetic
+    def __init__(self, dim, capacity):
+        self.rows = []
+
+    def add(self, emb):
+        self.rows.append(emb.float())
+
+    def search(self, qe, k, score_function):
+        from oracle import search as osearch
+
+        c = torch.cat(self.rows) if self.rows else torch.zeros(0, qe.shape[1])
+        sc = osearch.SCORE_FUNCTIONS[score_function](qe, c) if len(c) else torch.zeros(len(qe), 0)
+        s, i = osearch.topk_ids(sc, min(k, sc.shape[1])) if sc.shape[1] else (sc, sc.long())
+        pad = k - s.shape[1]
+        s = torch.cat([s, torch.full((len(s), pad), float("-inf"))], 1)
+        i = torch.cat([i, torch.full((len(i), pad), -1, dtype=torch.int64)], 1)
+        return s.contiguous(), i.contiguous()
+
+
+def _cpu_merge(gs, gi, exclude):
+    G, Q, kk = gs.shape
+    s = gs.permute(1, 0, 2).reshape(Q, G * kk).clone()
+    i = gi.permute(1, 0, 2).reshape(Q, G * kk)
+    s[i < 0] = float("-inf")
+    if exclude is not None:
+        s[i == exclude[:, None]] = float("-inf")
+    order = torch.argsort(-s, dim=1, stable=True)[:, :kk]
+    s, i = torch.gather(s, 1, order), torch.gather(i, 1, order)
+    return s, torch.where(torch.isinf(s), torch.full_like(i, -1), i)
+
+
+def _expected_results(corpus, queries, top_k):
+    """The reference algorithm on one process: oracle.search.search_embeddings over the length-sorted corpus."""
+    out = {}
+    cids = list(corpus)
+    cemb = torch.stack([_toy_embed((corpus[c]["title"] + " " + corpus[c]["text"]).strip()) for c in cids])
+    for qid, text in queries.items():
+        sc = torch.nn.functional.cosine_similarity(_toy_embed(text)[None], cemb)
+        ranked = [(float(s), c) for s, c in sorted(zip(sc.tolist(), cids), reverse=True) if c != qid][:top_k + 1]
+        out[qid] = {c: s for s, c in ranked}
+    return out
+
+
+def _sharded_dres_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        from sgpt_b200.dist import ShardedDenseRetrievalExactSearch
+
+        corpus, queries = _toy_corpus()
+        emb = _StubEmbedder()
+        dres = ShardedDenseRetrievalExactSearch(emb, batch_size=8, corpus_chunk_size=10, shard_factory=_CpuShard,
+                                                merge=_cpu_merge)
+        res = dres.search(corpus, queries, top_k=5, score_function="cos_sim")
+        q.put((rank, res, emb.corpus_calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_dres_two_ranks_gloo_matches_single_process():
+    """End-to-end multi-rank DRES on CPU (gloo, 2 ranks, stub embedder): the corpus is dealt i mod G over the ranks after
+    the length sort, each rank encodes only its share, and both ranks return the single-process result."""
+    import torch.multiprocessing as mp
+
+    corpus, queries = _toy_corpus()
+    want = _expected_results(corpus, queries, 5)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sharded_dres_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    seen = []
+    for rank, got, calls in res:
+        assert set(got) == set(want)
+        for qid in want:
+            assert set(got[qid]) == set(want[qid]), (rank, qid)
+            assert "d5" not in got["d5"]  # self match dropped (XS:118)
+            for cid, s in want[qid].items():
+                assert abs(got[qid][cid] - s) < 1e-5
+        assert max(got["q0"], key=got["q0"].get) == "d3"
+        assert all(len(ids) <= 10 for _, ids in calls) and [b for b, _ in calls] == [f"{rank}_{i}" for i in range(len(calls))]
+        seen.append([c for _, ids in calls for c in ids])
+    assert abs(len(seen[0]) - len(seen[1])) <= 1 and sorted(seen[0] + seen[1]) == sorted(corpus)  # disjoint cover
+    # single process (no process group): same class, same answer
+    from sgpt_b200.dist import ShardedDenseRetrievalExactSearch
+
+    solo = ShardedDenseRetrievalExactSearch(_StubEmbedder(), corpus_chunk_size=10, shard_factory=_CpuShard,
+                                            merge=_cpu_merge).search(corpus, queries, 5, "cos_sim")
+    assert {k: set(v) for k, v in solo.items()} == {k: set(v) for k, v in want.items()}
