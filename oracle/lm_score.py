@@ -22,19 +22,25 @@ def model_input(context_enc: Sequence[int], continuation_enc: Sequence[int], max
 
 
 def loglikelihood(spec, weights, requests: Sequence[Tuple[object, Sequence[int], Sequence[int]]], max_length: int,
-                  instruction_len: int = 0) -> List[float]:
-    """One float per request (cache_key, context_enc, continuation_enc): sum of log p(cont_i | prefix)."""
-    from . import gpt_neo
+                  instruction_len: int = 0, arch: str = "gpt_neo", lm_head=None, lm_bias=None) -> List[float]:
+    """One float per request (cache_key, context_enc, continuation_enc): sum of log p(cont_i | prefix).
+    arch "gpt_neo" (LM head tied to wte, HF GPTNeoForCausalLM) or "gptj" (untied ``lm_head`` weight [vocab, d] + bias,
+    HF GPTJForCausalLM)."""
+    from . import gpt_neo, gptj
 
-    wte = weights["wte.weight"].float()
+    fwd = {"gpt_neo": gpt_neo.forward, "gptj": gptj.forward}[arch]
+    wte = (weights["wte.weight"] if lm_head is None else lm_head).float()
     out = []
     for _, ctx, cont in requests:
         inp = model_input(ctx, cont, max_length, instruction_len)
         ids = torch.tensor([inp], dtype=torch.long)
         mask = torch.ones_like(ids)
         with torch.no_grad():
-            hidden = gpt_neo.forward(spec, weights, ids, mask)[-1][0]            # [S, d], after ln_f
-            logp = torch.log_softmax(hidden.float() @ wte.t(), dim=-1)          # :221
+            hidden = fwd(spec, weights, ids, mask)[-1][0]                       # [S, d], after ln_f
+            logits = hidden.float() @ wte.t()
+            if lm_bias is not None:
+                logits = logits + lm_bias.float()
+            logp = torch.log_softmax(logits, dim=-1)                            # :221
         rows = logp[len(inp) - len(cont):len(inp)]                              # :226
         out.append(float(rows.gather(1, torch.tensor(list(cont)).unsqueeze(1)).sum()))  # :247-250
     return out

@@ -226,3 +226,24 @@ def test_lm_score_oracle_matches_executed_reference_functions(golden_dir):
     np.testing.assert_allclose(got, z["loglik"], atol=2e-4)
     assert got[0] == got[-1]  # the duplicated request
     assert lm_score.model_input([1, 2, 3, 4, 5, 6], [7, 8], max_length=4, instruction_len=2) == [1, 2, 6, 7]
+
+
+def _gptj_head(vocab, d, seed):
+    g = torch.Generator().manual_seed(seed)  # same construction as tests/golden/make_ce.py:gptj_lm_head
+    w = (torch.randn(vocab, d, generator=g) * 0.05).to(torch.bfloat16).float()
+    return w, (torch.randn(vocab, generator=g) * 0.5).float()
+
+
+def test_lm_score_oracle_gptj_untied_head_with_bias(golden_dir):
+    """Same for HF GPTJForCausalLM (rotary, parallel residual, untied LM head + bias: the SGPT-CE 6.1B architecture)."""
+    from oracle import gptj as ogptj
+    from oracle import lm_score
+
+    z = np.load(os.path.join(golden_dir, "ce_gptj_tiny.npz"))
+    L, d, H, ff, vocab, max_pos, rd = [int(x) for x in z["spec"]]
+    spec = ogptj.GPTJSpec(n_layer=L, d_model=d, n_head=H, d_ff=ff, vocab=vocab, max_pos=max_pos, rotary_dim=rd)
+    w = ogptj.init_weights(spec, int(z["weight_seed"]))
+    hw, hb = _gptj_head(vocab, d, int(z["head_seed"]))
+    got = lm_score.loglikelihood(spec, w, _ce_requests(z), int(z["max_length"]), int(z["instruction_len"]), arch="gptj",
+                                 lm_head=hw, lm_bias=hb)
+    np.testing.assert_allclose(got, z["loglik"], atol=5e-4)
