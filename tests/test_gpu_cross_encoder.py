@@ -132,29 +132,3 @@ def test_gpt_ranker_and_rerank_vs_oracle(scorer):
         for d, wv, (_, _, cont) in zip(docs, want, reqs):
             assert abs(res[qid][d] - wv) < TOL_PER_TOKEN * len(cont), (qid, d, res[qid][d], wv)
     assert ranker.predict([("q", "")], batch_size=1)[0] < 0  # empty document text still has the prompt as context
-
-
-def test_gptj_untied_lm_head_with_bias_vs_executed_reference():
-    """GPT-J scorer (rotary QKV epilogue, parallel residual, hd 128, untied lm_head + bias — the SGPT-CE 6.1B
-    architecture) vs the reference functions executed on HF GPTJForCausalLM (tests/golden/make_ce.py)."""
-    from oracle import gptj as ogptj
-    from sgpt_b200 import ModelConfig
-    from sgpt_b200.cross_encoder import LogLikelihoodScorer
-
-    z = np.load(os.path.join(GOLDEN, "ce_gptj_tiny.npz"))
-    L, d, H, ff, vocab, max_pos, rd = [int(x) for x in z["spec"]]
-    spec = ogptj.GPTJSpec(n_layer=L, d_model=d, n_head=H, d_ff=ff, vocab=vocab, max_pos=max_pos, rotary_dim=rd)
-    w = ogptj.init_weights(spec, int(z["weight_seed"]))
-    g = torch.Generator().manual_seed(int(z["head_seed"]))  # same construction as make_ce.py:gptj_lm_head
-    hw = (torch.randn(vocab, d, generator=g) * 0.05).to(torch.bfloat16).float()
-    hb = (torch.randn(vocab, generator=g) * 0.5).float()
-    sd = {"transformer." + k: v for k, v in w.items()}  # *ForCausalLM checkpoint naming
-    sd["lm_head.weight"], sd["lm_head.bias"] = hw, hb
-    cfg = ModelConfig(arch="gptj", n_layer=L, d_model=d, n_head=H, d_ff=ff, vocab=vocab, max_pos=max_pos, rotary_dim=rd)
-    s = LogLikelihoodScorer(cfg, sd, max_tokens=1024, max_batch=8, rows_per_chunk=16)
-    assert s.lm_bias is not None and s.vocab == vocab
-    reqs = _requests(z)
-    got = s.loglikelihood_tokens(reqs, int(z["max_length"]), batch_size=4, instruction_len=int(z["instruction_len"]))
-    for gv, wv, (_, _, cont) in zip(got, z["loglik"], reqs):
-        assert abs(gv - wv) < TOL_PER_TOKEN * len(cont), (gv, wv, len(cont))
-    s.close()
