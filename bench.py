@@ -424,8 +424,8 @@ def run_b200(args, rank, world, local_rank):
         return t_total, nonlocal_h2d, nonlocal_d2h
 
     # W untimed warm-up steps of exactly this loop first: the warm-up at the top never runs the host->device query copy
-    # or the copies into the pinned result buffers.  (Without it the search leg measured 2.7 ms per step here against
-    # 0.52 ms in the stand-alone probe of the same calls, profiles/r01_e2e_search_probe.log.)
+    # or the copies into the pinned result buffers.  (one host stall of 18-87 ms per pass, always inside
+    # the 10th step's CorpusShard.search call, used to dominate the short timed region of the search leg.)
     e2e_pass(True, max(args.warmup, 3))
     e2e_s, h2d, d2h = e2e_pass(True, args.steps)
     # separate e2e encode-only timing for the headline emb/s
