@@ -168,6 +168,17 @@ def usable_cores():
     return max(1, n)
 
 
+def cpu_model_name():
+    """CPU model string of the box the CPU baseline ran on (SURVEY.md §8d asks for it next to the core count)."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_times(weights, enc_batch=32, n_enc=2, search_docs=100_000, warm=True):
     """Bounded sample of the reference CPU path: encode `n_enc` batches of `enc_batch` x 128 tokens, and cos_sim +
     topk(1001) of 128 queries over `search_docs` docs in 50k chunks with the heapq merge (XS:80-132)."""
@@ -228,7 +239,7 @@ def run_reference(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": workload_config(args.gpus), "search": {"value": qps, "unit": "queries/s"},
-            "cpu_baseline": {"value": emb_s, "unit": "embeddings/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": emb_s, "unit": "embeddings/s", "cores": cores, "cpu_model": cpu_model_name(), "kind": "port",
                              "sample": vals[-1]["sample"] + " per step", "how": vals[-1]["how"], "search_qps_1m": qps},
             "e2e": {"value": emb_s, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -507,6 +518,7 @@ def run_b200(args, rank, world, local_rank):
         eb, docs = calibrate_reference(weights, enc_seconds=5.0, search_seconds=2.0)
         r = cpu_reference_times(weights, enc_batch=eb, n_enc=2, search_docs=docs, warm=False)
         line["cpu_baseline"] = {"value": r["emb_s"], "unit": "embeddings/s", "cores": usable_cores(),
+                                "cpu_model": cpu_model_name(),
                                 "kind": "port", "sample": r["sample"], "how": r["how"], "search_qps_1m": r["qps_1m"]}
     print(json.dumps(line), flush=True)
     enc.close()
