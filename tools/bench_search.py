@@ -18,7 +18,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sgpt_b200 import CorpusShard  # noqa: E402
 
 SHAPES = [("config 1/2: 1M x 768", 1_000_000, 768), ("config 3: 1M x 2048", 1_000_000, 2048),
-          ("config 4 per GPU (1M/8): 125k x 4096", 125_000, 4096), ("config 5 per GPU (10M/8): 1.25M x 4096", 1_250_000, 4096)]
+          ("config 4 per GPU (1M/8): 125k x 4096", 125_000, 4096), ("config 5 per GPU (10M/8): 1.25M x 4096", 1_250_000, 4096),
+          ("north-star scaling anchor: 10M x 768 on one GPU", 10_000_000, 768)]
 
 
 def main():
@@ -35,8 +36,8 @@ def main():
     for label, n, D in SHAPES:
         g = torch.Generator(device=dev).manual_seed(7)
         shard = CorpusShard(D, n, device=dev)
-        for s0 in range(0, n, 50_000):
-            shard.add(torch.randn(min(50_000, n - s0), D, generator=g, device=dev))
+        for s0 in range(0, n, 250_000):
+            shard.add(torch.randn(min(250_000, n - s0), D, generator=g, device=dev))
         for nq in [int(x) for x in args.queries.split(",")]:
             q = torch.randn(nq, D, generator=g, device=dev)
             for _ in range(3):
