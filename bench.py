@@ -316,6 +316,13 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def maxr_early(x):  # max over ranks (device-timed numbers are reported as the slowest rank's)
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     # ---- warm-up -----------------------------------------------------------------------------------------------
     # nvidia-smi needs ~0.5 s to produce its first sample: start it before the warm-up; samples cover warm-up + both
     # timed loops (all of them run the same kernels back to back)
@@ -441,6 +448,44 @@ def run_b200(args, rank, world, local_rank):
     e2e_s, h2d, d2h = e2e_pass(True, args.steps)
     # separate e2e encode-only timing for the headline emb/s
     e2e_enc_s, _, _ = e2e_pass(False, args.steps)
+    # ---- optional: strong scaling of the exact search over ONE 10 M-doc corpus split across the ranks -------------------
+    # (north_star: "linear top-k scaling to 8 GPUs on a 10M-doc synthetic corpus"; the main line above is weak scaling
+    # at 1 M docs per GPU.)  Off by default until the 10 M-row shard has been validated on the GPU; runs after every
+    # other measurement so that a failure here cannot cost the main numbers.
+    big = None
+    if args.corpus_10m:
+        try:
+            from sgpt_b200.dist import shard_range
+
+            total = 10_000_000
+            lo, hi = shard_range(total, rank, world)
+            big_shard = CorpusShard(D, hi - lo, device=dev, id_base=lo)
+            for s0 in range(0, hi - lo, 250_000):
+                big_shard.add(torch.randn(min(250_000, hi - lo - s0), D, generator=g, device=dev))
+
+            def big_step():
+                s_, i_ = big_shard.search(queries, kk, "cos_sim")
+                if world > 1:
+                    gs_, gi_ = all_gather_topk(s_, i_)
+                    s_, i_ = merge_topk(gs_, gi_)
+                return s_, i_
+
+            for _ in range(3):
+                big_step()
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(args.steps):
+                big_step()
+            b1.record()
+            barrier()
+            big_ms = maxr_early(b0.elapsed_time(b1) / args.steps)
+            big = {"corpus_docs": total, "docs_per_gpu": hi - lo, "dim": D, "queries": NQ, "top_k": TOPK,
+                   "ms_per_search": big_ms, "queries_per_s": NQ / (big_ms / 1e3), "scaling": "strong",
+                   "frac_of_hbm_roofline": ((hi - lo) * (D * 2 + 4) / (big_ms / 1e3) / 1e9) / peaks()["hbm"]}
+            del big_shard
+        except Exception as e:  # noqa: BLE001 - reported, never fatal for the main line
+            big = {"error": repr(e)[:300]}
     clocks = sampler.stop() if sampler else None
 
     def maxr(x):
@@ -512,6 +557,8 @@ def run_b200(args, rank, world, local_rank):
                 "CorpusShard.search and device->host top-k"},
         "clocks": clocks, "wall_s_timed_loop": t_wall,
     }
+    if big is not None:
+        line["search_10m_strong_scaling"] = big
     e2e_search_ms = 1000 * e2e_s / K - 1000 * e2e_enc_s / K
     line["e2e"]["search_queries_per_s"] = NQ / (e2e_search_ms / 1e3) if e2e_search_ms > 0 else None
     if world == 1 and not args.no_cpu_baseline:
@@ -531,6 +578,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--corpus-10m", action="store_true",
+                    help="also time the exact search over one 10M x 768 corpus split across the ranks (strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
