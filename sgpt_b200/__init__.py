@@ -14,7 +14,8 @@ from .config import ModelConfig, preset  # noqa: F401
 
 __all__ = ["ModelConfig", "preset", "Encoder", "CustomEmbedder", "SentenceEncoder", "SentenceBERTBOSEOS",
            "SentenceBERTAsym", "DenseRetrievalExactSearch", "CorpusShard", "merge_topk", "semantic_search",
-           "sharded_search", "ShardedDenseRetrievalExactSearch", "DenseHead", "AsymHeads", "load_st_directory", "GenericDataLoader", "EvaluateRetrieval"]
+           "sharded_search", "ShardedDenseRetrievalExactSearch", "DenseHead", "AsymHeads", "load_st_directory", "GenericDataLoader", "EvaluateRetrieval",
+           "InformationRetrievalEvaluator"]
 
 
 def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
@@ -27,6 +28,9 @@ def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
     if name == "load_st_directory":
         from .st_loader import load_st_directory
         return load_st_directory
+    if name == "InformationRetrievalEvaluator":
+        from .evaluation import InformationRetrievalEvaluator
+        return InformationRetrievalEvaluator
     if name in ("GenericDataLoader", "EvaluateRetrieval"):
         from . import beir_compat
         return getattr(beir_compat, name)

@@ -201,3 +201,43 @@ def test_gpt_ranker_prompting_and_rerank_with_stub_scorer():
     corpus = {"a": {"title": "T", "text": "x"}, "b": {"text": "y y y"}, "c": {"title": "", "text": "z z"}}
     res = Rerank(ranker).rerank(corpus, {"q": "query"}, {"q": {"a": 0.1, "b": 0.9, "c": 0.5}}, top_k=2)
     assert sorted(res["q"]) == ["b", "c"]  # only the two best first-stage hits are re-scored
+
+
+def test_information_retrieval_evaluator_metrics_match_executed_reference(tmp_path):
+    """compute_metrics vs the reference's own method (executed from its syntax tree by tests/golden/make_ir_eval.py) on the
+    same seeded result lists; then the whole __call__ flow (encode -> search -> metrics -> CSV) with a stub model and an
+    injected CPU search."""
+    from oracle import search as osearch
+    from sgpt_b200.evaluation import InformationRetrievalEvaluator
+
+    with open(os.path.join(GOLDEN, "ir_eval.json")) as f:
+        z = json.load(f)
+    relevant = {k: set(v) for k, v in z["relevant"].items()}
+    ev = InformationRetrievalEvaluator(z["queries"], z["corpus"], relevant, mrr_at_k=[5, 10], ndcg_at_k=[3, 10],
+                                       accuracy_at_k=[1, 3], precision_recall_at_k=[1, 5], map_at_k=[10, 100])
+    assert ev.csv_headers == z["csv_headers"] and ev.csv_file == z["csv_file"]
+    assert "q10" not in ev.queries_ids and "q11" not in ev.queries_ids  # no relevant docs / not judged (:42-45)
+    got = ev.compute_metrics(z["results"])
+    for metric, by_k in z["scores"].items():
+        for k, v in by_k.items():
+            assert abs(got[metric][int(k)] - v) < 1e-12, (metric, k)
+
+    class StubModel:
+        def encode(self, sentences, batch_size=32, convert_to_tensor=True, **kw):
+            return torch.stack([torch.nn.functional.one_hot(torch.tensor(int(s.split()[-1]) % 7), 8).float() +
+                                0.01 * int(s.split()[-1]) for s in sentences])
+
+    def cpu_search(q, c, k, fn):
+        sc = osearch.SCORE_FUNCTIONS[fn](q, c)
+        return osearch.topk_ids(sc, k)
+
+    ev2 = InformationRetrievalEvaluator(z["queries"], z["corpus"], relevant, name="toy", search_fn=cpu_search,
+                                        main_score_function="cos_sim")
+    main = ev2(StubModel(), output_path=str(tmp_path), epoch=1, steps=2)
+    lines = open(tmp_path / "Information-Retrieval_evaluation_toy_results.csv").read().strip().splitlines()
+    assert lines[0].split(",")[:3] == ["epoch", "steps", "cos_sim-Accuracy@1"] and lines[1].startswith("1,2,")
+    assert len(lines[1].split(",")) == len(lines[0].split(",")) and 0.0 <= main <= 1.0
+    ev2(StubModel(), output_path=str(tmp_path))
+    assert len(open(tmp_path / "Information-Retrieval_evaluation_toy_results.csv").read().strip().splitlines()) == 3
+    with pytest.raises(ValueError):
+        InformationRetrievalEvaluator(z["queries"], z["corpus"], relevant, score_functions=["euclid"])
