@@ -81,3 +81,37 @@ def test_sharded_dres_world1_equals_chunked_dres():
         assert "d5" not in res1["d5"]
         assert sorted(res1[qid], key=res1[qid].get, reverse=True) == sorted(res[qid], key=res[qid].get, reverse=True), qid
         assert max(abs(res1[qid][c] - res[qid][c]) for c in res[qid]) < 2e-5
+
+
+def test_information_retrieval_evaluator_on_corpus_shard():
+    """InformationRetrievalEvaluator with its default search (CorpusShard on the GPU) == the same evaluator with the
+    oracle's CPU search on the same bf16-rounded embeddings."""
+    import json
+
+    from oracle import search as osearch
+    from sgpt_b200 import InformationRetrievalEvaluator
+
+    with open(os.path.join(GOLDEN, "ir_eval.json")) as f:
+        z = json.load(f)
+    relevant = {k: set(v) for k, v in z["relevant"].items()}
+    g = torch.Generator().manual_seed(2)
+    table = torch.randn(100, 64, generator=g).to(torch.bfloat16).float()  # bf16-exact so both paths see the same vectors
+
+    class StubModel:
+        def __init__(self, dev):
+            self.dev = dev
+
+        def encode(self, sentences, batch_size=32, convert_to_tensor=True, **kw):
+            return torch.stack([table[int(s.split()[-1])] for s in sentences]).to(self.dev)
+
+    def cpu_search(q, c, k, fn):
+        return osearch.topk_ids(osearch.SCORE_FUNCTIONS[fn](q.cpu(), c.cpu()), k)
+
+    kw = dict(mrr_at_k=[10], ndcg_at_k=[10], accuracy_at_k=[1, 5], precision_recall_at_k=[3], map_at_k=[20])
+    got = InformationRetrievalEvaluator(z["queries"], z["corpus"], relevant, **kw).compute_metrices(StubModel("cuda"))
+    want = InformationRetrievalEvaluator(z["queries"], z["corpus"], relevant, search_fn=cpu_search, **kw).compute_metrices(
+        StubModel("cpu"))
+    for name in ("cos_sim", "dot_score"):
+        for metric in want[name]:
+            for k, v in want[name][metric].items():
+                assert abs(got[name][metric][k] - v) < 1e-9, (name, metric, k)
