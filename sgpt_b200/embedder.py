@@ -109,9 +109,13 @@ class CustomEmbedder:
         optional specb brackets with mask 1, right-pad."""
         seqs = []
         docs_truncated = toks_truncated = total = 0
-        for txt in batch:
-            txt = txt.replace("\n", " ")  # BDR:166
-            tokens = self.tokenizer.convert_tokens_to_ids(self.tokenizer.tokenize(txt))  # BDR:169-170
+        batch = [txt.replace("\n", " ") for txt in batch]  # BDR:166
+        if getattr(self.tokenizer, "is_fast", False) and callable(self.tokenizer):
+            # a fast tokenizer encodes the whole batch in one native call; same ids as tokenize + convert_tokens_to_ids
+            all_tokens = self.tokenizer(list(batch), add_special_tokens=False)["input_ids"]
+        else:
+            all_tokens = [self.tokenizer.convert_tokens_to_ids(self.tokenizer.tokenize(txt)) for txt in batch]  # BDR:169-170
+        for tokens in all_tokens:
             n = len(tokens)
             total += n
             if n > self.max_token_len:
@@ -324,9 +328,15 @@ class SentenceEncoder:
             texts = [s.lower() for s in texts]  # :116-118
         spec = None not in (self.bos_spec_token_q, self.eos_spec_token_q, self.bos_spec_token_d, self.eos_spec_token_d)
         limit = self.max_seq_length - 2 if spec else self.max_seq_length  # :135
+        if getattr(self.tokenizer, "is_fast", False) and callable(self.tokenizer):
+            # one batched call like the reference (Transformer.py:127 / :132-135) — a fast tokenizer encodes the whole
+            # batch in native code instead of one Python call per text
+            batch_ids = [list(x) for x in self.tokenizer(texts, padding=False, truncation="longest_first",
+                                                        max_length=limit)["input_ids"]]
+        else:
+            batch_ids = [list(self.tokenizer.encode(t))[:limit] for t in texts]
         seqs = []
-        for t in texts:
-            ids = list(self.tokenizer.encode(t))[:limit]
+        for t, ids in zip(texts, batch_ids):
             if spec:
                 if ids and ids[0] == self.bos_spec_token_d:
                     if self.replace_bos:

@@ -241,3 +241,83 @@ def test_information_retrieval_evaluator_metrics_match_executed_reference(tmp_pa
     assert len(open(tmp_path / "Information-Retrieval_evaluation_toy_results.csv").read().strip().splitlines()) == 3
     with pytest.raises(ValueError):
         InformationRetrievalEvaluator(z["queries"], z["corpus"], relevant, score_functions=["euclid"])
+
+
+def test_sentence_encoder_tokenize_fast_tokenizer_batch_path_equals_per_text_path():
+    """A HuggingFace *fast* tokenizer is called once per batch (like models/Transformer.py:127,132-135); the result must
+    equal the per-text path other tokenizers take, incl. truncation and the specb bracket rules."""
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+
+    from sgpt_b200.embedder import SentenceEncoder
+
+    vocab = {"[UNK]": 0, "[PAD]": 1, "[SOS]": 2, "{SOS}": 3, "[": 4, "]": 5, "{": 6, "}": 7}
+    for i, w in enumerate("a b c d e f g hello world this is test".split()):
+        vocab[w] = 8 + i
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.WhitespaceSplit()
+    fast = PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="[UNK]", pad_token="[PAD]")
+
+    class Slow:  # same vocabulary through the per-text interface
+        pad_token_id = 1
+
+        def encode(self, text, add_special_tokens=False):
+            return [vocab.get(w, 0) for w in text.split()]
+
+    def make(tokenizer, spec):
+        e = object.__new__(SentenceEncoder)
+        e.tokenizer, e.max_seq_length, e.do_lower_case, e.pad_id = tokenizer, 6, False, 1
+        e.bos_spec_token_q = e.bos_spec_token_d = e.eos_spec_token_q = e.eos_spec_token_d = None
+        e.bos_spec_token_q_rep = e.bos_spec_token_d_rep = None
+        e.replace_bos = False
+        if spec:
+            e.bos_spec_token_q, e.bos_spec_token_d, e.eos_spec_token_q, e.eos_spec_token_d = 2, 3, 5, 7
+            e.bos_spec_token_q_rep, e.bos_spec_token_d_rep, e.replace_bos = 4, 6, True
+        return e
+
+    plain = ["a b c", "  hello world this is a test a b c d  ", "zzz", {"QRY": "d e"}]
+    for spec, texts in ((False, plain), (True, ["[SOS] a b c d e f g", "{SOS} hello", "[SOS] x"])):
+        ids_f, mask_f = make(fast, spec).tokenize(texts)
+        ids_s, mask_s = make(Slow(), spec).tokenize(texts)
+        assert np.array_equal(ids_f, ids_s) and np.array_equal(mask_f, mask_s), (spec, ids_f, ids_s)
+    ids, mask = make(fast, True).tokenize(["[SOS] a b c d e f g"])
+    assert ids[0].tolist() == [4, 8, 9, 10, 5] and mask[0].tolist() == [1] * 5  # max_seq_length-2 tokens, '[' ... ']'
+    with pytest.raises(ValueError, match="BOS"):
+        make(fast, True).tokenize(["a b"])
+
+
+def test_custom_embedder_tokenize_batch_fast_tokenizer_equals_two_step_path():
+    """CustomEmbedder.tokenize_batch: a fast tokenizer's batched call gives the ids of tokenize + convert_tokens_to_ids
+    (BDR:169-170), with the same truncation, specb brackets and empty-text error."""
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+
+    from sgpt_b200.embedder import CustomEmbedder
+
+    vocab = {"[UNK]": 0, "[PAD]": 1, "[": 4, "]": 5, "{": 6, "}": 7}
+    for i, w in enumerate("a b c d e f g hello world".split()):
+        vocab[w] = 8 + i
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.WhitespaceSplit()
+    fast = PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="[UNK]", pad_token="[PAD]")
+
+    class TwoStep:
+        def tokenize(self, text):
+            return text.split()
+
+        def convert_tokens_to_ids(self, tokens):
+            return [vocab.get(t, 0) for t in tokens]
+
+    def make(tokenizer):
+        e = object.__new__(CustomEmbedder)
+        e.tokenizer, e.max_token_len, e.specb, e.pad_id = tokenizer, 4, True, 1
+        e.bos_token_q, e.eos_token_q, e.bos_token_d, e.eos_token_d = [4], [5], [6], [7]
+        return e
+
+    texts = ["a b\nc d e f", "hello", "zzz world"]
+    for is_query in (True, False):
+        got, want = make(fast).tokenize_batch(texts, is_query), make(TwoStep()).tokenize_batch(texts, is_query)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert make(fast).tokenize_batch(texts, True)[0][0].tolist() == [4, 8, 9, 10, 11, 5]
+    with pytest.raises(ValueError, match="Empty items"):
+        make(fast).tokenize_batch(["a", "   "], True)
