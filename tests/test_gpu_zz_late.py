@@ -79,8 +79,12 @@ def test_sharded_dres_world1_equals_chunked_dres():
     res1 = ShardedDenseRetrievalExactSearch(emb, batch_size=16, corpus_chunk_size=50).search(corpus, queries, top_k, "cos_sim")
     for qid in queries:
         assert "d5" not in res1["d5"]
-        assert sorted(res1[qid], key=res1[qid].get, reverse=True) == sorted(res[qid], key=res[qid].get, reverse=True), qid
-        assert max(abs(res1[qid][c] - res[qid][c]) for c in res[qid]) < 2e-5
+        # both keep top_k+1 candidates per scan and drop the self match afterwards (XS:102-118), so a query that IS a corpus
+        # document ends with top_k entries from one scan and top_k+1 from three: compare the top_k both must have
+        r1 = sorted(res1[qid], key=res1[qid].get, reverse=True)[:top_k]
+        r0 = sorted(res[qid], key=res[qid].get, reverse=True)[:top_k]
+        assert len(res1[qid]) >= top_k and r1 == r0, qid
+        assert max(abs(res1[qid][c] - res[qid][c]) for c in r1) < 2e-5
 
 
 def test_information_retrieval_evaluator_on_corpus_shard():
