@@ -450,8 +450,9 @@ def run_b200(args, rank, world, local_rank):
     e2e_enc_s, _, _ = e2e_pass(False, args.steps)
     # ---- optional: strong scaling of the exact search over ONE 10 M-doc corpus split across the ranks -------------------
     # (north_star: "linear top-k scaling to 8 GPUs on a 10M-doc synthetic corpus"; the main line above is weak scaling
-    # at 1 M docs per GPU.)  Off by default until the 10 M-row shard has been validated on the GPU; runs after every
-    # other measurement so that a failure here cannot cost the main numbers.
+    # at 1 M docs per GPU.)  The 10 M-row single-GPU shard is validated by tools/bench_search.py
+    # (profiles/r01_search_sweep.jsonl); the leg runs after every other measurement and reports an error string
+    # instead of raising, so that a failure here cannot cost the main numbers.
     big = None
     if args.corpus_10m:
         try:
@@ -578,8 +579,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--corpus-10m", action="store_true",
-                    help="also time the exact search over one 10M x 768 corpus split across the ranks (strong scaling)")
+    ap.add_argument("--no-corpus-10m", dest="corpus_10m", action="store_false",
+                    help="skip the extra leg that times the exact search over one 10M x 768 corpus split across the ranks "
+                         "(strong scaling; reported as search_10m_strong_scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
