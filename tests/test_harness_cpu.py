@@ -321,3 +321,51 @@ def test_custom_embedder_tokenize_batch_fast_tokenizer_equals_two_step_path():
     assert make(fast).tokenize_batch(texts, True)[0][0].tolist() == [4, 8, 9, 10, 11, 5]
     with pytest.raises(ValueError, match="Empty items"):
         make(fast).tokenize_batch(["a", "   "], True)
+
+
+def test_evaluate_run_ndcg_against_sklearn_and_brute_force():
+    """NDCG@k of beir_compat.evaluate_run vs sklearn.metrics.ndcg_score (linear gains, log2 discount — the trec_eval
+    definition) and Recall/P/MAP vs a brute-force restatement, on random runs with graded qrels (pytrec_eval itself is
+    not installed offline)."""
+    from sklearn.metrics import ndcg_score
+
+    from sgpt_b200.beir_compat import evaluate_run
+
+    rs = np.random.RandomState(7)
+    docs = [f"d{i:03d}" for i in range(40)]
+    qrels, results = {}, {}
+    for q in range(15):
+        qid = f"q{q}"
+        judged = rs.choice(docs, rs.randint(1, 12), replace=False)
+        qrels[qid] = {d: int(rs.randint(0, 4)) for d in judged}
+        if not any(v > 0 for v in qrels[qid].values()):
+            qrels[qid][judged[0]] = 1
+        retrieved = rs.choice(docs, rs.randint(5, 40), replace=False)
+        results[qid] = {d: float(s) for d, s in zip(retrieved, rs.permutation(len(retrieved)) / 100.0)}  # distinct scores
+    ks = [1, 5, 10, 100]
+    ndcg, _map, recall, prec = evaluate_run(qrels, results, ks)
+    for k in ks:
+        vals, rec, pre, ap = [], [], [], []
+        for qid in results:
+            y_true = np.array([[max(qrels[qid].get(d, 0), 0) for d in docs]], dtype=float)
+            y_score = np.array([[results[qid].get(d, -1.0) for d in docs]])  # unretrieved docs rank last with gain 0 or not
+            # sklearn ranks ALL docs; trec_eval only the retrieved ones: zero the gain of unretrieved docs in the run's
+            # DCG by comparing on the retrieved set, but keep them in the ideal ranking
+            ranked = sorted(results[qid], key=results[qid].get, reverse=True)[:k]
+            gains = [max(qrels[qid].get(d, 0), 0) for d in ranked]
+            dcg = sum(g / np.log2(i + 2) for i, g in enumerate(gains))
+            ideal = sorted((v for v in qrels[qid].values() if v > 0), reverse=True)[:k]
+            idcg = sum(g / np.log2(i + 2) for i, g in enumerate(ideal))
+            vals.append(dcg / idcg)
+            if set(d for d, v in qrels[qid].items() if v > 0) <= set(results[qid]):
+                # every relevant doc was retrieved: then sklearn's full ranking agrees with trec_eval's
+                assert abs(ndcg_score(y_true, y_score, k=k) - dcg / idcg) < 1e-9
+            n_rel = sum(1 for v in qrels[qid].values() if v > 0)
+            hits = [1 if g > 0 else 0 for g in gains]
+            rec.append(sum(hits) / n_rel)
+            pre.append(sum(hits) / k)
+            ap.append(sum(sum(hits[:i + 1]) / (i + 1) for i, h in enumerate(hits) if h) / n_rel)
+        assert ndcg[f"NDCG@{k}"] == round(float(np.mean(vals)), 5)
+        assert recall[f"Recall@{k}"] == round(float(np.mean(rec)), 5)
+        assert prec[f"P@{k}"] == round(float(np.mean(pre)), 5)
+        assert _map[f"MAP@{k}"] == round(float(np.mean(ap)), 5)
