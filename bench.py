@@ -3,8 +3,11 @@
 (GPT-Neo forward + weighted-mean pool) and exact top-1001 cosine retrieval of 128 queries over a 1M-doc corpus shard.
 
 One "step" = encode one batch of 256 synthetic documents  +  search 128 synthetic queries against the resident
-1M x 768 shard (N>1: every rank encodes its own batch and scans its own 1M-doc shard — weak scaling — then one NCCL
-all-gather of the per-shard top-1001 and a merge).  Prints ONE JSON line (rank 0).
+1M x 768 shard (N>1: every rank encodes its own batch and scans its own 1M-doc shard — weak scaling — then the per-shard
+top-1001 lists are exchanged ONCE (kernel-to-kernel over NVLink peer mappings; NCCL all-gather of packed entries as the
+other transport) and merged on every rank; the merged result is verified against a single-rank search of the whole of
+a small planted corpus: `merge_verified`).  Extra keys (N=1): BASELINE configs 3-5 at full size, the fp32 top-k overlap,
+the 10M-doc strong-scaling legs.  Prints ONE JSON line (rank 0).
 
   python bench.py --gpus 1 --steps 10 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
@@ -264,18 +267,161 @@ def workload_config(n):
     return {"workload": "SGPT-125M (GPT-Neo-125M arch, random-init bf16) bi-encoder: encode batch 256 x seq_len 128 "
                         "(full-length rows) + weighted-mean pool; cos_sim top-1001 of 128 queries over a 1M x 768 bf16 "
                         "corpus shard per GPU", "batch": B, "seq_len": S, "queries": NQ, "docs_per_gpu": NDOCS,
-            "top_k": TOPK, "parallelism": f"dp{n} (corpus row-sharded, per-shard top-k all-gather)",
+            "top_k": TOPK, "parallelism": f"dp{n} (corpus row-sharded, per-shard top-k exchanged once, merged on every rank)",
             "l2": "inputs larger than L2 (activations 0.55 GB, shard 1.5 GB)"}
+
+
+CATS = ["embed", "layernorm", "linear_gemm", "attention", "pool", "similarity_gemm", "topk", "misc"]
+
+
+def fill_shard(shard, n, D, g, dev, queries=None, slab=100_000):
+    """Synthetic corpus generated on the device in slabs; with `queries`, 1 % of the rows are planted near-duplicates
+    (query + 0.5 noise) so that the top of every ranking is meaningful."""
+    for s0 in range(0, n, slab):
+        m = min(slab, n - s0)
+        c = torch.randn(m, D, generator=g, device=dev)
+        if queries is not None:
+            idx = torch.arange(0, m, 100, device=dev)
+            c[idx] = queries[((s0 + idx) // 100) % queries.shape[0]] + 0.5 * c[idx]
+        shard.add(c)
+        del c
+
+
+def time_search(fn, steps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def other_config_legs(dev, pk, lib, steps):
+    """BASELINE.json configs[2..4] at full size on ONE GPU: the encoder of each model at its batch x
+    seq_len (random-init bf16 weights drawn on the GPU, inputs resident) and the exact top-1001 search over the shard
+    shape the config puts on one GPU.  Extra keys of the JSON line; the headline stays configs[1]."""
+    from sgpt_b200 import CorpusShard, Encoder, preset
+    from tools.bench_models import SHAPES, rand_weights
+
+    out = {}
+    ms_cat, n_cat = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+    for key, name, shard_shape in (("config3_sgpt_1.3b", "sgpt-1.3b", (1_000_000, 2048, "1M x 2048 on one GPU")),
+                                   ("config4_sgpt_5.8b_gptj", "sgpt-5.8b", (125_000, 4096, "1M x 4096 over 8 GPUs: 125k per GPU")),
+                                   ("config5_sgpt_bloom_7b1", "sgpt-bloom-7b1", (1_250_000, 4096, "10M x 4096 over 8 GPUs: 1.25M per GPU"))):
+        leg = {}
+        try:
+            cfg = preset(name)
+            Bm, Sm = SHAPES[name]
+            sd = rand_weights(cfg, dev)
+            enc = Encoder(cfg, sd, device=dev, max_tokens=Bm * Sm, max_batch=Bm)
+            del sd
+            g = torch.Generator().manual_seed(1)
+            ids = torch.randint(0, cfg.vocab, (Bm, Sm), generator=g).numpy()
+            mask = np.ones((Bm, Sm), dtype=np.int8)
+            for _ in range(2):
+                o = enc.encode_tokens(ids, mask)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                o = enc.encode_tokens(ids, mask)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            lib.sgpt_profile_read(None, None, None)
+            lib.sgpt_profile_enable(1)
+            for _ in range(steps):
+                enc.encode_tokens(ids, mask)
+            torch.cuda.synchronize()
+            lib.sgpt_profile_enable(0)
+            lib.sgpt_profile_read(ms_cat, n_cat, None)
+            L, d, ff = cfg.n_layer, cfg.d_model, cfg.d_ff
+            lin = Bm * Sm * 2 * L * (4 * d * d + 2 * d * ff)
+            att = Bm * L * 2 * Sm * (Sm + 1) * d
+            gemm_tf = lin / (ms_cat[2] / steps / 1e3) / 1e12 if ms_cat[2] > 0 else None
+            att_tf = att / (ms_cat[3] / steps / 1e3) / 1e12 if ms_cat[3] > 0 else None
+            leg["encode"] = {
+                "model": name, "batch": Bm, "seq_len": Sm, "ms_per_batch": ms, "embeddings_per_s": Bm / (ms / 1e3),
+                "model_tflops": (lin + att) / (ms / 1e3) / 1e12, "finite": bool(torch.isfinite(o).all()),
+                "e2e": "Encoder.encode_tokens(host ids): pinned H2D of ids/positions inside the timed region, embeddings stay on the device",
+                "kernel_ms_per_batch": {c: ms_cat[i] / steps for i, c in enumerate(CATS) if ms_cat[i] > 0},
+                "roofline": {"kernel": "gemm_bf16_tn_kernel (linear layers)", "bound": "tensor", "achieved": gemm_tf,
+                             "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"] if gemm_tf else None,
+                             "traffic": None},
+                "roofline_attention": {"kernel": "attention kernel", "bound": "tensor", "achieved": att_tf,
+                                       "peak": pk["tf_sustained"], "unit": "TFLOP/s (causal FLOPs 2*S*(S+1)*d per layer per sequence)",
+                                       "frac": att_tf / pk["tf_sustained"] if att_tf else None, "traffic": None}}
+            enc.close()
+            del enc, o
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001 - an extra leg must never cost the headline
+            leg["encode"] = {"error": repr(e)[:300]}
+        try:
+            n, D, what = shard_shape
+            g = torch.Generator(device=dev).manual_seed(11)
+            q = torch.randn(NQ, D, generator=g, device=dev)
+            sh = CorpusShard(D, n, device=dev)
+            fill_shard(sh, n, D, g, dev, queries=q, slab=125_000)
+            ms = time_search(lambda: sh.search(q, TOPK + 1, "cos_sim"), max(steps, 10))
+            byts = n * D * 2 + n * 4 + NQ * D * 2
+            leg["search"] = {"shard": what, "docs": n, "dim": D, "queries": NQ, "top_k": TOPK, "ms_per_search": ms,
+                             "queries_per_s": NQ / (ms / 1e3),
+                             "roofline": {"kernel": "whole search (similarity scan x2 + radix selects)", "bound": "hbm",
+                                          "achieved": byts / (ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                          "frac": byts / (ms / 1e3) / 1e9 / pk["hbm"], "traffic": None,
+                                          "fits_l2": n * D * 2 < 126e6}}
+            del sh
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            leg["search"] = {"error": repr(e)[:300]}
+        out[key] = leg
+    return out
+
+
+def fp32_overlap_leg(dev):
+    """Top-k overlap of the bf16-storage search with the reference's pure-fp32 scoring (SURVEY.md §7 hard part 4, §8c):
+    the reference scores fp32 embeddings with cos_sim (sentence_transformers/util.py:24-43) and torch.topk (XS:102-108);
+    torch on the GPU evaluates exactly that here, as the checker, on a planted 200k x 768 corpus."""
+    from sgpt_b200 import CorpusShard
+
+    n, D, nq = 200_000, 768, 128
+    g = torch.Generator(device=dev).manual_seed(2024)
+    q = torch.randn(nq, D, generator=g, device=dev)
+    c = torch.randn(n, D, generator=g, device=dev)
+    idx = torch.arange(0, n, 100, device=dev)
+    c[idx] = q[(idx // 100) % nq] + 0.5 * c[idx]
+    sh = CorpusShard.from_embeddings(c, device=dev)
+    s, i = sh.search(q, TOPK + 1, "cos_sim")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = torch.nn.functional.normalize(q, dim=1) @ torch.nn.functional.normalize(c, dim=1).T
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    rs, ri = torch.topk(ref, TOPK + 1, dim=1)
+    out = {"docs": n, "dim": D, "queries": nq, "reference": "fp32 cos_sim + torch.topk(1001) of the un-rounded embeddings"}
+    for kk in (10, 100, 1001):
+        inter = sum(len(set(a[:kk]) & set(b[:kk])) for a, b in zip(i.tolist(), ri.tolist()))
+        out[f"overlap_at_{kk}"] = inter / (nq * kk)
+    # disagreements can only be documents whose fp32 scores sit within the bf16 storage error of the cut
+    cut = rs[:, -1:]
+    miss = [(ref[qi, list(set(ri[qi].tolist()) - set(i[qi].tolist()))] - cut[qi]).abs().max().item()
+            if set(ri[qi].tolist()) - set(i[qi].tolist()) else 0.0 for qi in range(nq)]
+    out["max_fp32_score_gap_of_a_missed_doc_to_the_cut"] = max(miss)
+    out["score_max_abs_err_vs_fp32"] = (ref.gather(1, i) - s).abs().max().item()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
 
-    from sgpt_b200 import CorpusShard, Encoder, _lib, preset
-    from sgpt_b200.dist import all_gather_topk
+    from sgpt_b200 import CorpusShard, Encoder, PeerGather, _lib, preset, sharded_search
+    from sgpt_b200.dist import all_gather_packed, shard_range
     from sgpt_b200.encoder import pack_ragged
-    from sgpt_b200.index import merge_topk
+    from sgpt_b200.index import merge_topk_packed
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
@@ -291,37 +437,79 @@ def run_b200(args, rank, world, local_rank):
         resident.append((torch.from_numpy(p).to(dev), torch.from_numpy(pos).to(dev), torch.from_numpy(cu).to(dev)))
     # corpus shard: generated on the device in slabs (1% planted near-duplicates of the queries)
     D = CFG["d_model"]
-    g = torch.Generator(device=dev).manual_seed(4321 + rank)
-    queries = torch.randn(NQ, D, generator=g, device=dev)
+    gq = torch.Generator(device=dev).manual_seed(4321)  # the SAME queries on every rank (a sharded search is collective)
+    queries = torch.randn(NQ, D, generator=gq, device=dev)
+    g = torch.Generator(device=dev).manual_seed(4321 + 17 * (rank + 1))
     shard = CorpusShard(D, NDOCS, device=dev, id_base=rank * NDOCS)
-    slab = 100_000
-    for s0 in range(0, NDOCS, slab):
-        c = torch.randn(slab, D, generator=g, device=dev)
-        idx = torch.arange(0, slab, 100, device=dev)
-        c[idx] = queries[(idx // 100) % NQ] + 0.5 * c[idx]
-        shard.add(c)
-    del c
+    fill_shard(shard, NDOCS, D, g, dev, queries=queries)
     q_host = queries.cpu().pin_memory()
     kk = TOPK + 1
 
-    def search_step(q_dev):
-        s, i = shard.search(q_dev, kk, "cos_sim")
-        if world > 1:
-            gs, gi = all_gather_topk(s, i)
-            s, i = merge_topk(gs, gi)
-        return s, i
+    # ---- exchange of the per-shard top-k (N > 1) -------------------------------------------------------------------
+    gather, transport = None, "none (single GPU)"
+    if world > 1:
+        transport = "nccl: one all-gather of packed 8-byte (score, id) entries + merge kernel"
+        if os.environ.get("SGPT_BENCH_TRANSPORT", "p2p") == "p2p":
+            ok = torch.zeros(1, device=dev)
+            try:
+                gather = PeerGather(NQ, kk, dev)
+                ok += 1
+            except Exception as e:  # noqa: BLE001 - e.g. CUDA IPC not permitted: every rank falls back together
+                print(f"[bench] rank {rank}: peer gather unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1:
+                gather = None
+            else:
+                transport = ("p2p: the final selection kernel stores its list into every rank's gather buffer over NVLink "
+                             "peer mappings and signals per query; the merge kernel waits on the signals (no collective)")
+
+    def search_step(q_dev, sh=None):
+        sh = sh or shard
+        if world == 1:
+            return sh.search(q_dev, kk, "cos_sim")
+        return sharded_search(q_dev, sh, kk, "cos_sim", gather=gather)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def maxr_early(x):  # max over ranks (device-timed numbers are reported as the slowest rank's)
+    def maxr(x):  # max over ranks (device-timed numbers are reported as the slowest rank's)
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
+
+    # ---- N > 1: verify the merged result -------------------------------------------------------
+    # A small planted corpus is split over the ranks exactly like the big one; every rank also holds the WHOLE corpus
+    # and searches it alone.  exchange + merge across ranks must reproduce the single-rank result: same scores, same ids
+    # except inside groups of tied scores at equal rank.
+    merge_verified = None
+    if world > 1:
+        nv = 64_000 * world
+        gv = torch.Generator(device=dev).manual_seed(99)
+        cv = torch.randn(nv, D, generator=gv, device=dev)
+        idx = torch.arange(0, nv, 100, device=dev)
+        cv[idx] = queries[(idx // 100) % NQ] + 0.5 * cv[idx]
+        whole = CorpusShard.from_embeddings(cv, device=dev)
+        lo, hi = shard_range(nv, rank, world)
+        part = CorpusShard.from_embeddings(cv[lo:hi], device=dev, id_base=lo)
+        ws_, wi_ = whole.search(queries, kk, "cos_sim")
+        good = True
+        for rep in range(3):  # both buffer parities of the peer exchange
+            ms_, mi_ = search_step(queries, part)
+            same_scores = bool((ms_ - ws_).abs().max().item() <= 1e-6)
+            agree = (mi_ == wi_).float().mean().item()
+            good = good and same_scores and agree > 0.999
+        # the NCCL transport as well (it stays the fallback)
+        ms2, mi2 = merge_topk_packed(all_gather_packed(part.search_packed(queries, kk, "cos_sim")))
+        good = good and bool((ms2 - ws_).abs().max().item() <= 1e-6) and (mi2 == wi_).float().mean().item() > 0.999
+        t = torch.tensor([1.0 if good else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        merge_verified = bool(t.item() > 0)
+        del cv, whole, part
+        torch.cuda.empty_cache()
 
     # ---- warm-up -----------------------------------------------------------------------------------------------
     # nvidia-smi needs ~0.5 s to produce its first sample: start it before the warm-up; samples cover warm-up + both
@@ -335,21 +523,22 @@ def run_b200(args, rank, world, local_rank):
     barrier()
 
     # ---- device-timed loop (inputs resident in HBM) -------------------------------------------------------------
-    # Two passes over the SAME K steps.  Pass 1 is the timed region of `value`: only three CUDA events per step.
-    # Pass 2 repeats it with the library's per-launch CUDA events switched on (two event records around each of the
-    # ~138 launches of a step cost ~7 % of the step, so they stay out of pass 1) and feeds `roofline` /
-    # `kernel_ms_per_step`; its own step time is reported as profiled_pass_ms_per_step.
+    # The timed region is K steps repeated R times back to back (R chosen so that the region lasts >= ~1.2 s: 30 steps of
+    # 7 ms alone would be a 0.2 s measurement); every number below is divided by K*R.  Two passes over the SAME steps:
+    # pass 1 is the timed region of `value` (three CUDA events per step); pass 2 repeats K steps with the library's
+    # per-launch CUDA events switched on (two event records around each of the ~140 launches of a step cost ~7 % of the
+    # step, so they stay out of pass 1) and feeds `roofline` / `kernel_ms_per_step`.
     prof_ms = (ctypes.c_double * 8)()
     prof_n = (ctypes.c_int64 * 8)()
     tot_n0 = (ctypes.c_int64 * 8)()
     tot_n1 = (ctypes.c_int64 * 8)()
     gclk_c, gclk_ns = ctypes.c_double(), ctypes.c_double()
 
-    def timed_pass():
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    def timed_pass(n_steps):
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_steps)]
         barrier()
         t_w0 = time.perf_counter()
-        for k in range(args.steps):
+        for k in range(n_steps):
             r = resident[k % len(resident)]
             ev[k][0].record()
             enc.encode_packed(r[0], r[1], r[2], B, B * S, S)
@@ -358,20 +547,42 @@ def run_b200(args, rank, world, local_rank):
             ev[k][2].record()
         barrier()
         t_w = time.perf_counter() - t_w0
-        e_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
-        s_ms = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps))
+        e_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(n_steps))
+        s_ms = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(n_steps))
         return e_ms, s_ms, ev[0][0].elapsed_time(ev[-1][2]), t_w
 
+    K = args.steps
+    _, _, probe_ms, _ = timed_pass(min(K, 5))
+    step_est = maxr(probe_ms / min(K, 5))
+    R = max(1, int(np.ceil(1200.0 / max(1e-3, step_est * K))))
+    if world > 1:
+        rt = torch.tensor([R], device=dev)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        R = int(rt.item())
+    KR = K * R
     lib.sgpt_profile_read(None, None, tot_n0)
     lib.sgpt_profile_gemm_clock(ctypes.byref(gclk_c), ctypes.byref(gclk_ns))  # reset
-    enc_ms, sea_ms, tot_ms, t_wall = timed_pass()
+    enc_ms, sea_ms, tot_ms, t_wall = timed_pass(KR)
     lib.sgpt_profile_read(None, None, tot_n1)
     lib.sgpt_profile_gemm_clock(ctypes.byref(gclk_c), ctypes.byref(gclk_ns))
     launches = sum(int(tot_n1[c] - tot_n0[c]) for c in range(8))
     lib.sgpt_profile_enable(1)
-    _, _, prof_tot_ms, _ = timed_pass()
+    _, _, prof_tot_ms, _ = timed_pass(K)
     lib.sgpt_profile_enable(0)
     lib.sgpt_profile_read(prof_ms, prof_n, tot_n1)
+
+    # ---- phases of the sharded search (N > 1): local search vs exchange + merge --------------------------------------
+    phases = None
+    if world > 1:
+        t_full = time_search(lambda: search_step(queries), 20)
+        t_local = time_search(lambda: shard.search_packed(queries, kk, "cos_sim"), 20)
+        pk_ = shard.search_packed(queries, kk, "cos_sim")
+        t_gather = time_search(lambda: all_gather_packed(pk_), 20)
+        gp_ = all_gather_packed(pk_)
+        t_merge = time_search(lambda: merge_topk_packed(gp_), 20)
+        phases = {"full_search_ms": maxr(t_full), "local_scan_and_selects_ms": maxr(t_local),
+                  "exchange_plus_merge_ms": maxr(t_full) - maxr(t_local),
+                  "nccl_all_gather_packed_alone_ms": maxr(t_gather), "merge_kernel_alone_ms": maxr(t_merge)}
 
     # ---- end-to-end loop: public API, HOST buffers in, HOST results out -------------------------------------------
     # Every step copies its inputs host->device (pinned, inside encode_tokens / .to) and its results device->host into
@@ -383,135 +594,98 @@ def run_b200(args, rank, world, local_rank):
     i_host = [torch.empty((NQ, kk), dtype=torch.int64).pin_memory() for _ in range(2)]
     slot_evt = [torch.cuda.Event() for _ in range(2)]
 
-    trace = os.environ.get("SGPT_BENCH_E2E_TRACE") == "1"  # per-step host/GPU timestamps of the e2e loop to stderr
-
     def e2e_pass(with_search, steps):
-        nonlocal_h2d = nonlocal_d2h = 0
-        tr_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)] if trace else None
-        tr_host, tr_calls = [], []
+        h2d = d2h = 0
         gc_was_on = gc.isenabled()
         if os.environ.get("SGPT_BENCH_GC", "off") == "off":
             gc.collect()
-            gc.disable()  # keep the collector's pauses out of the timed loop
+            gc.disable()  # keep the collector's pauses out of the timed loop (DESIGN.md §5.3)
         barrier()
         t0 = time.perf_counter()
         for k in range(steps):
             slot = k % 2
             slot_evt[slot].synchronize()  # the consumer of this slot's previous results is done with them
-            if trace:
-                tr_host.append(time.perf_counter() - t0)
-                tr_ev[k][0].record()
             emb = enc.encode_tokens(batches[k % 4].numpy(), mask)
-            if trace:
-                tr_ev[k][1].record()
-            nonlocal_h2d += enc.h2d_bytes_last
+            h2d += enc.h2d_bytes_last
             emb_host[slot].copy_(emb, non_blocking=True)
-            nonlocal_d2h += emb_host[slot].numel() * 4
+            d2h += emb_host[slot].numel() * 4
             if with_search:
-                h0 = time.perf_counter()
                 qd = q_host.to(dev, non_blocking=True)
-                h1 = time.perf_counter()
-                nonlocal_h2d += q_host.numel() * 4
+                h2d += q_host.numel() * 4
                 s, i = search_step(qd)
-                h2 = time.perf_counter()
                 s_host[slot].copy_(s, non_blocking=True)
                 i_host[slot].copy_(i, non_blocking=True)
-                h3 = time.perf_counter()
-                if trace:
-                    tr_calls.append((h1 - h0, h2 - h1, h3 - h2))
-                nonlocal_d2h += s_host[slot].numel() * 4 + i_host[slot].numel() * 8
-            if trace:
-                tr_ev[k][2].record()
+                d2h += s_host[slot].numel() * 4 + i_host[slot].numel() * 8
             slot_evt[slot].record()
         barrier()
         t_total = time.perf_counter() - t0
         if gc_was_on:
             gc.enable()
-        if trace:
-            print(f"[e2e trace] with_search={with_search} steps={steps} total {1e3 * t_total:.2f} ms", file=sys.stderr)
-            if tr_calls:
-                worst = [max(range(len(tr_calls)), key=lambda j: tr_calls[j][c]) for c in range(3)]
-                print("[e2e trace] slowest host call (ms, step): q.to(dev) %.2f @%d | shard.search %.2f @%d | D2H copy_ x2 "
-                      "%.2f @%d" % (1e3 * tr_calls[worst[0]][0], worst[0], 1e3 * tr_calls[worst[1]][1], worst[1],
-                                    1e3 * tr_calls[worst[2]][2], worst[2]), file=sys.stderr)
-            for k in range(steps):
-                gap = tr_ev[k - 1][2].elapsed_time(tr_ev[k][0]) if k else 0.0
-                print(f"[e2e trace] step {k:2d} host_start {1e3 * tr_host[k]:8.2f} ms | gpu encode "
-                      f"{tr_ev[k][0].elapsed_time(tr_ev[k][1]):6.2f} rest {tr_ev[k][1].elapsed_time(tr_ev[k][2]):6.2f} "
-                      f"gap_before {gap:6.2f}", file=sys.stderr)
-        return t_total, nonlocal_h2d, nonlocal_d2h
+        return t_total, h2d, d2h
 
-    # W untimed warm-up steps of exactly this loop first: the warm-up at the top never runs the host->device query copy
-    # or the copies into the pinned result buffers.  (one host stall of 18-87 ms per pass, always inside
-    # the 10th step's CorpusShard.search call, used to dominate the short timed region of the search leg.)
+    # W untimed warm-up steps of exactly this loop first (host->device query copy, copies into the pinned result buffers)
     e2e_pass(True, max(args.warmup, 3))
-    e2e_s, h2d, d2h = e2e_pass(True, args.steps)
-    # separate e2e encode-only timing for the headline emb/s
-    e2e_enc_s, _, _ = e2e_pass(False, args.steps)
-    # ---- optional: strong scaling of the exact search over ONE 10 M-doc corpus split across the ranks -------------------
-    # (north_star: "linear top-k scaling to 8 GPUs on a 10M-doc synthetic corpus"; the main line above is weak scaling
-    # at 1 M docs per GPU.)  The 10 M-row single-GPU shard is validated by tools/bench_search.py
-    # (profiles/r01_search_sweep.jsonl); the leg runs after every other measurement and reports an error string
-    # instead of raising, so that a failure here cannot cost the main numbers.
+    e2e_s, h2d, d2h = e2e_pass(True, KR)
+    e2e_enc_s, _, _ = e2e_pass(False, KR)  # encode-only variant (extra key)
+
+    # ---- strong scaling of the exact search over ONE 10 M-doc corpus split across the ranks -----------------------------
+    # (north_star: "linear top-k scaling to 8 GPUs on a 10M-doc synthetic corpus"; the main line above is weak scaling at
+    # 1 M docs per GPU.)  Two legs: D = 768 (the 125M model's embedding size) and D = 4096 (config 5: sgpt-bloom-7b1).  A
+    # failure is reported as an error string and cannot cost the main numbers.
     big = None
     if args.corpus_10m:
-        try:
-            from sgpt_b200.dist import shard_range
-
-            total = 10_000_000
-            lo, hi = shard_range(total, rank, world)
-            big_shard = CorpusShard(D, hi - lo, device=dev, id_base=lo)
-            for s0 in range(0, hi - lo, 250_000):
-                big_shard.add(torch.randn(min(250_000, hi - lo - s0), D, generator=g, device=dev))
-
-            def big_step():
-                s_, i_ = big_shard.search(queries, kk, "cos_sim")
-                if world > 1:
-                    gs_, gi_ = all_gather_topk(s_, i_)
-                    s_, i_ = merge_topk(gs_, gi_)
-                return s_, i_
-
-            for _ in range(3):
-                big_step()
-            barrier()
-            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            b0.record()
-            for _ in range(args.steps):
-                big_step()
-            b1.record()
-            barrier()
-            big_ms = maxr_early(b0.elapsed_time(b1) / args.steps)
-            big = {"corpus_docs": total, "docs_per_gpu": hi - lo, "dim": D, "queries": NQ, "top_k": TOPK,
-                   "ms_per_search": big_ms, "queries_per_s": NQ / (big_ms / 1e3), "scaling": "strong",
-                   "frac_of_hbm_roofline": ((hi - lo) * (D * 2 + 4) / (big_ms / 1e3) / 1e9) / peaks()["hbm"]}
-            del big_shard
-        except Exception as e:  # noqa: BLE001 - reported, never fatal for the main line
-            big = {"error": repr(e)[:300]}
+        big = {}
+        for Dbig in (768, 4096):
+            try:
+                total = 10_000_000
+                lo, hi = shard_range(total, rank, world)
+                gb = torch.Generator(device=dev).manual_seed(555 + rank)
+                qb_ = torch.randn(NQ, Dbig, generator=gq, device=dev)
+                big_shard = CorpusShard(Dbig, hi - lo, device=dev, id_base=lo)
+                fill_shard(big_shard, hi - lo, Dbig, gb, dev, queries=qb_, slab=125_000)
+                barrier()
+                n_it = max(5, min(K, 20))
+                big_ms = maxr(time_search(lambda: search_step(qb_, big_shard), n_it))
+                loc_ms = maxr(time_search(lambda: big_shard.search_packed(qb_, kk, "cos_sim"), n_it)) if world > 1 else big_ms
+                byts = (hi - lo) * (Dbig * 2 + 4)
+                big[f"dim_{Dbig}"] = {"corpus_docs": total, "docs_per_gpu": hi - lo, "dim": Dbig, "queries": NQ, "top_k": TOPK,
+                                      "ms_per_search": big_ms, "queries_per_s": NQ / (big_ms / 1e3), "scaling": "strong",
+                                      "local_scan_and_selects_ms": loc_ms, "exchange_plus_merge_ms": big_ms - loc_ms,
+                                      "frac_of_hbm_roofline": (byts / (big_ms / 1e3) / 1e9) / peaks()["hbm"]}
+                del big_shard
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001 - reported, never fatal for the main line
+                big[f"dim_{Dbig}"] = {"error": repr(e)[:300]}
     clocks = sampler.stop() if sampler else None
 
-    def maxr(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
     enc_ms, sea_ms, tot_ms, e2e_s, e2e_enc_s = maxr(enc_ms), maxr(sea_ms), maxr(tot_ms), maxr(e2e_s), maxr(e2e_enc_s)
+    extra_legs, overlap = None, None
+    if world == 1 and args.other_configs:
+        shard_keep = shard
+        try:
+            overlap = fp32_overlap_leg(dev)
+        except Exception as e:  # noqa: BLE001
+            overlap = {"error": repr(e)[:300]}
+        extra_legs = other_config_legs(dev, peaks(), lib, steps=5)
+        del shard_keep
+    if gather is not None:
+        gather.close()
     if rank != 0:
         return
-    K = args.steps
     pk = peaks()
     lin_flops, att_flops = encoder_flops_per_seq(S)
-    emb_per_s = world * B * K / (enc_ms / 1e3)
-    qps = NQ * K / (sea_ms / 1e3)
+    emb_per_s = world * B * KR / (enc_ms / 1e3)
+    qps = NQ * KR / (sea_ms / 1e3)
     gemm_ms, gemm_n = prof_ms[2], int(prof_n[2])
     gemm_tflops = (lin_flops * B * K) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    att_ms = prof_ms[3]
+    att_tflops = (att_flops * B * K) / (att_ms / 1e3) / 1e12 if att_ms > 0 else None
     sim_ms, sim_n = prof_ms[5], int(prof_n[5])
     sim_bytes = NDOCS * D * 2 + NDOCS * 4 + NQ * D * 2  # corpus shard + inv norms + queries
     # the search streams the shard ONCE per query batch, split over two launches of the same kernel (sample pass +
     # filtered pass): bytes per search / summed device time of both launches
     sim_gbs = sim_bytes * K / (sim_ms / 1e3) / 1e9 if sim_ms > 0 else None
-    cats = ["embed", "layernorm", "linear_gemm", "attention", "pool", "similarity_gemm", "topk", "misc"]
+    whole_search_gbs = sim_bytes * KR / (sea_ms / 1e3) / 1e9
     traffic, traffic_src = measured_traffic()
     gemm_traffic = traffic.get("linear_gemm", {}).get("dram_bytes_per_launch")
     sim_traffic = traffic.get("similarity_gemm", {}).get("dram_bytes_per_launch")
@@ -522,23 +696,31 @@ def run_b200(args, rank, world, local_rank):
                       + Tt * dm * 2 + dm * dm * 2 + 2 * Tt * dm * 4            # out-proj + residual
                       + Tt * dm * 2 + dm * ffd * 2 + Tt * ffd * 2              # c_fc + gelu
                       + Tt * ffd * 2 + dm * ffd * 2 + 2 * Tt * dm * 4) / 4     # c_proj + residual
+    gemm_launches_per_step = max(1, gemm_n // max(1, K))
     line = {
         "metric": METRIC, "value": emb_per_s, "unit": "embeddings/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-        "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": tot_ms / KR, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(world),
-        "encode_ms_per_step": enc_ms / K, "search_ms_per_step": sea_ms / K,
+        "timed_region": {"repeats_of_the_K_steps": R, "steps_timed": KR, "device_seconds": tot_ms / 1e3,
+                         "note": "every per-step figure is the region's total divided by steps_timed"},
+        "encode_ms_per_step": enc_ms / KR, "search_ms_per_step": sea_ms / KR,
         "search": {"value": qps, "unit": "queries/s", "corpus_docs": NDOCS * world, "top_k": TOPK,
-                   "pairs_per_s": qps * NDOCS * world},
-        "encoder_model_tflops": (lin_flops + att_flops) * B * world * K / (enc_ms / 1e3) / 1e12,
+                   "pairs_per_s": qps * NDOCS * world, "exchange": transport,
+                   "whole_search_frac_of_hbm": whole_search_gbs / pk["hbm"]},
+        "encoder_model_tflops": (lin_flops + att_flops) * B * world * KR / (enc_ms / 1e3) / 1e12,
         "roofline": {"kernel": "gemm_bf16_tn_kernel (tcgen05 linear layers)", "bound": "tensor", "achieved": gemm_tflops,
                      "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": (gemm_tflops / pk["tf_sustained"]) if gemm_tflops else None, "traffic": gemm_traffic,
-                     "traffic_unit": "DRAM bytes per launch (ncu, read+write, mean over the 4 layer shapes)",
+                     "traffic_unit": "DRAM bytes per launch (ncu, read+write, mean over the layer shapes)",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": gemm_alg_bytes,
                      "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
-                     "timed_in": "pass 2: the same K steps repeated with per-launch CUDA events on the launching stream",
+                     "timed_in": "pass 2: K steps repeated with per-launch CUDA events on the launching stream",
                      "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(1, gemm_n),
-                     "algorithmic_flops_per_launch": lin_flops * B / 48},
+                     "algorithmic_flops_per_launch": lin_flops * B / gemm_launches_per_step},
+        "roofline_attention": {"kernel": "attention kernel", "bound": "tensor", "achieved": att_tflops,
+                               "peak": pk["tf_sustained"], "unit": "TFLOP/s (causal FLOPs 2*S*(S+1)*d per layer per sequence)",
+                               "frac": (att_tflops / pk["tf_sustained"]) if att_tflops else None,
+                               "device_ms_per_step": att_ms / K, "traffic": traffic.get("attention", {}).get("dram_bytes_per_launch")},
         "roofline_similarity": {"kernel": "gemm_bf16_tn_kernel<EpiFilterRows> (query x corpus, threshold filter)",
                                 "bound": "hbm", "achieved": sim_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                 "frac": (sim_gbs / pk["hbm"]) if sim_gbs else None,
@@ -547,24 +729,37 @@ def run_b200(args, rank, world, local_rank):
                                 "traffic_source": traffic_src,
                                 "algorithmic_bytes_per_search": sim_bytes, "launches_per_search": sim_n // max(1, K),
                                 "device_ms_per_search": sim_ms / K},
-        "kernel_ms_per_step": {c: prof_ms[i] / K for i, c in enumerate(cats)},
+        "kernel_ms_per_step": {c: prof_ms[i] / K for i, c in enumerate(CATS)},
         "profiled_pass_ms_per_step": prof_tot_ms / K,
         "gemm_sm_clock_mhz": (1e3 * gclk_c.value / gclk_ns.value) if gclk_ns.value > 0 else None,
         "gpu_launches": launches,
-        "e2e": {"value": world * B * K / e2e_enc_s, "unit": "embeddings/s", "h2d_bytes_per_step": h2d // K,
-                "d2h_bytes_per_step": d2h // K, "full_step_ms": 1000 * e2e_s / K,
-                "search_queries_per_s": None, "note": "public API: Encoder.encode_tokens(host ids) -> async copy into "
-                "pinned host memory (double-buffered); full_step_ms also includes host->device queries, "
-                "CorpusShard.search and device->host top-k"},
+        "e2e": {"value": world * B * KR / e2e_s, "unit": "embeddings/s", "h2d_bytes_per_step": h2d // KR,
+                "d2h_bytes_per_step": d2h // KR, "full_step_ms": 1000 * e2e_s / KR,
+                "encode_only_embeddings_per_s": world * B * KR / e2e_enc_s,
+                "search_queries_per_s": None,
+                "note": "FULL step through the public API: Encoder.encode_tokens(host ids) -> embeddings copied into pinned "
+                        "host memory, host->device queries, exact top-1001 search (+ cross-GPU exchange/merge at N>1), "
+                        "device->host scores and ids; double-buffered, all copies inside the timed region; value = "
+                        "embeddings of the encode half of every step per second of the whole step"},
         "clocks": clocks, "wall_s_timed_loop": t_wall,
     }
+    if merge_verified is not None:
+        line["merge_verified"] = merge_verified
+        line["search_phases_ms"] = phases
     if big is not None:
         line["search_10m_strong_scaling"] = big
-    e2e_search_ms = 1000 * e2e_s / K - 1000 * e2e_enc_s / K
+    e2e_search_ms = 1000 * e2e_s / KR - 1000 * e2e_enc_s / KR
     line["e2e"]["search_queries_per_s"] = NQ / (e2e_search_ms / 1e3) if e2e_search_ms > 0 else None
+    if overlap is not None:
+        line["topk_overlap_vs_fp32_reference"] = overlap
+    if extra_legs is not None:
+        line["other_configs"] = extra_legs
     if world == 1 and not args.no_cpu_baseline:
-        eb, docs = calibrate_reference(weights, enc_seconds=5.0, search_seconds=2.0)
-        r = cpu_reference_times(weights, enc_batch=eb, n_enc=2, search_docs=docs, warm=False)
+        # batch 256 at least once when this host can do it in bounded time, else a smaller sample
+        probe = cpu_reference_times(weights, enc_batch=8, n_enc=1, search_docs=10_000, warm=True)
+        eb = 256 if 256 / max(probe["emb_s"], 1e-6) < 45 else int(min(64, max(4, round(probe["emb_s"] * 5.0))))
+        docs = int(min(200_000, max(10_000, round(10_000 * 2.0 / max(probe["t_search"], 1e-3) / 10_000) * 10_000)))
+        r = cpu_reference_times(weights, enc_batch=eb, n_enc=1 if eb == 256 else 2, search_docs=docs, warm=False)
         line["cpu_baseline"] = {"value": r["emb_s"], "unit": "embeddings/s", "cores": usable_cores(),
                                 "cpu_model": cpu_model_name(),
                                 "kind": "port", "sample": r["sample"], "how": r["how"], "search_qps_1m": r["qps_1m"]}
@@ -580,8 +775,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-corpus-10m", dest="corpus_10m", action="store_false",
-                    help="skip the extra leg that times the exact search over one 10M x 768 corpus split across the ranks "
-                         "(strong scaling; reported as search_10m_strong_scaling)")
+                    help="skip the extra legs that time the exact search over one 10M-doc corpus (D = 768 and 4096) split "
+                         "across the ranks (strong scaling; reported as search_10m_strong_scaling)")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false",
+                    help="skip the N=1 legs for BASELINE configs 3-5 (1.3B / 5.8B / bloom-7b1 encoders, their shard shapes) "
+                         "and the fp32 top-k overlap leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

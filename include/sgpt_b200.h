@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SGPT_ABI_VERSION 1
+#define SGPT_ABI_VERSION 2
 
 #define SGPT_OK 0
 #define SGPT_ERR_INVALID 1     /* bad argument / unsupported shape */
@@ -274,6 +274,38 @@ int64_t sgpt_search_workspace_bytes(int nq, int64_t n, int k);
 int sgpt_search(const void* Q, const void* C, const float* q_scale, const float* c_scale, int nq, int64_t n, int D,
                 int k, int64_t id_base, float* out_scores, int64_t* out_ids, void* ws, int64_t ws_bytes,
                 sgpt_stream_t stream);
+
+/* Same search, result as ONE packed list: out_packed uint64[nq,k], entry = (int32 global id << 32) | fp32 score bits,
+ *     descending, empty slots (-inf, -1); requires id_base + n < 2^31.  This is the 8-byte entry of SURVEY.md §8e: one
+ *     all-gather of Q*(k+1)*8 bytes per rank when the exchange goes through NCCL (sgpt_b200/dist.py). */
+int sgpt_search_packed(const void* Q, const void* C, const float* q_scale, const float* c_scale, int nq, int64_t n,
+                       int D, int k, int64_t id_base, uint64_t* out_packed, void* ws, int64_t ws_bytes,
+                       sgpt_stream_t stream);
+/* S3 on packed lists: in_packed uint64[G,nq,k] (the all-gathered sgpt_search_packed outputs; chunk = shard in
+ *     XS:121-132) -> out_scores fp32[nq,k], out_ids int64[nq,k]; ids < 0 and ids == exclude_ids[q] (XS:118) dropped. */
+int sgpt_topk_merge_packed(const uint64_t* in_packed, int G, int nq, int k, float* out_scores, int64_t* out_ids,
+                           const int64_t* exclude_ids, sgpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * §8e without a collective library call: the per-shard top-k lists are PUSHED into every rank's gather buffer by the
+ * final selection kernel itself (stores through NVLink peer mappings + a system-scope release per query) and merged by
+ * a kernel that acquires those per-query counters — the reference's sequential chunk/heapq merge (XS:80-132) with
+ * chunk = GPU.  One context per process (= per GPU):
+ *   sgpt_gather_create    allocates this rank's buffer and returns its CUDA IPC handle (SGPT_IPC_HANDLE_BYTES bytes);
+ *   sgpt_gather_connect   maps the buffers of all ranks from the concatenated handles [world][SGPT_IPC_HANDLE_BYTES]
+ *                         (exchanged by the host, e.g. torch.distributed.all_gather_object);
+ *   sgpt_search_gather    = sgpt_search on this rank's shard + push + merge: every rank of the group must call it with
+ *                         the same nq and k, in the same order; all ranks receive the identical merged top-k
+ *                         (out_scores fp32[nq,k], out_ids int64[nq,k], self matches exclude_ids[q] dropped).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define SGPT_IPC_HANDLE_BYTES 64
+typedef struct sgpt_gather* sgpt_gather_t;
+int sgpt_gather_create(int rank, int world, int nq_cap, int k, sgpt_gather_t* out, void* handle_out);
+int sgpt_gather_connect(sgpt_gather_t g, const void* all_handles);
+void sgpt_gather_destroy(sgpt_gather_t g);
+int sgpt_search_gather(sgpt_gather_t g, const void* Q, const void* C, const float* q_scale, const float* c_scale,
+                       int nq, int64_t n, int D, int k, int64_t id_base, const int64_t* exclude_ids, float* out_scores,
+                       int64_t* out_ids, void* ws, int64_t ws_bytes, sgpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): launch counters are always on; with profiling enabled every kernel launch issued

@@ -14,7 +14,7 @@ from .config import ModelConfig, preset  # noqa: F401
 
 __all__ = ["ModelConfig", "preset", "Encoder", "CustomEmbedder", "SentenceEncoder", "SentenceBERTBOSEOS",
            "SentenceBERTAsym", "DenseRetrievalExactSearch", "CorpusShard", "merge_topk", "semantic_search",
-           "sharded_search", "ShardedDenseRetrievalExactSearch", "DenseHead", "AsymHeads", "load_st_directory", "GenericDataLoader", "EvaluateRetrieval",
+           "merge_topk_packed", "unpack_topk", "sharded_search", "PeerGather", "ShardedDenseRetrievalExactSearch", "DenseHead", "AsymHeads", "load_st_directory", "GenericDataLoader", "EvaluateRetrieval",
            "InformationRetrievalEvaluator"]
 
 
@@ -40,10 +40,10 @@ def __getattr__(name):  # lazy: torch / CUDA pieces are imported on first use
     if name == "DenseRetrievalExactSearch":
         from .exact_search import DenseRetrievalExactSearch
         return DenseRetrievalExactSearch
-    if name in ("CorpusShard", "merge_topk", "semantic_search"):
+    if name in ("CorpusShard", "merge_topk", "merge_topk_packed", "unpack_topk", "semantic_search"):
         from . import index
         return getattr(index, name)
-    if name in ("sharded_search", "ShardedDenseRetrievalExactSearch"):
+    if name in ("sharded_search", "PeerGather", "ShardedDenseRetrievalExactSearch"):
         from . import dist
         return getattr(dist, name)
     raise AttributeError(name)

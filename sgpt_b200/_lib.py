@@ -73,7 +73,16 @@ _SIGNATURES = {
     "sgpt_profile_read": (i32, [vp, vp, vp]),
     "sgpt_profile_gemm_clock": (i32, [vp, vp]),
     "sgpt_search": (i32, [vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, vp, vp, i64, vp]),
+    "sgpt_search_packed": (i32, [vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, vp, i64, vp]),
+    "sgpt_topk_merge_packed": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
+    "sgpt_gather_create": (i32, [i32, i32, i32, i32, C.POINTER(vp), vp]),
+    "sgpt_gather_connect": (i32, [vp, vp]),
+    "sgpt_gather_destroy": (None, [vp]),
+    "sgpt_search_gather": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, vp, vp, vp, i64, vp]),
 }
+
+ABI_VERSION = 2  # include/sgpt_b200.h SGPT_ABI_VERSION these signatures / struct layouts were written for
+IPC_HANDLE_BYTES = 64
 
 _lib: Optional[C.CDLL] = None
 
@@ -95,6 +104,10 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here means the .so is stale: fail loudly
             fn.restype = res
             fn.argtypes = args
+        got = handle.sgpt_abi_version()
+        if got != ABI_VERSION:  # a stale .so would take these argument lists / struct layouts and corrupt them silently
+            raise RuntimeError(f"{LIB_PATH} has ABI version {got}, the Python binding expects {ABI_VERSION}: rebuild "
+                               "(python -c 'import __graft_entry__ as g; g.build()')")
         _lib = handle
     return _lib
 

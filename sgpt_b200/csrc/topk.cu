@@ -34,7 +34,12 @@ __device__ __forceinline__ Elem load_elem(const TopkSrc& s, int q, int g, long l
   if (s.packed != nullptr) {
     const uint2 p = s.packed[off];
     e.key = score_key(__uint_as_float(p.x));
-    e.id = s.id_base + static_cast<long long>(p.y);
+    if (s.packed_global) {
+      e.id = static_cast<long long>(static_cast<int32_t>(p.y));
+      if (e.id < 0 || (s.exclude != nullptr && e.id == s.exclude[q])) e.key = 0;
+    } else {
+      e.id = s.id_base + static_cast<long long>(p.y);
+    }
   } else {
     e.key = score_key(s.scores[off]);
     if (s.ids != nullptr) {
@@ -116,6 +121,22 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   const int lane = tid & 31, warp = tid >> 5;
 
   pdl_sync();  // programmatic dependent launch: see common.cuh
+  if (src.wait_flag != nullptr) {
+    // cross-GPU gather: the lists of this query are complete once every rank has signalled (topk.cuh TopkExtra::flag)
+    if (tid == 0) {
+      unsigned int v, polls = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src.wait_flag + q) : "memory");
+        if (static_cast<int>(v - src.wait_target) >= 0) break;
+        if (++polls > (1u << 26)) {
+          printf("sgpt: cross-GPU gather timed out (query %d: flag %u, waiting for %u)\n", q, v, src.wait_target);
+          __trap();
+        }
+        __nanosleep(64);
+      } while (true);
+    }
+    __syncthreads();
+  }
   // flat index space over the lists: s_len[g], s_off[g] = sum of the padded lengths of lists < g (block-wide scan)
   if (src.G <= kMaxFlatLists) {
     const uint32_t mylen = (tid < src.G) ? static_cast<uint32_t>(list_len(src, q, tid)) : 0u;
@@ -277,7 +298,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   }
   __syncthreads();
   // bitonic sort, descending by key then ascending by id (skipped when only the threshold / unordered seeds are wanted)
-  for (int size = 2; size <= KP && out_scores != nullptr; size <<= 1) {
+  for (int size = 2; size <= KP && (out_scores != nullptr || extra.n_dst > 0); size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = tid; i < KP / 2; i += kTopkThreads) {
         const int lo = 2 * i - (i & (stride - 1));
@@ -300,6 +321,25 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       const uint32_t key = skey[i];
       out_scores[static_cast<size_t>(q) * k + i] = key ? key_score(key) : -INFINITY;
       out_ids[static_cast<size_t>(q) * k + i] = key ? sid[i] : -1;
+    }
+  }
+  // packed final output to this rank's buffer and/or the peers' gather buffers (16-byte stores of two entries; over
+  // NVLink for peer-mapped destinations), then one system-scope release per destination
+  if (extra.n_dst > 0) {
+    for (int p = 0; p < extra.n_dst; ++p) {
+      uint2* row = extra.dst[p] + (static_cast<size_t>(extra.dst_slot) * extra.dst_nq + q) * k;
+      for (int i = tid; i < k; i += kTopkThreads) {
+        const uint32_t key = skey[i];
+        row[i] = key ? make_uint2(__float_as_uint(key_score(key)), static_cast<uint32_t>(static_cast<int32_t>(sid[i])))
+                     : make_uint2(0xff800000u, 0xffffffffu);  // (-inf, -1)
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      for (int p = 0; p < extra.n_dst; ++p)
+        if (extra.flag[p] != nullptr)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(extra.flag[p] + q) : "memory");
     }
   }
   // optional side outputs for the two-pass search: winners re-packed as the head of another candidate list, and the

@@ -10,6 +10,12 @@ struct TopkSrc {
   const long long* ids = nullptr;    // explicit ids (id < 0 = empty slot); null -> id = id_base + position
   const long long* exclude = nullptr;  // per-query id to drop (self match, XS:118); only with explicit ids
   const uint2* packed = nullptr;     // (score bits, local index) pairs; overrides scores/ids when set
+  int packed_global = 0;             // packed.y is a signed GLOBAL id (< 0 = empty slot) instead of a local index: the
+                                     // gathered per-shard lists of a cross-shard merge (exclude applies)
+  // cross-GPU gather: before touching the lists, wait until wait_flag[q] >= wait_target (system-scope acquire): the
+  // producers of the lists are the selection kernels of the OTHER ranks, writing through NVLink peer mappings
+  const unsigned int* wait_flag = nullptr;
+  unsigned int wait_target = 0;
   const int32_t* counts = nullptr;   // per-(list, query) valid length (clamped to L); null -> L
   long long id_base = 0;
   int G = 1;                         // lists per query
@@ -20,11 +26,21 @@ struct TopkSrc {
 
 // Optional side outputs of a selection (two-pass search): the winners re-packed as the head of a candidate list
 // (local index = id - src.id_base) with its count, and the k-th best score as the query's admission threshold.
+constexpr int kMaxPeers = 16;
 struct TopkExtra {
   uint2* packed = nullptr;  // [nq, cap]
   int* count = nullptr;     // [nq]
   long long cap = 0;
   float* tau = nullptr;     // [nq]
+  // packed final output (score bits, int32 global id; id -1 = empty), written to `n_dst` destinations — this rank's
+  // buffer and, for a sharded corpus, the gather buffers of every peer GPU (peer-mapped pointers): row
+  // dst[p][(dst_slot * dst_nq + q) * k + i].  After the rows of query q have been written, flag[p][q] is incremented
+  // with a system-scope release (flag[p] == nullptr: no signal).
+  uint2* dst[kMaxPeers] = {};
+  unsigned int* flag[kMaxPeers] = {};
+  int n_dst = 0;
+  int dst_slot = 0;
+  int dst_nq = 0;
 };
 
 // out_scores / out_ids may be null when only the side outputs are wanted.

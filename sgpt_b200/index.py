@@ -107,6 +107,18 @@ class CorpusShard:
         shard.n = n
         return shard
 
+    def _prepare(self, queries: torch.Tensor, k: int, score_function: str):
+        """Queries -> bf16 rows + 1/||q|| (cos_sim) + a workspace large enough for this search."""
+        _check_score_function(score_function)
+        q = queries.to(self.device)
+        qb = q.contiguous() if q.dtype == torch.bfloat16 else to_bf16_rows(q.float())
+        cos = score_function == "cos_sim"
+        q_scale = row_inv_norms(qb) if cos else None
+        need = _lib.lib().sgpt_search_workspace_bytes(qb.shape[0], self.n, k)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return qb, q_scale, (self.inv_norms.data_ptr() if cos else None)
+
     def search(self, queries: torch.Tensor, k: int, score_function: str = "cos_sim") -> Tuple[torch.Tensor, torch.Tensor]:
         """Exact top-k of this shard for fp32/bf16 queries [Q, D] (device).
 
@@ -114,25 +126,51 @@ class CorpusShard:
         tail is (-inf, -1).  Queries are rounded to bf16 (the tensor-core input type); their 1/||q|| is taken from the
         rounded rows so the result equals cos_sim of the stored/rounded vectors evaluated in fp32.
         """
-        _check_score_function(score_function)
-        q = queries.to(self.device)
-        qb = q.contiguous() if q.dtype == torch.bfloat16 else to_bf16_rows(q.float())
+        qb, q_scale, c_scale = self._prepare(queries, k, score_function)
         nq = qb.shape[0]
-        cos = score_function == "cos_sim"
-        q_scale = row_inv_norms(qb) if cos else None
         out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
         out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
-        lib = _lib.lib()
-        need = lib.sgpt_search_workspace_bytes(nq, self.n, k)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            rc = lib.sgpt_search(qb.data_ptr(), self.vectors.data_ptr(), _lib.ptr(q_scale),
-                                 self.inv_norms.data_ptr() if cos else None, nq, self.n, self.dim, k, self.id_base,
-                                 out_s.data_ptr(), out_i.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
-                                 _lib.current_stream())
+            rc = _lib.lib().sgpt_search(qb.data_ptr(), self.vectors.data_ptr(), _lib.ptr(q_scale), c_scale, nq, self.n,
+                                        self.dim, k, self.id_base, out_s.data_ptr(), out_i.data_ptr(),
+                                        self._ws.data_ptr(), self._ws.numel(), _lib.current_stream())
         _lib.check(rc, "sgpt_search")
         return out_s, out_i
+
+    def search_packed(self, queries: torch.Tensor, k: int, score_function: str = "cos_sim") -> torch.Tensor:
+        """The same search with the result as ONE tensor of packed 8-byte entries, int64 [Q,k] whose low 32 bits are the
+        fp32 score and high 32 bits the int32 global id (-inf / -1 = empty): what a rank contributes to the single
+        all-gather of a sharded search.  Needs id_base + n < 2^31."""
+        qb, q_scale, c_scale = self._prepare(queries, k, score_function)
+        nq = qb.shape[0]
+        out = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().sgpt_search_packed(qb.data_ptr(), self.vectors.data_ptr(), _lib.ptr(q_scale), c_scale, nq,
+                                               self.n, self.dim, k, self.id_base, out.data_ptr(), self._ws.data_ptr(),
+                                               self._ws.numel(), _lib.current_stream())
+        _lib.check(rc, "sgpt_search_packed")
+        return out
+
+
+def unpack_topk(packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Packed entries int64[...] -> (scores fp32[...], ids int64[...]) (host-side convenience for tests and tools)."""
+    halves = packed.contiguous().view(torch.int32).view(*packed.shape, 2)
+    return halves[..., 0].contiguous().view(torch.float32), halves[..., 1].to(torch.int64)
+
+
+def merge_topk_packed(packed: torch.Tensor, exclude_ids: Optional[torch.Tensor] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge G packed candidate lists per query: int64 [G,Q,k] -> (scores fp32 [Q,k], ids int64 [Q,k]) descending;
+    empty slots and ids == exclude_ids[q] (XS:118) are dropped."""
+    G, Q, k = packed.shape
+    packed = packed.contiguous()
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=packed.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=packed.device)
+    with torch.cuda.device(packed.device):
+        rc = _lib.lib().sgpt_topk_merge_packed(packed.data_ptr(), G, Q, k, out_s.data_ptr(), out_i.data_ptr(),
+                                               _lib.ptr(exclude_ids), _lib.current_stream())
+    _lib.check(rc, "sgpt_topk_merge_packed")
+    return out_s, out_i
 
 
 def merge_topk(scores: torch.Tensor, ids: torch.Tensor, exclude_ids: Optional[torch.Tensor] = None
