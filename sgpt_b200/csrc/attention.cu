@@ -437,10 +437,9 @@ static int launch_attention_tc_impl(const CUtensorMap& map, void* out, const int
                                     int window, int max_seqlen, const float* alibi, cudaStream_t stream) {
   using Cfg = AttnCfg<HD, kSingle>;
   auto kern = attention_tc_kernel<HD, kSingle>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   dim3 grid((max_seqlen + kAttnTile - 1) / kAttnTile, B, H);
   const float sl2 = scale * 1.4426950408889634f;

@@ -22,10 +22,9 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
                         kGemmBK);
   if (rc != SGPT_OK) return rc;
   auto kern = gemm_bf16_tn_kernel<BN, Epi, CL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   const int m_tiles = ((M + kGemmBM - 1) / kGemmBM + CL - 1) / CL;
   const int n_tiles = tmap.count((N + BN - 1) / BN);

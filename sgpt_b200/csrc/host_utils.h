@@ -36,7 +36,15 @@ int make_tma_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 int make_tma_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                     uint32_t box_cols);
 
-int sm_count();
+int sm_count();  // multiprocessors of the CURRENT device (cached per device)
+
+// "Do this once per device": kernel attributes such as cudaFuncAttributeMaxDynamicSharedMemorySize are per device, so a
+// process that drives several GPUs (one Encoder / CorpusShard per device) must opt in on each of them.
+//   static PerDeviceOnce once;  if (once.first()) cudaFuncSetAttribute(...);
+struct PerDeviceOnce {
+  bool first();            // true exactly once per CUDA device (current device), thread-safe
+  unsigned char done_[64] = {};
+};
 
 // Programmatic dependent launch is on unless SGPT_PDL=0 is set in the environment (A/B measurements).
 bool pdl_enabled();

@@ -375,11 +375,10 @@ int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int
     cache_keys = want < room ? want : room;
   }
   const size_t dsm = static_cast<size_t>(KP) * 12 + kSubCap * 4 + cache_keys * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kDynMax)));
-    attr_set = true;
   }
   LaunchScope _ls(kCatTopk, stream);
   SGPT_CHECK_CUDA(launch_kernel(topk_select_kernel, dim3(nq), dim3(kTopkThreads), dsm, stream, src, k, KP,

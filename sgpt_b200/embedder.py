@@ -45,6 +45,22 @@ def _pad_batch(seqs: Sequence[Sequence[int]], pad_id: int) -> Tuple[np.ndarray, 
     return ids, mask
 
 
+
+def split_by_token_budget(lengths, max_tokens: int, max_rows: int) -> List[Tuple[int, int]]:
+    """Greedy consecutive row ranges [lo, hi) whose token sums fit `max_tokens` and row counts `max_rows`.  A single row
+    longer than the budget is an error (the workspace must at least hold max_seq_length tokens)."""
+    out, lo, tok = [], 0, 0
+    for r, n in enumerate(int(x) for x in lengths):
+        if n > max_tokens:
+            raise ValueError(f"a sequence of {n} tokens exceeds the encoder workspace of {max_tokens} tokens")
+        if tok + n > max_tokens or r - lo >= max_rows:
+            out.append((lo, r))
+            lo, tok = r, 0
+        tok += n
+    if len(lengths) > lo:
+        out.append((lo, len(lengths)))
+    return out
+
 class CustomEmbedder:
     def __init__(self, model_name: str = "EleutherAI/gpt-neo-1.3B", batch_size: int = 250, device: str = "cuda:0",
                  save_emb: bool = False, reinit: bool = False, layeridx: int = -1, method: str = "mean",
@@ -136,7 +152,11 @@ class CustomEmbedder:
         out = torch.empty((len(sentences), self.config.d_model), dtype=torch.float32, device=self.device)
         for i in range(0, len(sentences), self.batch_size):
             ids, mask = self.tokenize_batch(sentences[i:i + self.batch_size], is_query)
-            out[i:i + len(ids)] = self.encoder.encode_tokens(ids, mask, method=self.method, layer_idx=self.layeridx)
+            # the reference simply runs whatever a batch holds (BDR:205); the workspace here is sized in tokens, so a
+            # batch of long documents (DRES sorts longest first, XS:66-71) is cut greedily into sub-batches that fit
+            for lo, hi in split_by_token_budget(mask.sum(axis=1), self.encoder.max_tokens, self.encoder.max_batch):
+                out[i + lo:i + hi] = self.encoder.encode_tokens(ids[lo:hi], mask[lo:hi], method=self.method,
+                                                                layer_idx=self.layeridx)
         return out
 
     def embed_batcher(self, texts: List[Tuple[str, str]], is_query: bool, out_name=None, **kwargs) -> Dict[str, np.ndarray]:
@@ -430,7 +450,23 @@ class SentenceBERTBOSEOS:
                  speca: bool = False):
         self.model, self.sep, self.specb, self.speca = model, sep, specb, speca
         tok = model.tokenizer
-        first = lambda text: tok.encode(text)[0]  # noqa: E731
+        vocab = model.encoder.cfg.vocab
+
+        def first(text, must_embed=False):
+            """The id of a marker that must be ONE token (the reference registers the markers with add_tokens,
+            sentence_bert_asym.py:36-38, 56-58; without that '[SOS]' would tokenize to '[' + ... and silently pass)."""
+            ids = list(tok.encode(text, add_special_tokens=False))
+            if len(ids) != 1:
+                raise ValueError(f"{text!r} tokenizes to {len(ids)} ids {ids[:4]}; it must be a single (added) token")
+            if must_embed and not 0 <= ids[0] < vocab:
+                raise ValueError(f"token {text!r} has id {ids[0]} but the checkpoint's embedding matrix has {vocab} rows "
+                                 "(speca needs a checkpoint trained with the added tokens, sentence_bert_asym.py:56-58)")
+            return ids[0]
+
+        if (specb or speca) and hasattr(tok, "add_tokens"):
+            # sentence_bert_asym.py:36-37 / :56-57.  (resize_token_embeddings has no analogue: specb replaces the marker
+            # ids before the embedding lookup, speca requires them inside the checkpoint's matrix — checked below.)
+            tok.add_tokens(["[SOS]", "{SOS}"] if specb else ["[SOS]", "[EOS]", "{SOS}", "{EOS}"], special_tokens=True)
         if specb:
             model.bos_spec_token_q = sos_q if sos_q is not None else first("[SOS]")
             model.bos_spec_token_d = sos_d if sos_d is not None else first("{SOS}")
@@ -440,10 +476,10 @@ class SentenceBERTBOSEOS:
             model.eos_spec_token_d = first("}")
             model.replace_bos = True
         elif speca:
-            model.bos_spec_token_q = sos_q if sos_q is not None else first("[SOS]")
-            model.eos_spec_token_q = first("[EOS]")
-            model.bos_spec_token_d = sos_d if sos_d is not None else first("{SOS}")
-            model.eos_spec_token_d = first("{EOS}")
+            model.bos_spec_token_q = sos_q if sos_q is not None else first("[SOS]", must_embed=True)
+            model.eos_spec_token_q = first("[EOS]", must_embed=True)
+            model.bos_spec_token_d = sos_d if sos_d is not None else first("{SOS}", must_embed=True)
+            model.eos_spec_token_d = first("{EOS}", must_embed=True)
 
     def encode_queries(self, queries: List[str], batch_size: int = 16, **kwargs):
         if self.specb or self.speca:

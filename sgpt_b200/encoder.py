@@ -208,6 +208,9 @@ class Encoder:
         if T > self.max_tokens or B > self.max_batch:
             raise ValueError(f"batch of {B} rows / {T} tokens exceeds the encoder workspace "
                              f"({self.max_batch} rows / {self.max_tokens} tokens)")
+        if T and (int(ids.min()) < 0 or int(ids.max()) >= self.cfg.vocab):
+            # torch's embedding lookup raises on such ids (HF:gpt_neo:462); the gather kernel would otherwise clamp them
+            raise IndexError(f"token id out of range [0, {self.cfg.vocab}): min {int(ids.min())}, max {int(ids.max())}")
         if self.cfg.arch != "bloom" and max_len > self.cfg.max_pos:
             raise ValueError(f"sequence length {max_len} exceeds max_position_embeddings {self.cfg.max_pos}")
         n = 2 * T + B + 1

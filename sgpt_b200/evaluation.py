@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import logging
 import os
+import torch
 from typing import Callable, Dict, List, Optional, Set
 
 import numpy as np
@@ -84,6 +85,23 @@ class InformationRetrievalEvaluator:
         shard = c_emb if isinstance(c_emb, CorpusShard) else CorpusShard.from_embeddings(c_emb)
         return shard.search(q_emb.to(shard.device), k, score_function)
 
+    def _encode_corpus(self, corpus_model, q_emb):
+        """The corpus is encoded `corpus_chunk_size` documents at a time like the reference (:150-152), each chunk added
+        to ONE bf16 shard and its fp32 embeddings dropped — a multi-million-document corpus never exists as an fp32
+        [N, d] device tensor.  (With an injected search_fn the chunks are concatenated instead.)"""
+        chunk = max(1, int(self.corpus_chunk_size))
+        if self.search_fn is not None:
+            parts = [corpus_model.encode(self.corpus[s0:s0 + chunk], show_progress_bar=False, batch_size=self.batch_size,
+                                         convert_to_tensor=True) for s0 in range(0, len(self.corpus), chunk)]
+            return torch.cat(parts) if parts else q_emb[:0]
+        from .index import CorpusShard
+
+        shard = CorpusShard(q_emb.shape[1], max(len(self.corpus), 1), device=q_emb.device)
+        for s0 in range(0, len(self.corpus), chunk):
+            shard.add(corpus_model.encode(self.corpus[s0:s0 + chunk], show_progress_bar=False, batch_size=self.batch_size,
+                                          convert_to_tensor=True))
+        return shard
+
     def compute_metrices(self, model, corpus_model=None, corpus_embeddings=None, num_proc: int = None) -> Dict[str, dict]:
         if corpus_model is None:
             corpus_model = model
@@ -92,8 +110,7 @@ class InformationRetrievalEvaluator:
         q_emb = model.encode(self.queries, show_progress_bar=self.show_progress_bar, batch_size=self.batch_size,
                              convert_to_tensor=True)
         if corpus_embeddings is None:
-            corpus_embeddings = corpus_model.encode(self.corpus, show_progress_bar=False, batch_size=self.batch_size,
-                                                    convert_to_tensor=True)
+            corpus_embeddings = self._encode_corpus(corpus_model, q_emb)
         k = min(max_k, len(self.corpus))
         scores = {}
         for name in self.score_function_names:
