@@ -199,6 +199,11 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float2 lds_v2(uint32_t addr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
@@ -374,6 +379,33 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ---------------------------------------------------------------------------------------------------------------
 // numerics
 // ---------------------------------------------------------------------------------------------------------------
+// LayerNorm statistics of a residual-stream row from its partial sums.  The kernels that WRITE the residual stream (token
+// embedding, out-proj / c_proj epilogues) leave, per row and per group of 128 columns, (sum x, sum x^2) in
+// stats[row * P + group] (P = ceil(d / 128)); the kernels that consume LN(row) — the QKV / c_fc GEMM epilogues with the
+// LayerNorm folded into the weights, and the ln_f + pooling kernel — rebuild mean and 1/sqrt(var + eps) from them in a
+// fixed summation order (deterministic).  rm = rstd * mean.
+struct LnRow {
+  float r, rm;
+};
+__device__ __forceinline__ LnRow ln_row_from_partials(const float2* __restrict__ stats, int P, float inv_d, float eps,
+                                                      int row, int M) {
+  float s1 = 0.f, s2 = 0.f;
+  if (row < M) {
+    const float2* s = stats + static_cast<size_t>(row) * P;
+    for (int g = 0; g < P; ++g) {
+      const float2 t = __ldg(s + g);
+      s1 += t.x;
+      s2 += t.y;
+    }
+  }
+  const float mean = s1 * inv_d;
+  const float var = fmaxf(s2 * inv_d - mean * mean, 0.f);
+  LnRow o;
+  o.r = rsqrtf(var + eps);
+  o.rm = o.r * mean;
+  return o;
+}
+
 // gelu_new(x) = 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))   (HF activations.py NewGELUActivation)
 __device__ __forceinline__ float gelu_new(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
