@@ -186,7 +186,10 @@ typedef struct sgpt_model_weights {
 typedef struct sgpt_model* sgpt_model_t;
 
 /* Replaces AutoModel.from_pretrained(...).to(device) at BDR:123 / ST/models/Transformer.py:38 (weights are handed
- * over already on the device; the handle borrows them and owns only its activation workspace). */
+ * over already on the device; the handle borrows them and owns its activation workspace and the LayerNorm-folded copies
+ * it derives at creation: per layer w_qkv, b_qkv, w_fc, b_fc and ln1 / ln2 are folded into library-owned buffers
+ * (sgpt_fold_layernorm) and are NOT referenced after sgpt_model_create returns — the caller may free them; wte, wpe, w_o,
+ * b_o, w_proj, b_proj, ln_f and the embedding LayerNorm stay borrowed).  Synchronises the device. */
 int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_weights* w, sgpt_model_t* out);
 void sgpt_model_destroy(sgpt_model_t m);
 
