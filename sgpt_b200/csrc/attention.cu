@@ -15,6 +15,7 @@
 //
 // SIMT kernel (impl 1): one warp per (token, head), fp32 everywhere — test cross-check only.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/sgpt_b200.h"
 #include "common.cuh"
@@ -382,6 +383,348 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised, persistent variant (impl 0 for head_dim 64 / 128).
+//
+// One CTA per SM, 320 threads, TWO independent work slots per CTA.  A work unit = (sequence, head, 128-query tile); slot s
+// of CTA c walks units (2c + s), (2c + s) + 2 G, ... (heaviest q-tiles first).  Roles:
+//   warps 0-3   softmax / correction / epilogue warpgroup of slot 0   (thread = query row = TMEM lane)
+//   warps 4-7   the same for slot 1
+//   warp  8     TMA producer (one lane): Q tile of each unit, K/V tiles of its key loop, for both slots
+//   warp  9     tcgen05.mma issuer (one lane) for both slots + TMEM allocation
+// Per slot: smem Q [128 x hd] | NKV stages of { K_j [128 x hd] (re-used for P_j: K_j is dead once S_j = Q K_j^T has
+// completed) | V_j [128 x hd] }; TMEM S (128 fp32 columns) | O (hd columns).  Per key tile j of a unit:
+//       producer : K_j, V_j -> stage (after the P V MMA that last read the stage has completed)
+//       mma      : S = Q K_j^T                       -> s_full
+//       softmax  : row max, p = exp2(...), P -> bf16 -> smem (over K_j), O *= alpha (after o_full of tile j-1) -> p_full
+//       mma      : O += P V_j                        -> kv_empty (stage), o_full
+// The two slots are independent units, so the tensor core runs slot 1's MMAs while slot 0's warpgroup is in its softmax
+// and vice versa, and the producer runs ahead of both (NKV = 2 stages at hd 64); the single in-order issue thread and the
+// single producer thread serve both slots with non-blocking mbarrier polls (whichever slot is ready goes first), so
+// units of different lengths do not stall each other.  The old one-CTA-per-unit kernel serialised load -> MMA ->
+// softmax -> MMA inside a CTA and relied on 2-4 co-resident CTAs for overlap.
+// ---------------------------------------------------------------------------------------------------------------
+template <int HD>
+struct AttnWsCfg {
+  static constexpr int kSub = HD / 64;
+  static constexpr int kQBytes = kSub * kSubBytes;            // Q / K / V tile bytes
+  static constexpr int kKPBytes = 2 * kSubBytes;              // K region also hosts P [128 x 128] bf16
+  static constexpr int kStageBytes = kKPBytes + kQBytes;      // { K|P , V }
+  static constexpr int kNKV = (HD == 64) ? 2 : 1;
+  static constexpr int kSlotBytes = kQBytes + kNKV * kStageBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = 1024 + 2 * kSlotBytes + kBarBytes;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kTmemSlot = 256;                       // columns per slot: S at +0, O at +128
+  static_assert(kSmemBytes <= 232448, "attention: exceeds the 227 KB per-CTA shared memory limit");
+  static_assert(HD == 64 || HD == 128, "warp-specialised attention: head_dim 64 or 128");
+};
+
+struct AttnUnit {
+  int b, h, qt;     // sequence, head, query tile
+  int seq0, len;    // first token row / length of the sequence
+  int j_lo, j_hi;   // key tiles visited
+};
+
+// unit number -> work description; false when the unit does not exist (query tile beyond the sequence's length)
+__device__ __forceinline__ bool attn_unit(int u, int B, int H, int QT, int window, const int32_t* __restrict__ cu,
+                                          AttnUnit& w) {
+  const int bh = B * H;
+  w.qt = QT - 1 - u / bh;  // heaviest query tiles (most key tiles) first
+  const int r = u % bh;
+  w.b = r / H;
+  w.h = r % H;
+  w.seq0 = __ldg(cu + w.b);
+  w.len = __ldg(cu + w.b + 1) - w.seq0;
+  const int qp0 = w.qt * kAttnTile;
+  if (qp0 >= w.len) return false;
+  const int lo_pos = (window > 0) ? max(0, qp0 - window + 1) : 0;
+  w.j_lo = lo_pos / kAttnTile;
+  w.j_hi = w.qt;
+  return true;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv,
+                                                               __nv_bfloat16* __restrict__ out,
+                                                               const int32_t* __restrict__ cu, int B, int H, int QT,
+                                                               float sl2, int window, const float* __restrict__ alibi) {
+  using Cfg = AttnWsCfg<HD>;
+  constexpr int NKV = Cfg::kNKV;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // barriers, per slot: q_full q_empty s_full p_full o_full | k_full[NKV] v_full[NKV] kv_empty[NKV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * Cfg::kSlotBytes);
+  constexpr int kBarsPerSlot = 5 + 3 * NKV;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kBarsPerSlot);
+  auto bar = [&](int s, int i) { return bars + s * kBarsPerSlot + i; };
+  enum { Q_FULL = 0, Q_EMPTY = 1, S_FULL = 2, P_FULL = 3, O_FULL = 4, K_FULL = 5, V_FULL = 5 + NKV, KV_EMPTY = 5 + 2 * NKV };
+  auto slot_q = [&](int s) { return smem + s * Cfg::kSlotBytes; };
+  auto slot_k = [&](int s, int st) { return smem + s * Cfg::kSlotBytes + Cfg::kQBytes + st * Cfg::kStageBytes; };
+  auto slot_v = [&](int s, int st) { return slot_k(s, st) + Cfg::kKPBytes; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = H * HD;
+  const int n_units = QT * B * H;
+  const int stride = 2 * static_cast<int>(gridDim.x);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(s, Q_FULL), 1);
+      mbar_init(bar(s, Q_EMPTY), 1);
+      mbar_init(bar(s, S_FULL), 1);
+      mbar_init(bar(s, P_FULL), 128);
+      mbar_init(bar(s, O_FULL), 1);
+      for (int i = 0; i < NKV; ++i) {
+        mbar_init(bar(s, K_FULL + i), 1);
+        mbar_init(bar(s, V_FULL + i), 1);
+        mbar_init(bar(s, KV_EMPTY + i), 1);
+      }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_holder, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_sync();  // cu_seqlens is written by a copy, qkv by the previous kernel: nothing global is read above this line
+
+  if (warp == 8) {
+    // ===================== TMA producer (both slots, non-blocking round robin) =====================
+    if (lane == 0) {
+      int u[2] = {2 * static_cast<int>(blockIdx.x), 2 * static_cast<int>(blockIdx.x) + 1};
+      int j[2] = {0, 0};          // next key tile to load of the current unit (valid when have[s])
+      bool have[2] = {false, false}, q_sent[2] = {false, false};
+      AttnUnit w[2];
+      uint32_t nq[2] = {0, 0}, nkv[2] = {0, 0};  // Q tiles / KV tiles issued so far per slot
+      bool done[2] = {false, false};
+      uint32_t idle = 0;  // consecutive polls without progress: a protocol bug traps instead of hanging the GPU
+      while (!(done[0] && done[1])) {
+        if (++idle > (1u << 26)) {
+          printf("sgpt: attention producer stalled (block %d)\n", blockIdx.x);
+          __trap();
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (done[s]) continue;
+          if (!have[s]) {
+            while (u[s] < n_units && !attn_unit(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
+            if (u[s] >= n_units) { done[s] = true; continue; }
+            have[s] = true;
+            q_sent[s] = false;
+            j[s] = w[s].j_lo;
+          }
+          if (!q_sent[s]) {
+            // the Q buffer is free once every S MMA of the previous unit has completed
+            if (!mbar_try_wait(bar(s, Q_EMPTY), (nq[s] & 1u) ^ 1u)) continue;
+            mbar_expect_tx(bar(s, Q_FULL), Cfg::kQBytes);
+            for (int x = 0; x < Cfg::kSub; ++x)
+              tma_load_2d(slot_q(s) + x * kSubBytes, &tma_qkv, bar(s, Q_FULL), w[s].h * HD + 64 * x,
+                          w[s].seq0 + w[s].qt * kAttnTile);
+            ++nq[s];
+            q_sent[s] = true;
+          }
+          const int st = static_cast<int>(nkv[s] % NKV);
+          if (!mbar_try_wait(bar(s, KV_EMPTY + st), ((nkv[s] / NKV) & 1u) ^ 1u)) continue;
+          mbar_expect_tx(bar(s, K_FULL + st), Cfg::kQBytes);
+          for (int x = 0; x < Cfg::kSub; ++x)
+            tma_load_2d(slot_k(s, st) + x * kSubBytes, &tma_qkv, bar(s, K_FULL + st), d + w[s].h * HD + 64 * x,
+                        w[s].seq0 + j[s] * kAttnTile);
+          mbar_expect_tx(bar(s, V_FULL + st), Cfg::kQBytes);
+          for (int x = 0; x < Cfg::kSub; ++x)
+            tma_load_2d(slot_v(s, st) + x * kSubBytes, &tma_qkv, bar(s, V_FULL + st), 2 * d + w[s].h * HD + 64 * x,
+                        w[s].seq0 + j[s] * kAttnTile);
+          ++nkv[s];
+          idle = 0;
+          if (++j[s] > w[s].j_hi) {
+            have[s] = false;
+            u[s] += stride;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer (both slots, non-blocking round robin) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, true);
+      int u[2] = {2 * static_cast<int>(blockIdx.x), 2 * static_cast<int>(blockIdx.x) + 1};
+      int j[2] = {0, 0};
+      bool have[2] = {false, false}, want_pv[2] = {false, false}, done[2] = {false, false};
+      AttnUnit w[2];
+      uint32_t nq[2] = {0, 0}, nt[2] = {0, 0};  // units started / key tiles completed per slot
+      uint32_t idle = 0;
+      while (!(done[0] && done[1])) {
+        if (++idle > (1u << 26)) {
+          printf("sgpt: attention MMA issuer stalled (block %d)\n", blockIdx.x);
+          __trap();
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (done[s]) continue;
+          if (!have[s]) {
+            while (u[s] < n_units && !attn_unit(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
+            if (u[s] >= n_units) { done[s] = true; continue; }
+            have[s] = true;
+            j[s] = w[s].j_lo;
+            want_pv[s] = false;
+          }
+          const int st = static_cast<int>(nt[s] % NKV);
+          const uint32_t st_par = (nt[s] / NKV) & 1u;
+          const uint32_t tS = tmem_base + s * Cfg::kTmemSlot, tO = tS + 128;
+          if (!want_pv[s]) {
+            // ---- S = Q K_j^T ---- (the S columns are free: this slot's previous P V waited for p_full of the previous tile)
+            if (j[s] == w[s].j_lo && !mbar_try_wait(bar(s, Q_FULL), nq[s] & 1u)) continue;
+            if (!mbar_try_wait(bar(s, K_FULL + st), st_par)) continue;
+            tc_fence_after();
+            const uint32_t aq = smem_u32(slot_q(s)), ak = smem_u32(slot_k(s, st));
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) {
+              const uint32_t off = (kk >> 2) * kSubBytes + (kk & 3) * 32;
+              umma_bf16_ss(tS, make_smem_desc_sw128(aq + off, 16, 1024), make_smem_desc_sw128(ak + off, 16, 1024),
+                           idesc_s, kk != 0);
+            }
+            umma_commit(bar(s, S_FULL));
+            idle = 0;
+            if (j[s] == w[s].j_hi) {  // last S of the unit: Q may be overwritten once these MMAs are done
+              umma_commit(bar(s, Q_EMPTY));
+              ++nq[s];
+            }
+            want_pv[s] = true;
+          } else {
+            // ---- O += P V_j ----
+            if (!mbar_try_wait(bar(s, P_FULL), nt[s] & 1u)) continue;
+            if (!mbar_try_wait(bar(s, V_FULL + st), st_par)) continue;
+            tc_fence_after();
+            const uint32_t ap = smem_u32(slot_k(s, st)), av = smem_u32(slot_v(s, st));
+#pragma unroll
+            for (int kk = 0; kk < kAttnTile / 16; ++kk) {
+              const uint64_t da = make_smem_desc_sw128(ap + (kk >> 2) * kSubBytes + (kk & 3) * 32, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(av + kk * 2048, kSubBytes, 1024);
+              umma_bf16_ss(tO, da, db, idesc_o, (j[s] > w[s].j_lo) || (kk != 0));
+            }
+            umma_commit(bar(s, KV_EMPTY + st));  // the stage (P over K, and V) may be refilled
+            umma_commit(bar(s, O_FULL));
+            idle = 0;
+            ++nt[s];
+            want_pv[s] = false;
+            if (++j[s] > w[s].j_hi) {
+              have[s] = false;
+              u[s] += stride;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue warpgroups =====================
+    const int s = warp >> 2;            // slot
+    const int row = tid & 127;          // query row of the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + s * Cfg::kTmemSlot + lane_off, tO = tS + 128;
+    uint32_t nt = 0;                    // key tiles completed by this slot
+    AttnUnit w;
+    for (int u = 2 * static_cast<int>(blockIdx.x) + s; u < n_units; u += stride) {
+      if (!attn_unit(u, B, H, QT, window, cu, w)) continue;
+      const int qp0 = w.qt * kAttnTile;
+      const float slope2 = (alibi != nullptr) ? __ldg(alibi + w.h) * 1.4426950408889634f : 0.f;
+      const RowVis rv = make_row_vis(qp0, row, w.len, window);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = w.j_lo; j <= w.j_hi; ++j, ++nt) {
+        const int st = static_cast<int>(nt % NKV);
+        mbar_wait(bar(s, S_FULL), nt & 1u);
+        tc_fence_after();
+        const int kv0 = j * kAttnTile;
+        const float m_new = fmaxf(m_run, softmax_tile_max(tS, kv0, rv, sl2, slope2));
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = exp2f(m_run - m_use);
+        // P over the K tile of this stage: the S MMAs that read K_j have completed (s_full)
+        const float lsum = softmax_tile_exp(tS, kv0, rv, sl2, slope2, m_use, smem_u32(slot_k(s, st)), row);
+        l_run = l_run * alpha + lsum;
+        m_run = m_new;
+        if (j > w.j_lo) {
+          // O = alpha * O once the previous tile's P V has landed
+          mbar_wait(bar(s, O_FULL), (nt - 1u) & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(tO + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+        tc_fence_before();
+        mbar_arrive(bar(s, P_FULL));
+      }
+      // ---- epilogue: O / l -> bf16 -> out[token, head] ----
+      mbar_wait(bar(s, O_FULL), (nt - 1u) & 1u);
+      tc_fence_after();
+      const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      const bool row_ok = qp0 + row < w.len;
+      __nv_bfloat16* dst = out + static_cast<size_t>(w.seq0 + qp0 + row) * d + w.h * HD;
+#pragma unroll 1
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[i] = pack_bf16(__uint_as_float(v[8 * q4 + 2 * i]) * inv_l, __uint_as_float(v[8 * q4 + 2 * i + 1]) * inv_l);
+            d4[q4] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      // the next unit's first P V (accumulate = 0) overwrites O only after this warpgroup's p_full arrivals, which
+      // follow these loads in program order
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int HD>
+static int launch_attention_ws(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale, int window,
+                               int max_seqlen, const float* alibi, cudaStream_t stream) {
+  using Cfg = AttnWsCfg<HD>;
+  CUtensorMap map;
+  int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
+  if (rc != SGPT_OK) return rc;
+  auto kern = attention_ws_kernel<HD>;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
+    SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const int QT = (max_seqlen + kAttnTile - 1) / kAttnTile;
+  const long long units = static_cast<long long>(QT) * B * H;
+  long long ctas = (units + 1) / 2;
+  if (ctas > sm_count()) ctas = sm_count();
+  if (ctas < 1) ctas = 1;
+  const float sl2 = scale * 1.4426950408889634f;
+  LaunchScope _ls(kCatAttention, stream);
+  SGPT_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(ctas)), dim3(320), Cfg::kSmemBytes, stream, map,
+                                static_cast<__nv_bfloat16*>(out), cu, B, H, QT, sl2, window, alibi));
+  return SGPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // SIMT cross-check: one warp per (token, head); lanes split the head dimension; fp32 online softmax.
 // ---------------------------------------------------------------------------------------------------------------
 template <int HD>
@@ -475,6 +818,15 @@ static int launch_attention_simt(const void* qkv, void* out, const int32_t* cu, 
 
 using namespace sgpt;
 
+// SGPT_ATTN_IMPL=legacy routes impl 0 to the one-CTA-per-unit kernel (A/B measurements)
+static bool attention_legacy_forced() {
+  static const bool v = [] {
+    const char* e = getenv("SGPT_ATTN_IMPL");
+    return e != nullptr && e[0] == 'l';
+  }();
+  return v;
+}
+
 extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seqlens, int B, int T, int H, int hd,
                               float scale, int window, int max_seqlen, const float* alibi_slopes, int impl,
                               sgpt_stream_t stream_) {
@@ -485,7 +837,13 @@ extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seql
   SGPT_REQUIRE(window >= 0, "sgpt_attention: window must be >= 0");
   SGPT_REQUIRE(max_seqlen > 0 || T == 0, "sgpt_attention: max_seqlen must be positive");
   if (B == 0 || T == 0) return SGPT_OK;
-  if (impl == 0) {
+  if (impl == 0 && hd != 256 && !attention_legacy_forced()) {
+    // warp-specialised persistent kernel (two work slots per CTA); head_dim 256 (GPT-J) keeps the one-CTA-per-unit kernel
+    SGPT_REQUIRE(static_cast<long long>(B) * H * ((max_seqlen + 127) / 128) < (1ll << 30), "sgpt_attention: too many work units");
+    if (hd == 64) return launch_attention_ws<64>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, alibi_slopes, stream);
+    return launch_attention_ws<128>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, alibi_slopes, stream);
+  }
+  if (impl == 0 || impl == 2) {
     SGPT_REQUIRE(H <= 65535 && B <= 65535, "sgpt_attention: grid limits exceeded (B=%d H=%d)", B, H);
     switch (hd) {
       case 64: return launch_attention_tc<64>(qkv, out, cu_seqlens, B, T, H, scale, window, max_seqlen, alibi_slopes, stream);

@@ -2,6 +2,8 @@
 // similarity (S1) and its threshold-filter variant used by the fused search (search.cu).
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 #include "../../include/sgpt_b200.h"
 #include "gemm_api.h"
 #include "host_utils.h"
@@ -289,6 +291,10 @@ extern "C" int sgpt_linear_resid_ln(const void* x, int64_t ldx, const void* w, i
   p.bias = bias;
   p.stats = reinterpret_cast<float2*>(stats_out);
   p.P = (N + 127) / 128;
+  {
+    static const int l2pf = [] { const char* e = getenv("SGPT_RESID_L2_PREFETCH"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+    p.l2_prefetch = l2pf;
+  }
   // always 256-wide tiles: each epilogue warp then owns exactly one 128-column statistics group
   return M > kGemmBM ? launch_gemm<256, EpiResidLn, 2>(x, ldx, w, ldw, M, N, K, p, stream)
                      : launch_gemm<256, EpiResidLn, 1>(x, ldx, w, ldw, M, N, K, p, stream);

@@ -52,6 +52,11 @@ struct GemmCfg {
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
+template <class Epi, class = void>
+struct EpiHasPrefetch { static constexpr bool value = false; };
+template <class Epi>
+struct EpiHasPrefetch<Epi, decltype((void)&Epi::prefetch_next)> { static constexpr bool value = true; };
+
 // Epilogues may state a total staging size (kStagingBytes member); 0 / absent = the default rule of GemmCfg.
 template <class Epi, class = void>
 struct EpiStaging { static constexpr int value = 0; };
@@ -243,7 +248,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int tile = cid; tile < num_tiles; tile += ncl) {
       const int m0 = ((tile / n_tiles) * CL + static_cast<int>(crank)) * kGemmBM + ew * 32;  // this warp's 32-row slab
       const int n0 = tmap.map(tile % n_tiles) * BN + half * kColsPerWarp;
-      // work that does not depend on the accumulator (EpiResidLn: the first residual loads) overlaps the mainloop
+      // work that does not depend on the accumulator (EpiResidLn: the first residual loads, and an L2 prefetch of the
+      // residual boxes of the tile after this one) overlaps the mainloop
+      if constexpr (EpiHasPrefetch<Epi>::value) {
+        const int nt = tile + ncl;
+        if (nt < num_tiles)
+          Epi::prefetch_next(ep, ((nt / n_tiles) * CL + static_cast<int>(crank)) * kGemmBM + ew * 32,
+                             tmap.map(nt % n_tiles) * BN + half * kColsPerWarp, lane, M, N);
+      }
       Epi::template pre_tile<kColsPerWarp, kSlabBytes>(st, ep, m0, n0, lane, stage_slab, M, N);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -565,6 +577,7 @@ struct EpiResidLn {
     const float* bias;      // may be null
     float2* stats;          // [M, P]
     int P;
+    int l2_prefetch;        // prefetch the NEXT tile's residual boxes into L2 one tile ahead (hides the HBM latency)
   };
   struct State {
     uint32_t it;     // residual boxes processed so far by this warp (selects the load buffer and its barrier phase)
@@ -584,6 +597,12 @@ struct EpiResidLn {
   }
   static __device__ __forceinline__ void finish(State&, const Params&, int lane_row) {
     if ((lane_row & 31) == 0) bulk_wait_group<0>();
+  }
+  // called right before pre_tile of the current tile with the coordinates of the tile AFTER it
+  static __device__ __forceinline__ void prefetch_next(const Params& p, int m0, int n0, int lane, int M, int N) {
+    if (!p.l2_prefetch || m0 >= M || lane != 0) return;
+    const int nb = boxes(n0, N, 128);
+    for (int j = 0; j < nb; ++j) tma_prefetch_l2_2d(&p.resid_map, n0 + 32 * j, m0);
   }
   static __device__ __forceinline__ int boxes(int n0, int N, int cols) {
     if (n0 >= N) return 0;

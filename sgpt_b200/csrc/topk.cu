@@ -61,6 +61,17 @@ __device__ __forceinline__ long long list_len(const TopkSrc& s, int q, int g) {
 }
 
 constexpr int kTopkThreads = 1024;
+
+// Sum of `v` over the 1024 threads of the CTA, returned to every thread; ONE barrier per call (scratch double-buffered by
+// call parity: a buffer is rewritten two calls later, i.e. after the barrier of the call in between).
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t (*buf)[32], uint32_t& parity, int lane, int warp) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  if (lane == 0) buf[parity][warp] = v;
+  __syncthreads();
+  const uint32_t t = __reduce_add_sync(0xffffffffu, buf[parity][lane]);
+  parity ^= 1u;
+  return t;
+}
 constexpr int kBins = 2048;
 
 constexpr int kMaxFlatLists = 1024;
@@ -190,7 +201,80 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   uint32_t prefix = 0, mask = 0, need = kk;
   uint32_t sub_n = 0;
   bool use_sub = false;  // digits 2 and 3 run over the compacted survivors of digit 1 instead of all keys
-  if (kk > 0) {
+  // ---- fast path (all keys cached in shared memory) ------------------------------------------------------------------
+  // Histogram passes cost ~3 shared-memory atomics / warp-matches per key (ncu r2_1: 7 k instructions per warp, 80 us per
+  // launch at 38 k keys).  Instead: (1) a 1024-key strided SAMPLE (one key per thread) gives, by a 32-round bitwise
+  // search with block-wide counts, a pivot `lo` that is below the k-th largest key with overwhelming probability but
+  // keeps only a few k / n of the keys; (2) ONE pass compacts the keys >= lo (with their flat positions) into a short
+  // list and counts them — the count proves the pivot valid, otherwise the histogram path below takes over; (3) the
+  // exact k-th key is found by the same bitwise search on the short list (<= 4 keys per thread, in registers).
+  uint2* sub_kj = reinterpret_cast<uint2*>(sub_key);  // (key, flat index) pairs, kSubCap / 2 entries
+  constexpr uint32_t kSubPairs = kSubCap / 2;
+  __shared__ uint32_t s_red[2][32];
+  uint32_t red_par = 0;
+  bool fast_done = false;
+  if (cached && kk > 0) {
+    uint32_t lo_key = 1u;  // smallest valid key: keeps everything
+    if (total > kSubPairs) {
+      const uint32_t step = flat_total / kTopkThreads;  // >= 1 here (flat_total >= total > 4096)
+      const uint32_t skeyv = ckeys[static_cast<uint32_t>(tid) * step];
+      // expected rank of the k-th key inside the sample, plus ~4 sigma of the sampling noise
+      const float er = static_cast<float>(kk) * static_cast<float>(kTopkThreads) / static_cast<float>(total);
+      const uint32_t rank = static_cast<uint32_t>(er + 4.0f * sqrtf(er) + 4.0f);
+      if (rank < static_cast<uint32_t>(kTopkThreads)) {
+        uint32_t pv = 0;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+          const uint32_t cand = pv | (1u << bit);
+          if (block_sum(skeyv >= cand ? 1u : 0u, s_red, red_par, lane, warp) >= rank) pv = cand;
+        }
+        lo_key = pv > 0u ? pv : 1u;  // the rank-th largest sampled key
+      }
+    }
+    // (2) compaction of the keys >= lo_key
+    if (tid == 0) s_sub_n = 0;
+    __syncthreads();
+    for (uint32_t j0 = 0; j0 < flat_total; j0 += kTopkThreads) {  // flat_total is a multiple of 32: warps stay converged
+      const uint32_t j = j0 + tid;
+      const uint32_t key = (j < flat_total) ? ckeys[j] : 0u;
+      const bool keep = key >= lo_key && key != 0u;
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (m != 0u) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s_sub_n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+        if (keep && slot < kSubPairs) sub_kj[slot] = make_uint2(key, j);
+      }
+    }
+    __syncthreads();
+    sub_n = s_sub_n;
+    if (sub_n >= kk && sub_n <= kSubPairs) {
+      // (3) exact kk-th largest key of the short list: <= 4 keys per thread in registers
+      uint32_t kr[kSubPairs / kTopkThreads];
+#pragma unroll
+      for (uint32_t i = 0; i < kSubPairs / kTopkThreads; ++i) {
+        const uint32_t e = tid + i * kTopkThreads;
+        kr[i] = e < sub_n ? sub_kj[e].x : 0u;
+      }
+      uint32_t pv = 0;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = pv | (1u << bit);
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < kSubPairs / kTopkThreads; ++i) c += (kr[i] >= cand) ? 1u : 0u;
+        if (block_sum(c, s_red, red_par, lane, warp) >= kk) pv = cand;
+      }
+      prefix = pv;
+      uint32_t cgt = 0;
+#pragma unroll
+      for (uint32_t i = 0; i < kSubPairs / kTopkThreads; ++i) cgt += (kr[i] > pv) ? 1u : 0u;
+      need = kk - block_sum(cgt, s_red, red_par, lane, warp);  // winners among the keys equal to the kk-th key
+      fast_done = true;
+    }
+  }
+  if (kk > 0 && !fast_done) {
     const int shifts[3] = {21, 10, 0};
     const uint32_t widths[3] = {11, 11, 10};
 #pragma unroll 1
@@ -278,7 +362,33 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
         }
       }
     };
-    if (cached) {
+    if (fast_done) {
+      // winners come from the short list; their ids are fetched afterwards by ONE thread per winner
+      for (uint32_t e = tid; e < sub_n; e += kTopkThreads) {
+        const uint2 kj = sub_kj[e];
+        if (kj.x > prefix) {
+          const uint32_t slot = atomicAdd(&s_cnt_gt, 1u);
+          skey[slot] = kj.x;
+          sid[slot] = static_cast<long long>(kj.y);  // flat position for now
+        } else if (kj.x == prefix) {
+          const uint32_t e2 = atomicAdd(&s_cnt_eq, 1u);
+          if (e2 < need) {
+            skey[n_gt + e2] = kj.x;
+            sid[n_gt + e2] = static_cast<long long>(kj.y);
+          }
+        }
+      }
+      __syncthreads();
+      for (uint32_t t = tid; t < kk; t += kTopkThreads) {
+        const uint32_t j = static_cast<uint32_t>(sid[t]);
+        int lo = 0, hi = src.G;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_off[mid] <= j) lo = mid; else hi = mid;
+        }
+        sid[t] = load_elem(src, q, lo, static_cast<long long>(j - s_off[lo])).id;
+      }
+    } else if (cached) {
       for (uint32_t j = tid; j < flat_total; j += kTopkThreads) {
         const uint32_t key = ckeys[j];
         if (key == 0 || key < prefix) continue;
