@@ -322,6 +322,20 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// The same, MULTICAST: the tile lands at this smem offset in every CTA of `cta_mask`; each destination CTA's complete_tx is
+// delivered to the mbarrier at `bar_addr`'s CTA-relative offset in the LEADER (even-ranked CTA) of the destination's own
+// pair — bar_addr is the shared::cluster address of the barrier in the ISSUING CTA's pair leader (mapa).  Used by the
+// 4-CTA cluster GEMM: two CTA pairs share every weight tile, fetched from L2 once.
+__device__ __forceinline__ void tma_load_2d_pair_multicast(void* smem_dst, const CUtensorMap* desc, uint32_t bar_addr,
+                                                           int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 //   [4,6) D format (1 = f32)   [7,10) A format (1 = bf16)   [10,13) B format (1 = bf16)
 //   [15] A major (0 = K)       [16] B major (0 = K, 1 = MN) [17,23) N >> 3            [24,29) M >> 4

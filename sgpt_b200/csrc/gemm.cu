@@ -19,7 +19,8 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   int rc = make_tma_2d_bf16(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
                             kGemmBM, kGemmBK);
   if (rc != SGPT_OK) return rc;
-  // in a CTA pair each CTA fetches (and holds) half of the B tile
+  // in a CTA pair each CTA holds half of the B tile; with two pairs per cluster (CL = 4) it fetches a quarter and
+  // receives the other quarter of its half by multicast from the CTA of its parity in the other pair
   rc = make_tma_2d_bf16(&tb, b, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), BN / CL,
                         kGemmBK);
   if (rc != SGPT_OK) return rc;
@@ -33,14 +34,38 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles;  // tile groups (one per cluster iteration)
   if (tiles == 0) return SGPT_OK;
   long long clusters = sm_count() / CL;
-  if (tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
   cfg.blockDim = dim3(128 + 32 * Epi::kEpiWarps);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
+  if (CL == 4) {
+    // 4-CTA clusters cannot use every SM (GPCs whose SM count is not a multiple of 4): ask how many fit at once
+    static int max_clusters[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && max_clusters[dev] == 0) {
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3(static_cast<unsigned>(clusters * CL));
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = static_cast<int>(clusters);
+      }
+      max_clusters[dev] = n;
+    }
+    if (dev >= 0 && dev < 64 && max_clusters[dev] > 0 && max_clusters[dev] < clusters) clusters = max_clusters[dev];
+  }
+  if (tiles < clusters) clusters = tiles;
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
   if (CL > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = CL;
@@ -60,15 +85,27 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   return SGPT_OK;
 }
 
+// SGPT_GEMM_CL4=0 disables the 4-CTA (two pairs, multicast weights) clusters (A/B measurements)
+static bool cl4_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("SGPT_GEMM_CL4");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return v;
+}
+
 // nn.Linear dispatch: tile width by wave efficiency; CTA pairs (cta_group::2, M = 256) whenever there are at least two
-// M-tiles — a third less L2->SM and smem traffic per FLOP than independent CTAs.
+// M-tiles — a third less L2->SM and smem traffic per FLOP than independent CTAs; two pairs per cluster sharing the weight
+// tile by multicast (another quarter less L2->SM traffic) when there are at least four M-tiles and 256-wide tiles.
 template <class Epi>
 static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                          const typename Epi::Params& p, int bn, cudaStream_t stream) {
   const bool pair = M > kGemmBM;
-  if (bn == 256)
+  if (bn == 256) {
+    if (M >= 4 * kGemmBM && cl4_enabled()) return launch_gemm<256, Epi, 4>(x, ldx, w, ldw, M, N, K, p, stream);
     return pair ? launch_gemm<256, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream)
                 : launch_gemm<256, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream);
+  }
   return pair ? launch_gemm<128, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream)
               : launch_gemm<128, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream);
 }
@@ -296,6 +333,7 @@ extern "C" int sgpt_linear_resid_ln(const void* x, int64_t ldx, const void* w, i
     p.l2_prefetch = l2pf;
   }
   // always 256-wide tiles: each epilogue warp then owns exactly one 128-column statistics group
+  if (M >= 4 * kGemmBM && cl4_enabled()) return launch_gemm<256, EpiResidLn, 4>(x, ldx, w, ldw, M, N, K, p, stream);
   return M > kGemmBM ? launch_gemm<256, EpiResidLn, 2>(x, ldx, w, ldw, M, N, K, p, stream)
                      : launch_gemm<256, EpiResidLn, 1>(x, ldx, w, ldw, M, N, K, p, stream);
 }

@@ -35,7 +35,7 @@ constexpr int kStageBytesPerWarp = 8192;  // per epilogue warp: 2 TMA boxes of 3
 template <int BN, int CL = 1, int kStagingOverride = 0>
 struct GemmCfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
-  static constexpr int kBBytes = (BN / CL) * kGemmBK * 2;  // a CTA pair splits the B tile between its two CTAs
+  static constexpr int kBBytes = (BN / (CL >= 2 ? 2 : 1)) * kGemmBK * 2;  // a CTA pair splits the B tile between its two CTAs
   static constexpr int kStageBytes = kABytes + kBBytes;    // 48 / 32 KB (single CTA, BN 256 / 128); 32 / 24 KB (pair)
   static constexpr int kBarrierBytes = 512;
   // epilogue staging: 4 KB boxes, one per epilogue warp behind the 48 KB stages, two (double-buffered) otherwise; an
@@ -100,13 +100,21 @@ struct TileMap {
 //   Barrier protocol: full[s] (leader, 1 arrive + 2 x stage bytes) <- both producers' TMA; empty[s] (each CTA, count 1)
 //   <- leader's tcgen05.commit multicast; tmem_full[a] (each CTA) <- commit multicast; tmem_empty[a] (leader, count
 //   2 x epilogue warps) <- both CTAs' epilogue warps (remote arrive from the peer).
+// CL = 4: TWO CTA pairs (ranks {0,1} and {2,3}) on the same N-tile and adjacent 256-row M-groups.  At K = 768 the
+//   CL = 2 mainloop is bound by the L2 -> SM operand stream (64 B/clk/SM at the tensor peak against the ~43 B/clk/SM the
+//   L2 delivers: ncu l1tex__m_xbar2l1tex_read_bytes 12.9 TB/s), not by the tensor pipe.  Both pairs need the SAME weight
+//   tile, so every CTA fetches only a QUARTER of it (BN/4 rows) and multicasts it into its own smem and into the smem of
+//   the CTA of the same parity in the other pair: per k-block the four CTAs read 64 KB of A + 32 KB of B from L2 instead
+//   of 64 + 64 (-25 %).  Each pair still runs its own cta_group::2 MMA from its own leader; a smem stage is written by
+//   CTAs of BOTH pairs, so empty[s] counts one commit from each pair's leader (multicast to all four CTAs).
 template <int BN, class Epi, int CL = 1>
 __global__ void __launch_bounds__(128 + 32 * Epi::kEpiWarps, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
                     int N, int K, const __grid_constant__ typename Epi::Params ep, TileMap tmap) {
   using Cfg = GemmCfg<BN, CL, EpiStaging<Epi>::value>;
   constexpr int kStages = Cfg::kStages;
-  static_assert(CL == 1 || CL == 2, "cluster size");
+  static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
+  constexpr bool kPair = CL >= 2;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -127,7 +135,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   // 0/1 the epilogue's issue time added directly to the MMA time of every tile).
   constexpr int kWarpProducer = Epi::kEpiWarps, kWarpMma = Epi::kEpiWarps + 1, kWarpTmem = Epi::kEpiWarps + 2;
 
-  const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;  // position inside the cluster = M-tile of the pair
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;  // position inside the cluster = M-tile of the group
+  const uint32_t prank = crank & 1u;                       // rank inside the CTA pair; leader = crank & ~1
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;      // cluster index / number of clusters
   const int m_tiles = ((M + kGemmBM - 1) / kGemmBM + CL - 1) / CL;  // M-tile groups (CL tiles each)
   const int n_tiles = tmap.count((N + BN - 1) / BN);                // N-tiles this launch visits
@@ -141,16 +150,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL == 4 ? 2 : 1);  // CL = 4: both pairs must have consumed the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], CL * Epi::kEpiWarps);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tmem_empty_bar[i], (kPair ? 2 : 1) * Epi::kEpiWarps);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == kWarpTmem) {
-    if (CL == 2) {
+    if (kPair) {
       tmem_alloc_pair(tmem_holder, Cfg::kTmemCols);
       tmem_relinquish_pair();
     } else {
@@ -159,7 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   }
   tc_fence_before();
-  if (CL == 2) cluster_sync_all();  // peer barriers / TMEM must exist before any remote arrive, commit or pair MMA
+  if (kPair) cluster_sync_all();  // peer barriers / TMEM must exist before any remote arrive, commit or pair MMA
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
@@ -180,12 +189,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (CL == 2) {
-            // my A rows and my half of the B tile land in MY smem; the bytes are accounted on the leader's barrier
-            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          if (kPair) {
+            // my A rows and my half of the B tile land in MY smem; the bytes are accounted on the pair leader's barrier
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), crank & ~1u);
+            if (prank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             tma_load_2d_pair(sa, &tma_a, leader_full, kb * kGemmBK, m0);
-            tma_load_2d_pair(sb, &tma_b, leader_full, kb * kGemmBK, n0 + static_cast<int>(crank) * (BN / 2));
+            if (CL == 2) {
+              tma_load_2d_pair(sb, &tma_b, leader_full, kb * kGemmBK, n0 + static_cast<int>(prank) * (BN / 2));
+            } else {
+              // quarter (crank >> 1) of my pair-rank's half of the weight tile, multicast to the CTA of my parity in both
+              // pairs (same smem offset there); each destination accounts the bytes on ITS pair leader's full barrier
+              const int quarter = static_cast<int>(crank >> 1);
+              tma_load_2d_pair_multicast(sb + quarter * (BN / 4) * 128, &tma_b, leader_full,
+                                         kb * kGemmBK, n0 + static_cast<int>(prank) * (BN / 2) + quarter * (BN / 4),
+                                         static_cast<uint16_t>(0x5u << prank));
+            }
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * kGemmBK, m0);
@@ -197,8 +215,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM * CL, BN, false);
+    if (lane == 0 && prank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM * (kPair ? 2 : 1), BN, false);
+      // commit masks: my pair's two CTAs; the smem stages of a 4-CTA cluster are shared by both pairs
+      const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (crank & ~1u));
+      const uint16_t stage_mask = (CL == 4) ? static_cast<uint16_t>(0xF) : pair_mask;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -217,16 +238,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-            if (CL == 2) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (kPair) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
-          if (CL == 2) umma_commit_pair(&empty_bar[stage], 0x3);
+          if (kPair) umma_commit_pair(&empty_bar[stage], stage_mask);
           else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if (CL == 2) umma_commit_pair(&tmem_full_bar[acc], 0x3);
+        if (kPair) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
         else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -240,7 +261,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     constexpr int kColsPerWarp = BN / (Epi::kEpiWarps / 4);
     constexpr int kSlabBytes = Cfg::kStagingBytes / Epi::kEpiWarps;
     float* stage_slab = stage_base + warp * (kSlabBytes / 4);
-    const uint32_t leader_tmem_empty0 = (CL == 2) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    const uint32_t leader_tmem_empty0 = kPair ? mapa_shared(smem_u32(&tmem_empty_bar[0]), crank & ~1u) : 0u;
     typename Epi::State st;
     Epi::init(st, ep, ew * 32 + lane, epi_bars + 2 * warp);
     int acc = 0;
@@ -264,7 +285,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CL == 2) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
+        if (kPair) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
         else mbar_arrive(&tmem_empty_bar[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -277,11 +298,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 
   tc_fence_before();
-  if (CL == 2) cluster_sync_all();  // the peer may still multicast-arrive on this CTA's barriers until it is done too
+  if (kPair) cluster_sync_all();  // the peers may still multicast-arrive on this CTA's barriers until they are done too
   else __syncthreads();
   if (warp == kWarpTmem) {
     tc_fence_after();
-    if (CL == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
     else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
@@ -289,19 +310,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------
 // TMA epilogue driver: TMEM -> registers (thread = row) -> Op (bias / activation) -> swizzled smem box -> TMA
 // ---------------------------------------------------------------------------------------------------------------
+template <class Row>
 struct EpiTmaState {
   uint32_t it;  // boxes issued so far by this warp (selects the double buffer)
+  Row row;      // per-row constants of the CURRENT tile (LayerNorm mean / rstd), fetched in pre_tile: the loads overlap
+                // the wait for the accumulator instead of sitting at the head of the epilogue's critical path
 };
 
 template <class Op, int kDebug = 0>  // kDebug: 1 = skip the TMA store (timing experiment), 2 = skip the smem-reuse wait
 struct EpiTma {
   using Params = typename Op::Params;
-  using State = EpiTmaState;
+  using State = EpiTmaState<typename Op::Row>;
   static constexpr int kEpiWarps = 8;                 // 2 warps per TMEM lane quarter; each owns ONE 4 KB smem box
   static constexpr int kCols = 128 / Op::kElemBytes;  // columns per 128-byte row segment: 64 (bf16) or 32 (fp32)
   static __device__ __forceinline__ void init(State& st, const Params&, int, uint64_t*) { st.it = 0; }
   template <int BN, int kSlabBytes>
-  static __device__ __forceinline__ void pre_tile(State&, const Params&, int, int, int, float*, int, int) {}
+  static __device__ __forceinline__ void pre_tile(State& st, const Params& p, int m0, int, int lane, float*, int M, int) {
+    if (m0 < M) st.row = Op::row_init(p, m0 + lane, M);
+  }
   static __device__ __forceinline__ void finish(State&, const Params&, int lane_row) {
     if ((lane_row & 31) == 0) bulk_wait_group<0>();  // all stores of this warp have fully completed
   }
@@ -311,7 +337,7 @@ struct EpiTma {
                                               float* slab, int M, int N) {
     if (m0 >= M) return;  // whole 32-row slab out of range (warp-uniform)
     const uint32_t sbase = smem_u32(slab);
-    const typename Op::Row rc = Op::row_init(p, m0 + lane, M);  // per-row constants (thread = row): LayerNorm mean / rstd
+    const typename Op::Row rc = st.row;  // per-row constants (thread = row), fetched in pre_tile
 #pragma unroll 1
     for (int c = 0; c < BN; c += kCols) {
       const int n = n0 + c;
