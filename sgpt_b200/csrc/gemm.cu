@@ -85,11 +85,14 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   return SGPT_OK;
 }
 
-// SGPT_GEMM_CL4=0 disables the 4-CTA (two pairs, multicast weights) clusters (A/B measurements)
+// SGPT_GEMM_CL4=1 enables the 4-CTA (two pairs, multicast weights) clusters.  Measured on B200 (profiles/
+// r02_gemm_epilogues_cl4_vs_cl2.jsonl): correct, but 3-8 % SLOWER than plain pairs on every encoder shape — the mainloop
+// is not bound by the L2 -> SM stream the multicast relieves but by the per-SM shared-memory fill, which is unchanged —
+// so it stays off by default.
 static bool cl4_enabled() {
   static const bool v = [] {
     const char* e = getenv("SGPT_GEMM_CL4");
-    return !(e != nullptr && e[0] == '0');
+    return e != nullptr && e[0] == '1';
   }();
   return v;
 }
