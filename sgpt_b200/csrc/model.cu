@@ -11,12 +11,16 @@
 // of at most cfg.max_tokens rows:
 //     resid fp32[T,d] | xb bf16[T,d] | qkv bf16[T,3d] | attn bf16[T,d] | ffn bf16[T,ff] | stats fp32[2T*P+B]
 //
-// LayerNorm never runs as a pass of its own inside the blocks.  The kernels that WRITE the residual stream (token
-// embedding; out-proj / c_proj epilogues, gemm.cuh EpiResidLn) also leave xb = bf16(resid) and per-row partial sums
-// (sum x, sum x^2 per 128 columns); the GEMMs that consume LN(resid) (QKV, c_fc) run on xb with gamma folded into their
-// weight columns and apply  y = r (xb W'^T) - r mu c + b'  per row in the epilogue (gemm.cuh OpTmaLnBiasActBF16); ln_f is
-// folded into the pooling kernel the same way.  The folded weights W', column sums c and biases b' are built once in
-// sgpt_model_create (the caller's w_qkv / w_fc / LayerNorm tensors are not referenced afterwards).
+// Two block flows (chosen when the handle is created):
+//   default         LayerNorm as its own HBM pass (fp32 residual -> bf16), GEMMs with bias / gelu / reduce-add epilogues.
+//   SGPT_LN_FOLD=1  no LayerNorm pass inside the blocks: the kernels that WRITE the residual stream (token embedding;
+//                   out-proj / c_proj epilogues, gemm.cuh EpiResidLn) also leave xb = bf16(resid) and per-row partial sums
+//                   (sum x, sum x^2 per 128 columns); the GEMMs that consume LN(resid) (QKV, c_fc) run on xb with gamma folded
+//                   into their weight columns and apply  y = r (xb W'^T) - r mu c + b'  per row in the epilogue
+//                   (OpTmaLnBiasActBF16); ln_f is folded into the pooling kernel the same way.  Parity-tested like the
+//                   default, and measured SLOWER on every config (profiles/r02_gemm_epilogues_*.jsonl): the
+//                   step is power-capped, every instruction and every byte the GEMM epilogues move costs as much time as
+//                   the 30 us LayerNorm pass it replaces — the folded c_fc epilogue alone loses 36 us of 135.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,6 +38,7 @@ struct sgpt_model {
   float* resid = nullptr;
   void* xn = nullptr;  // xb: bf16 copy of the residual stream
   int P = 0;           // statistics groups per row = ceil(d / 128)
+  bool ln_fold = false;  // SGPT_LN_FOLD=1 at creation
   float* sumsq = nullptr;
   // LayerNorm-folded parameters per layer (library-owned)
   std::vector<void*> wq_f, wfc_f;
@@ -110,10 +115,14 @@ extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_
   if (e == cudaSuccess) e = cudaMalloc(&m->attn, T * d * 2);
   if (e == cudaSuccess) e = cudaMalloc(&m->ffn, T * static_cast<size_t>(cfg->d_ff) * 2);
   m->P = (cfg->d_model + 127) / 128;
+  {
+    const char* lf = getenv("SGPT_LN_FOLD");
+    m->ln_fold = (lf != nullptr && lf[0] == '1');
+  }
   if (e == cudaSuccess) e = cudaMalloc(&m->stats, (2 * T * m->P + static_cast<size_t>(cfg->max_batch)) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&m->sumsq, static_cast<size_t>(cfg->max_batch) * 4);
   // fold ln_1 into the QKV projection and ln_2 (GPT-J: ln_1 again) into the MLP's first layer
-  for (int l = 0; l < cfg->n_layer && e == cudaSuccess; ++l) {
+  for (int l = 0; l < cfg->n_layer && e == cudaSuccess && m->ln_fold; ++l) {
     const sgpt_layer_weights& lw = m->layers[l];
     const size_t ff = static_cast<size_t>(cfg->d_ff);
     void *wq = nullptr, *wf = nullptr;
@@ -226,6 +235,7 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
   if (c.arch == SGPT_ARCH_BLOOM)
     SGPT_TRY(sgpt_layernorm_f32_inplace(m->resid, m->w.emb_ln_g, m->w.emb_ln_b, T, d, c.ln_eps, stream));
   const int n_run = layer_idx;  // hidden_states[i] is the input of block i; hidden_states[L] is ln_f(output of block L-1)
+  if (m->ln_fold) {
   // bf16 copy + LayerNorm partial sums of the embedded residual stream; inside the blocks the residual epilogues keep
   // both up to date
   SGPT_TRY(sgpt_resid_stats(m->resid, m->xn, m->stats, T, d, stream));
@@ -264,18 +274,55 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
       SGPT_TRY(sgpt_linear_resid_ln(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, m->xn, m->stats, T, d, ff, stream));
     }
   }
+  } else {
+    for (int l = 0; l < n_run && l < c.n_layer; ++l) {
+      const sgpt_layer_weights& lw = m->layers[l];
+      if (all_layers)  // hidden_states[l] = the residual stream entering block l (no ln_f)
+        SGPT_TRY(sgpt_pool_accumulate(m->resid, pos, cu_seqlens, nullptr, nullptr, c.ln_eps, out, nullptr, B, T, d,
+                                      base_mode, clamp_denominator, 0, /*accumulate=*/l > 0, layer_scale, stream));
+      SGPT_TRY(sgpt_layernorm(m->resid, lw.ln1_g, lw.ln1_b, m->xn, T, d, c.ln_eps, stream));
+      if (c.arch == SGPT_ARCH_GPT_NEO) {
+        SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
+        const int window = (lw.local_attention && c.window > 0 && max_seqlen > c.window) ? c.window : 0;
+        SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, /*scale=*/1.0f, window, max_seqlen, nullptr, 0,
+                                stream));
+        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
+        SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
+        SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
+        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+                             stream));
+      } else if (c.arch == SGPT_ARCH_GPTJ) {
+        SGPT_TRY(sgpt_linear_qkv_rotary(m->xn, d, lw.w_qkv, m->qkv, pos, m->rotary, T, d, hd, c.rotary_dim, c.max_pos,
+                                        stream));
+        SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, inv_sqrt_hd, 0, max_seqlen, nullptr, 0, stream));
+        // both branches read the same ln_1 output and are accumulated into the residual stream (attn + mlp + residual)
+        SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
+        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
+        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+                             stream));
+      } else {  // BLOOM
+        SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
+        SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, inv_sqrt_hd, 0, max_seqlen, m->alibi, 0, stream));
+        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
+        SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
+        SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
+        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+                             stream));
+      }
+    }
+  }
   if (pool_mode == kNoPooling) return SGPT_OK;
   const bool final_ln = (layer_idx == c.n_layer);
-  if (final_ln) {
+  if (final_ln && m->ln_fold) {
     // ln_f folded into the pooling kernel; its row statistics come from the partial sums the last c_proj (or the
     // embedding, for a 0-layer run) left behind: ONE pass over the residual stream
     SGPT_TRY(sgpt_pool_partials(m->resid, pos, cu_seqlens, m->w.lnf_g, m->w.lnf_b, c.ln_eps, pool_w, pool_w ? m->n_pool_w : 0,
-                                out, m->stats, P, m->sumsq, B, T, d, base_mode, clamp_denominator, normalize,
+                                out, m->stats, m->P, m->sumsq, B, T, d, base_mode, clamp_denominator, normalize,
                                 /*accumulate=*/all_layers && c.n_layer > 0, layer_scale, stream));
   } else {
     // (the partial sums are dead after the last block: the scratch only hosts the normalisation's per-row sums here)
-    SGPT_TRY(sgpt_pool_ex(m->resid, pos, cu_seqlens, nullptr, nullptr, c.ln_eps, pool_w, pool_w ? m->n_pool_w : 0, out,
-                          m->stats, B, T, d, base_mode, clamp_denominator, normalize,
+    SGPT_TRY(sgpt_pool_ex(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr, c.ln_eps,
+                          pool_w, pool_w ? m->n_pool_w : 0, out, m->stats, B, T, d, base_mode, clamp_denominator, normalize,
                           /*accumulate=*/all_layers && c.n_layer > 0, layer_scale, stream));
   }
   return SGPT_OK;

@@ -68,12 +68,16 @@ class Encoder:
         self._keep = []  # device tensors the C handle borrows
         sd = {(k[len("transformer."):] if k.startswith("transformer.") else k): v for k, v in state_dict.items()}
 
-        consumed = []  # tensors sgpt_model_create folds into library-owned buffers (LayerNorm parameters, q/k/v and
-        # first-MLP-layer weights and biases: csrc/model.cu) — released as soon as the handle exists
+        # SGPT_LN_FOLD=1 (csrc/model.cu): sgpt_model_create folds LayerNorm parameters, q/k/v and first-MLP-layer weights
+        # and biases into library-owned buffers; those tensors are released as soon as the handle exists
+        import os
+
+        ln_fold = os.environ.get("SGPT_LN_FOLD", "0")[:1] == "1"
+        consumed = []
 
         def dev(t, dtype, keep=True):
             x = t.detach().to(device=self.device, dtype=dtype).contiguous()
-            (self._keep if keep else consumed).append(x)
+            (self._keep if (keep or not ln_fold) else consumed).append(x)
             return x
 
         def p32(name, keep=True):

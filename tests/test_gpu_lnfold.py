@@ -105,3 +105,35 @@ def test_linear_resid_ln(M, K, N, with_bias):
                                      st.data_ptr(), M, N, K, L.current_stream()))
     want2 = want + x.double() @ w.double().T + (bias.double() if with_bias else 0.0)
     assert (rd.cpu().double() - want2).abs().max().item() < 4e-3 * max(1.0, want2.abs().max().item())
+
+
+def test_ln_fold_block_flow_matches_reference_fixture(golden_dir, monkeypatch):
+    """The opt-in block flow without LayerNorm passes (SGPT_LN_FOLD=1, csrc/model.cu) against the same HF fixture as the
+    default flow: pooled embeddings within 1e-3 cosine, all-layer pooling modes, and the two flows agree with each other."""
+    import os
+
+    import numpy as np
+
+    from oracle import gpt_neo
+    from sgpt_b200 import Encoder
+    from tests.helpers import min_row_cosine
+    from tests.test_gpu_parity import _cfg_from_spec, _spec_from
+
+    z = np.load(os.path.join(golden_dir, "neo_tiny.npz"))
+    spec = _spec_from(z)
+    w = gpt_neo.init_weights(spec, seed=int(z["weight_seed"]))
+    ids, mask = z["input_ids"], z["attention_mask"]
+    outs = {}
+    for fold in ("0", "1"):
+        monkeypatch.setenv("SGPT_LN_FOLD", fold)
+        enc = Encoder(_cfg_from_spec(spec), w, device="cuda:0", max_tokens=4096, max_batch=64)
+        outs[fold] = {m: enc.encode_tokens(ids, mask, method=m).cpu() for m in ("weightedmean", "mean", "meanmean", "lasttoken")}
+        outs[fold]["mid"] = enc.encode_tokens(ids, mask, method="weightedmean", layer_idx=int(z["mid_layer"])).cpu()
+        outs[fold]["norm"] = enc.encode_tokens(ids, mask, method="weightedmean", normalize=True).cpu()
+        enc.close()
+    assert min_row_cosine(outs["1"]["weightedmean"], z["pooled_weightedmean"]) > 1 - 1e-3
+    assert min_row_cosine(outs["1"]["mean"], z["pooled_mean"]) > 1 - 1e-3
+    assert min_row_cosine(outs["1"]["mid"], z["pooled_weightedmean_mid"]) > 1 - 1e-3
+    for k in outs["0"]:
+        assert min_row_cosine(outs["1"][k], outs["0"][k]) > 1 - 2e-4, k
+    assert torch.allclose(outs["1"]["norm"].norm(dim=1), torch.ones(len(ids)), atol=1e-5)
