@@ -59,6 +59,7 @@ int sgpt_layernorm(const float* x, const float* gamma, const float* beta, void* 
 #define SGPT_EPI_BF16 0
 #define SGPT_EPI_GELU_BF16 1
 #define SGPT_EPI_RESID_F32 2
+#define SGPT_EPI_RESID_BF16 3 /* out bf16[M,N] += acc + bias, in place (resid == out): bf16 residual stream */
 int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out, int64_t ldo,
                 const float* resid, int M, int N, int K, int epilogue, sgpt_stream_t stream);
 
@@ -309,6 +310,23 @@ void sgpt_gather_destroy(sgpt_gather_t g);
 int sgpt_search_gather(sgpt_gather_t g, const void* Q, const void* C, const float* q_scale, const float* c_scale,
                        int nq, int64_t n, int D, int k, int64_t id_base, const int64_t* exclude_ids, float* out_scores,
                        int64_t* out_ids, void* ws, int64_t ws_bytes, sgpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Residual stream in bf16 (SGPT_RESID_BF16=1 when the model handle is created; default fp32).  HF keeps hidden_states in
+ * the model dtype, i.e. bf16 for the reference's bf16 configs (BASELINE configs 3-5); the `_ex` entry points take the
+ * residual stream as `const void*` + a flag.  sgpt_linear(..., SGPT_EPI_RESID_BF16) adds into it with a bf16 TMA reduce.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int sgpt_embed_tokens_ex(const int32_t* ids, const int32_t* pos, const void* wte, const void* wpe, void* resid, int T,
+                         int d, int vocab, int max_pos, int resid_bf16, sgpt_stream_t stream);
+int sgpt_layernorm_ex(const void* x, int x_bf16, const float* gamma, const float* beta, void* y, int T, int d, float eps,
+                      sgpt_stream_t stream);
+int sgpt_layernorm_gather_ex(const void* x, int x_bf16, const int32_t* row_idx, const float* gamma, const float* beta,
+                             void* y, int M, int d, float eps, sgpt_stream_t stream);
+int sgpt_pool_ex2(const void* x, int x_bf16, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                  const float* beta, float eps, const float* pos_weights, int n_pos_weights, float* out,
+                  float* row_stats_ws, int B, int T, int d, int mode, int clamp_denominator, int normalize,
+                  int accumulate, float out_scale, sgpt_stream_t stream);
+int sgpt_bf16_to_f32(const void* x, float* y, int64_t count, sgpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * LayerNorm without a pass of its own (F2 fused into F3 / F6 / F7).  HF applies ln_1 / ln_2 as separate modules

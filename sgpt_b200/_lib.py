@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsgpt_b200.so")
 
 SGPT_OK = 0
-EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32 = 0, 1, 2
+EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_RESID_BF16 = 0, 1, 2, 3
 POOL_MEAN, POOL_WEIGHTEDMEAN, POOL_LASTTOKEN, POOL_MEANMEAN, POOL_LASTTOKENMEAN = 0, 1, 2, 3, 4
 ARCH_GPT_NEO, ARCH_GPTJ, ARCH_BLOOM = 0, 1, 2
 ACT_IDENTITY, ACT_TANH, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
@@ -73,6 +73,11 @@ _SIGNATURES = {
     "sgpt_profile_read": (i32, [vp, vp, vp]),
     "sgpt_profile_gemm_clock": (i32, [vp, vp]),
     "sgpt_search": (i32, [vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, vp, vp, i64, vp]),
+    "sgpt_embed_tokens_ex": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "sgpt_layernorm_ex": (i32, [vp, i32, vp, vp, vp, i32, i32, f32, vp]),
+    "sgpt_layernorm_gather_ex": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, f32, vp]),
+    "sgpt_pool_ex2": (i32, [vp, i32, vp, vp, vp, vp, f32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "sgpt_bf16_to_f32": (i32, [vp, vp, i64, vp]),
     "sgpt_fold_layernorm": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "sgpt_resid_stats": (i32, [vp, vp, vp, i32, i32, vp]),
     "sgpt_linear_lnfold": (i32, [vp, i64, vp, i64, vp, vp, vp, i32, f32, vp, i64, i32, i32, i32, i32, vp]),

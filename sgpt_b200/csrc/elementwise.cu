@@ -9,13 +9,23 @@
 
 namespace sgpt {
 
+// Four consecutive elements of a residual-stream row: the stream is fp32 (default) or bf16 (SGPT_RESID_BF16=1, the storage
+// the reference's own bf16 checkpoints use: HF keeps hidden_states in the model dtype).  idx4 counts groups of 4 elements.
+__device__ __forceinline__ float4 ld_row4(const void* x, size_t idx4, int is_bf16) {
+  if (is_bf16) {
+    const uint2 u = reinterpret_cast<const uint2*>(x)[idx4];
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  return reinterpret_cast<const float4*>(x)[idx4];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // F1: resid[t, :] = wte[ids[t], :] (+ wpe[pos[t], :])        one warp-wide 16-B vector per thread-iteration
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos,
                                                     const uint4* __restrict__ wte, const uint4* __restrict__ wpe,
                                                     float4* __restrict__ resid, int T, int d8, int vocab,
-                                                    int max_pos) {
+                                                    int max_pos, int out_bf16) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
   // d8 = d / 8: number of 16-B bf16 vectors per row.  Grid-stride over (token, vector).
   const long long total = static_cast<long long>(T) * d8;
@@ -35,9 +45,14 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
       f[0] += bf16_lo(q.x); f[1] += bf16_hi(q.x); f[2] += bf16_lo(q.y); f[3] += bf16_hi(q.y);
       f[4] += bf16_lo(q.z); f[5] += bf16_hi(q.z); f[6] += bf16_lo(q.w); f[7] += bf16_hi(q.w);
     }
-    float4* dst = resid + (static_cast<size_t>(t) * d8 + v) * 2;
-    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+    if (out_bf16) {
+      reinterpret_cast<uint4*>(resid)[static_cast<size_t>(t) * d8 + v] =
+          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    } else {
+      float4* dst = resid + (static_cast<size_t>(t) * d8 + v) * 2;
+      dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+      dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
   }
 }
 
@@ -68,7 +83,7 @@ __device__ __forceinline__ void ln_store(float4* y, size_t idx, float o0, float 
 }
 
 template <int TPR, int V, class OutT>
-__device__ __forceinline__ void layernorm_body(const float4* x, const float4* __restrict__ g,
+__device__ __forceinline__ void layernorm_body(const void* x, int x_bf16, const float4* __restrict__ g,
                                                const float4* __restrict__ b, OutT* y, int T, int d4, float eps,
                                                const int32_t* __restrict__ src_rows = nullptr) {
   constexpr int ROWS = 256 / TPR;
@@ -84,7 +99,7 @@ __device__ __forceinline__ void layernorm_body(const float4* x, const float4* __
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = l + i * TPR;
-    v[i] = (active && c < d4) ? x[static_cast<size_t>(src) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = (active && c < d4) ? ld_row4(x, static_cast<size_t>(src) * d4 + c, x_bf16) : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float inv_d = 1.0f / static_cast<float>(d4 * 4);
@@ -116,22 +131,22 @@ __device__ __forceinline__ void layernorm_body(const float4* x, const float4* __
 }
 
 template <int TPR, int V>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ g,
-                                                        const float4* __restrict__ b, uint2* __restrict__ y, int T,
-                                                        int d4, float eps) {
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* x, const float4* __restrict__ g,
+                                                        const float4* __restrict__ b, uint2* y, int T,
+                                                        int d4, float eps, int x_bf16) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
-  layernorm_body<TPR, V>(x, g, b, y, T, d4, eps);
+  layernorm_body<TPR, V>(x, x_bf16, g, b, y, T, d4, eps);  // (bf16 in: y may alias x — a thread rewrites only what it read)
 }
 
 // LayerNorm of a gathered subset of rows: y[m,:] = LN(x[rows[m],:]) (the LM-head input of the cross-encoder scorer)
 template <int TPR, int V>
-__global__ void __launch_bounds__(256) layernorm_gather_kernel(const float4* __restrict__ x,
+__global__ void __launch_bounds__(256) layernorm_gather_kernel(const void* __restrict__ x,
                                                                const float4* __restrict__ g,
                                                                const float4* __restrict__ b, uint2* __restrict__ y,
                                                                int M, int d4, float eps,
-                                                               const int32_t* __restrict__ rows) {
+                                                               const int32_t* __restrict__ rows, int x_bf16) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
-  layernorm_body<TPR, V>(x, g, b, y, M, d4, eps, rows);
+  layernorm_body<TPR, V>(x, x_bf16, g, b, y, M, d4, eps, rows);
 }
 
 // fp32 output, may run in place (each thread rewrites exactly the elements it read)
@@ -140,13 +155,13 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float4* x, con
                                                             const float4* __restrict__ b, float4* y, int T, int d4,
                                                             float eps) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
-  layernorm_body<TPR, V>(x, g, b, y, T, d4, eps);
+  layernorm_body<TPR, V>(x, 0, g, b, y, T, d4, eps);
 }
 
 // Row statistics only (mean, rstd) -> stats[2*t], used by the pooling kernel to apply ln_f on the fly.
 template <int TPR, int V>
-__global__ void __launch_bounds__(256) row_stats_kernel(const float4* __restrict__ x, float2* __restrict__ stats,
-                                                        int T, int d4, float eps) {
+__global__ void __launch_bounds__(256) row_stats_kernel(const void* __restrict__ x, float2* __restrict__ stats,
+                                                        int T, int d4, float eps, int x_bf16) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
   constexpr int ROWS = 256 / TPR;
   __shared__ float scratch[ROWS * (TPR / 32) + 1];
@@ -159,7 +174,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float4* __restrict
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = l + i * TPR;
-    v[i] = (active && c < d4) ? x[static_cast<size_t>(row) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = (active && c < d4) ? ld_row4(x, static_cast<size_t>(row) * d4 + c, x_bf16) : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float inv_d = 1.0f / static_cast<float>(d4 * 4);
@@ -263,13 +278,13 @@ __global__ void __launch_bounds__(256) fold_layernorm_kernel(const __nv_bfloat16
 //   With ln_f:  sum_t w_t ((x_t - mu_t) r_t g + b) = g * sum_t w_t r_t (x_t - mu_t) + b * W.
 //   w_t = pos_t + 1 (weightedmean), pw[pos_t] (learnt WeightedMeanPooling), 1 (mean) or [t is last] (lasttoken).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x, const int32_t* __restrict__ pos,
+__global__ void __launch_bounds__(128) pool_kernel(const void* __restrict__ x, const int32_t* __restrict__ pos,
                                                    const float* __restrict__ pw, int n_pw,
                                                    const int32_t* __restrict__ cu, const float2* __restrict__ stats,
                                                    const float4* __restrict__ g, const float4* __restrict__ bta,
                                                    float4* __restrict__ out, float* __restrict__ sumsq, int d4,
                                                    int mode, int clamp_den, int accumulate, float out_scale,
-                                                   int n_partials, float eps) {
+                                                   int n_partials, float eps, int x_bf16) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
   __shared__ float4 part[4][32];
   __shared__ float wpart[4];
@@ -291,7 +306,7 @@ __global__ void __launch_bounds__(128) pool_kernel(const float4* __restrict__ x,
     else w = 1.f;
     wsum += w;
     if (w != 0.f && col_ok) {
-      float4 v = x[static_cast<size_t>(t) * d4 + col];
+      float4 v = ld_row4(x, static_cast<size_t>(t) * d4 + col, x_bf16);
       if (stats != nullptr) {
         // n_partials == 0: stats[t] = (mean, rstd) from row_stats_kernel; > 0: the partial sums left by the kernel that
         // wrote the residual stream (no separate pass over it)
@@ -387,6 +402,15 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const uint2* __restrict__ x, float4* __restrict__ y, long long n4) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint2 u = x[i];
+    y[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+}
+
 // one warp per row; D % 8 == 0
 __global__ void __launch_bounds__(256) row_inv_norm_kernel(const uint4* __restrict__ x, float* __restrict__ inv,
                                                            long long n, int d8) {
@@ -468,6 +492,12 @@ using namespace sgpt;
 
 extern "C" int sgpt_embed_tokens(const int32_t* ids, const int32_t* pos, const void* wte, const void* wpe,
                                  float* resid, int T, int d, int vocab, int max_pos, sgpt_stream_t stream_) {
+  return sgpt_embed_tokens_ex(ids, pos, wte, wpe, resid, T, d, vocab, max_pos, 0, stream_);
+}
+
+extern "C" int sgpt_embed_tokens_ex(const int32_t* ids, const int32_t* pos, const void* wte, const void* wpe,
+                                    void* resid, int T, int d, int vocab, int max_pos, int resid_bf16,
+                                    sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(T >= 0 && d > 0 && d % 8 == 0, "sgpt_embed_tokens: d=%d must be a positive multiple of 8", d);
   SGPT_REQUIRE(wpe == nullptr || pos != nullptr, "sgpt_embed_tokens: pos required when wpe is given");
@@ -476,35 +506,45 @@ extern "C" int sgpt_embed_tokens(const int32_t* ids, const int32_t* pos, const v
   LaunchScope _ls(kCatEmbed, stream);
   SGPT_CHECK_CUDA(launch_kernel(embed_kernel, dim3(grid_for(static_cast<long long>(T) * d8, 256)), dim3(256), 0, stream,
                                 ids, pos, static_cast<const uint4*>(wte), static_cast<const uint4*>(wpe),
-                                reinterpret_cast<float4*>(resid), T, d8, vocab, max_pos));
+                                reinterpret_cast<float4*>(resid), T, d8, vocab, max_pos, resid_bf16));
   return SGPT_OK;
 }
 
 extern "C" int sgpt_layernorm(const float* x, const float* gamma, const float* beta, void* y, int T, int d,
                               float eps, sgpt_stream_t stream_) {
+  return sgpt_layernorm_ex(x, 0, gamma, beta, y, T, d, eps, stream_);
+}
+
+extern "C" int sgpt_layernorm_ex(const void* x, int x_bf16, const float* gamma, const float* beta, void* y, int T, int d,
+                                 float eps, sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(T >= 0 && d > 0 && d % 4 == 0, "sgpt_layernorm: d=%d must be a positive multiple of 4", d);
   if (T == 0) return SGPT_OK;
   const int d4 = d / 4;
   LaunchScope _ls(kCatLayerNorm, stream);
-  SGPT_ROW_DISPATCH(layernorm_kernel, d4, T, stream, reinterpret_cast<const float4*>(x),
+  SGPT_ROW_DISPATCH(layernorm_kernel, d4, T, stream, x,
                     reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
-                    static_cast<uint2*>(y), T, d4, eps);
+                    static_cast<uint2*>(y), T, d4, eps, x_bf16);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }
 
 extern "C" int sgpt_layernorm_gather(const float* x, const int32_t* row_idx, const float* gamma, const float* beta, void* y,
                                      int M, int d, float eps, sgpt_stream_t stream_) {
+  return sgpt_layernorm_gather_ex(x, 0, row_idx, gamma, beta, y, M, d, eps, stream_);
+}
+
+extern "C" int sgpt_layernorm_gather_ex(const void* x, int x_bf16, const int32_t* row_idx, const float* gamma,
+                                        const float* beta, void* y, int M, int d, float eps, sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGPT_REQUIRE(M >= 0 && d > 0 && d % 4 == 0, "sgpt_layernorm_gather: d=%d must be a positive multiple of 4", d);
   SGPT_REQUIRE(row_idx != nullptr, "sgpt_layernorm_gather: rows required");  // (`rows` is a local of the macro below)
   if (M == 0) return SGPT_OK;
   const int d4 = d / 4;
   LaunchScope _ls(kCatLayerNorm, stream);
-  SGPT_ROW_DISPATCH(layernorm_gather_kernel, d4, M, stream, reinterpret_cast<const float4*>(x),
+  SGPT_ROW_DISPATCH(layernorm_gather_kernel, d4, M, stream, x,
                     reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta),
-                    static_cast<uint2*>(y), M, d4, eps, row_idx);
+                    static_cast<uint2*>(y), M, d4, eps, row_idx, x_bf16);
   SGPT_CHECK_CUDA(cudaGetLastError());
   return SGPT_OK;
 }
@@ -524,18 +564,18 @@ extern "C" int sgpt_layernorm_f32_inplace(float* x, const float* gamma, const fl
 }
 
 // shared launcher: `stats` is either (mean, rstd) per row (n_partials == 0) or the [T, n_partials] partial sums
-static int pool_launch(const float* x, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma, const float* beta,
-                       float eps, const float* pos_weights, int n_pos_weights, float* out, const float2* stats,
-                       int n_partials, float* sumsq, int B, int d, int mode, int clamp_denominator, int normalize,
-                       int accumulate, float out_scale, cudaStream_t stream) {
+static int pool_launch(const void* x, int x_bf16, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                       const float* beta, float eps, const float* pos_weights, int n_pos_weights, float* out,
+                       const float2* stats, int n_partials, float* sumsq, int B, int d, int mode, int clamp_denominator,
+                       int normalize, int accumulate, float out_scale, cudaStream_t stream) {
   const int d4 = d / 4;
   if (normalize) SGPT_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * B, stream));
   dim3 grid(B, (d4 + 31) / 32);
-  SGPT_CHECK_CUDA(launch_kernel(pool_kernel, grid, dim3(128), 0, stream, reinterpret_cast<const float4*>(x), pos,
+  SGPT_CHECK_CUDA(launch_kernel(pool_kernel, grid, dim3(128), 0, stream, x, pos,
                                 pos_weights, n_pos_weights, cu_seqlens, stats, reinterpret_cast<const float4*>(gamma),
                                 reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(out),
                                 normalize ? sumsq : nullptr, d4, mode, clamp_denominator, accumulate, out_scale,
-                                n_partials, eps));
+                                n_partials, eps, x_bf16));
   if (normalize) {
     SGPT_CHECK_CUDA(launch_kernel(l2_scale_rows_kernel, dim3(grid_for(static_cast<long long>(B) * d4, 256)), dim3(256),
                                   0, stream, reinterpret_cast<float4*>(out), sumsq, B, d4));
@@ -559,6 +599,14 @@ extern "C" int sgpt_pool_ex(const float* x, const int32_t* pos, const int32_t* c
                             const float* beta, float eps, const float* pos_weights, int n_pos_weights, float* out,
                             float* row_stats_ws, int B, int T, int d, int mode, int clamp_denominator, int normalize,
                             int accumulate, float out_scale, sgpt_stream_t stream_) {
+  return sgpt_pool_ex2(x, 0, pos, cu_seqlens, gamma, beta, eps, pos_weights, n_pos_weights, out, row_stats_ws, B, T, d, mode,
+                       clamp_denominator, normalize, accumulate, out_scale, stream_);
+}
+
+extern "C" int sgpt_pool_ex2(const void* x, int x_bf16, const int32_t* pos, const int32_t* cu_seqlens, const float* gamma,
+                             const float* beta, float eps, const float* pos_weights, int n_pos_weights, float* out,
+                             float* row_stats_ws, int B, int T, int d, int mode, int clamp_denominator, int normalize,
+                             int accumulate, float out_scale, sgpt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = pool_check(pos, gamma, beta, pos_weights, n_pos_weights, d, mode);
   if (rc != SGPT_OK) return rc;
@@ -569,12 +617,12 @@ extern "C" int sgpt_pool_ex(const float* x, const int32_t* pos, const int32_t* c
   const int d4 = d / 4;
   const float2* stats = nullptr;
   if (gamma != nullptr && T > 0) {
-    SGPT_ROW_DISPATCH(row_stats_kernel, d4, T, stream, reinterpret_cast<const float4*>(x),
-                      reinterpret_cast<float2*>(row_stats_ws), T, d4, eps);
+    SGPT_ROW_DISPATCH(row_stats_kernel, d4, T, stream, x,
+                      reinterpret_cast<float2*>(row_stats_ws), T, d4, eps, x_bf16);
     SGPT_CHECK_CUDA(cudaGetLastError());
     stats = reinterpret_cast<const float2*>(row_stats_ws);
   }
-  return pool_launch(x, pos, cu_seqlens, gamma, beta, eps, pos_weights, n_pos_weights, out, stats, 0,
+  return pool_launch(x, x_bf16, pos, cu_seqlens, gamma, beta, eps, pos_weights, n_pos_weights, out, stats, 0,
                      normalize ? row_stats_ws + 2 * static_cast<size_t>(T) : nullptr, B, d, mode, clamp_denominator,
                      normalize, accumulate, out_scale, stream);
 }
@@ -595,7 +643,7 @@ extern "C" int sgpt_pool_partials(const float* x, const int32_t* pos, const int3
   SGPT_REQUIRE(!normalize || sumsq_ws != nullptr, "sgpt_pool_partials: normalize needs sumsq_ws");
   if (B == 0) return SGPT_OK;
   LaunchScope _ls(kCatPool, stream);
-  return pool_launch(x, pos, cu_seqlens, gamma, beta, eps, pos_weights, n_pos_weights, out,
+  return pool_launch(x, 0, pos, cu_seqlens, gamma, beta, eps, pos_weights, n_pos_weights, out,
                      reinterpret_cast<const float2*>(partial_stats), n_partials, sumsq_ws, B, d, mode, clamp_denominator,
                      normalize, accumulate, out_scale, stream);
 }
@@ -672,6 +720,16 @@ extern "C" int sgpt_row_inv_norms(const void* x, float* inv_norm, int64_t n, int
   LaunchScope _ls(kCatMisc, stream);
   SGPT_CHECK_CUDA(launch_kernel(row_inv_norm_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream,
                                 static_cast<const uint4*>(x), inv_norm, n, D / 8));
+  return SGPT_OK;
+}
+
+extern "C" int sgpt_bf16_to_f32(const void* x, float* y, int64_t count, sgpt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGPT_REQUIRE(count >= 0 && count % 4 == 0, "sgpt_bf16_to_f32: count must be a multiple of 4");
+  if (count == 0) return SGPT_OK;
+  LaunchScope _ls(kCatMisc, stream);
+  SGPT_CHECK_CUDA(launch_kernel(bf16_to_f32_kernel, dim3(grid_for(count / 4, 256)), dim3(256), 0, stream,
+                                static_cast<const uint2*>(x), reinterpret_cast<float4*>(y), count / 4));
   return SGPT_OK;
 }
 

@@ -207,6 +207,17 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
       EpiResidualF32::Params p{om, bias, out, static_cast<int>(ldo)};
       return launch_linear<EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, bn, stream);
     }
+    case SGPT_EPI_RESID_BF16: {
+      SGPT_REQUIRE(resid != nullptr && static_cast<const void*>(resid) == out,
+                   "sgpt_linear: SGPT_EPI_RESID_BF16 updates the bf16 residual stream in place (resid must alias out)");
+      SGPT_REQUIRE(ldo % 8 == 0, "sgpt_linear: ldo must be a multiple of 8 for bf16 output");
+      CUtensorMap om;
+      int rc = make_tma_2d_bf16(&om, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N),
+                                static_cast<uint64_t>(ldo), 32, 64);
+      if (rc != SGPT_OK) return rc;
+      EpiResidualBF16::Params p{om, bias, out, static_cast<int>(ldo)};
+      return launch_linear<EpiResidualBF16>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+    }
     case 102:
     case 103:
     case 104:

@@ -502,6 +502,39 @@ struct OpTmaResidAddF32 {
   }
 };
 
+// resid_bf16[m, n] += acc + bias[n]     (bf16 residual stream, SGPT_RESID_BF16=1: the add is a bf16 TMA reduce-add
+// performed by the L2 — half the epilogue's shared-memory and HBM traffic of the fp32 stream)
+struct OpTmaResidAddBF16 {
+  static constexpr int kElemBytes = 2;
+  struct Params {
+    CUtensorMap out_map;  // bf16 [M, N], box 32 rows x 64 cols, SWIZZLE_128B
+    const float* bias;    // may be null
+    void* out_ptr;
+    int ldc;
+  };
+  struct Row {};
+  static __device__ __forceinline__ Row row_init(const Params&, int, int) { return Row(); }
+  static __device__ __forceinline__ void chunk(const Params& p, const Row&, const uint32_t* acc, int col, int N,
+                                               int /*row*/, uint32_t (&o)[4]) {
+    float x[8];
+    if (p.bias && col + 8 <= N) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + bb[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + bias_at(p.bias, col + i, N);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+  }
+  static __device__ __forceinline__ void issue(const Params& p, const void* box, int n, int m0) {
+    tma_reduce_add_2d(&p.out_map, box, n, m0);
+  }
+};
+
 // ---- LayerNorm folded into the consumer GEMM -------------------------------------------------------------------------
 // y = LN(x) W^T + b  with  LN(x) = (x - mu) r (*) gamma + beta   is evaluated as
 //     y[t, n] = r_t * (xb W'^T)[t, n] - r_t mu_t * c[n] + b'[n],
@@ -925,6 +958,7 @@ using EpiFilterCandidates = EpiFilterRows;
 template <bool kGelu>
 using EpiBiasActBF16 = EpiTma<OpTmaBiasActBF16<kGelu>>;
 using EpiResidualF32 = EpiTma<OpTmaResidAddF32>;
+using EpiResidualBF16 = EpiTma<OpTmaResidAddBF16>;
 using EpiRotaryBF16 = EpiTma<OpTmaRotaryBF16>;
 template <bool kGelu>
 using EpiLnBiasActBF16 = EpiTma<OpTmaLnBiasActBF16<kGelu>>;

@@ -39,6 +39,7 @@ struct sgpt_model {
   void* xn = nullptr;  // xb: bf16 copy of the residual stream
   int P = 0;           // statistics groups per row = ceil(d / 128)
   bool ln_fold = false;  // SGPT_LN_FOLD=1 at creation
+  bool resid_bf16 = false;  // SGPT_RESID_BF16=1 at creation: residual stream stored in bf16 (default flow only)
   float* sumsq = nullptr;
   // LayerNorm-folded parameters per layer (library-owned)
   std::vector<void*> wq_f, wfc_f;
@@ -118,6 +119,8 @@ extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_
   {
     const char* lf = getenv("SGPT_LN_FOLD");
     m->ln_fold = (lf != nullptr && lf[0] == '1');
+    const char* rb = getenv("SGPT_RESID_BF16");
+    m->resid_bf16 = (rb != nullptr && rb[0] == '1') && !m->ln_fold;
   }
   if (e == cudaSuccess) e = cudaMalloc(&m->stats, (2 * T * m->P + static_cast<size_t>(cfg->max_batch)) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&m->sumsq, static_cast<size_t>(cfg->max_batch) * 4);
@@ -230,10 +233,14 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
   const float inv_sqrt_hd = 1.0f / sqrtf(static_cast<float>(hd));
   m->last_T = T;
 
-  SGPT_TRY(sgpt_embed_tokens(ids, pos, m->w.wte, c.arch == SGPT_ARCH_GPT_NEO ? m->w.wpe : nullptr, m->resid, T, d,
-                             c.vocab, c.max_pos, stream));
-  if (c.arch == SGPT_ARCH_BLOOM)
-    SGPT_TRY(sgpt_layernorm_f32_inplace(m->resid, m->w.emb_ln_g, m->w.emb_ln_b, T, d, c.ln_eps, stream));
+  const int rb = m->resid_bf16 ? 1 : 0;  // residual stream dtype: 0 fp32, 1 bf16 (same buffer, half of it used)
+  const int epi_resid = rb ? SGPT_EPI_RESID_BF16 : SGPT_EPI_RESID_F32;
+  SGPT_TRY(sgpt_embed_tokens_ex(ids, pos, m->w.wte, c.arch == SGPT_ARCH_GPT_NEO ? m->w.wpe : nullptr, m->resid, T, d,
+                                c.vocab, c.max_pos, rb, stream));
+  if (c.arch == SGPT_ARCH_BLOOM) {
+    if (rb) SGPT_TRY(sgpt_layernorm_ex(m->resid, 1, m->w.emb_ln_g, m->w.emb_ln_b, m->resid, T, d, c.ln_eps, stream));
+    else SGPT_TRY(sgpt_layernorm_f32_inplace(m->resid, m->w.emb_ln_g, m->w.emb_ln_b, T, d, c.ln_eps, stream));
+  }
   const int n_run = layer_idx;  // hidden_states[i] is the input of block i; hidden_states[L] is ln_f(output of block L-1)
   if (m->ln_fold) {
   // bf16 copy + LayerNorm partial sums of the embedded residual stream; inside the blocks the residual epilogues keep
@@ -278,18 +285,18 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
     for (int l = 0; l < n_run && l < c.n_layer; ++l) {
       const sgpt_layer_weights& lw = m->layers[l];
       if (all_layers)  // hidden_states[l] = the residual stream entering block l (no ln_f)
-        SGPT_TRY(sgpt_pool_accumulate(m->resid, pos, cu_seqlens, nullptr, nullptr, c.ln_eps, out, nullptr, B, T, d,
-                                      base_mode, clamp_denominator, 0, /*accumulate=*/l > 0, layer_scale, stream));
-      SGPT_TRY(sgpt_layernorm(m->resid, lw.ln1_g, lw.ln1_b, m->xn, T, d, c.ln_eps, stream));
+        SGPT_TRY(sgpt_pool_ex2(m->resid, rb, pos, cu_seqlens, nullptr, nullptr, c.ln_eps, nullptr, 0, out, nullptr, B, T, d,
+                               base_mode, clamp_denominator, 0, /*accumulate=*/l > 0, layer_scale, stream));
+      SGPT_TRY(sgpt_layernorm_ex(m->resid, rb, lw.ln1_g, lw.ln1_b, m->xn, T, d, c.ln_eps, stream));
       if (c.arch == SGPT_ARCH_GPT_NEO) {
         SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
         const int window = (lw.local_attention && c.window > 0 && max_seqlen > c.window) ? c.window : 0;
         SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, /*scale=*/1.0f, window, max_seqlen, nullptr, 0,
                                 stream));
-        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
-        SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
+        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, epi_resid, stream));
+        SGPT_TRY(sgpt_layernorm_ex(m->resid, rb, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
         SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
-        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, epi_resid,
                              stream));
       } else if (c.arch == SGPT_ARCH_GPTJ) {
         SGPT_TRY(sgpt_linear_qkv_rotary(m->xn, d, lw.w_qkv, m->qkv, pos, m->rotary, T, d, hd, c.rotary_dim, c.max_pos,
@@ -297,16 +304,16 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
         SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, inv_sqrt_hd, 0, max_seqlen, nullptr, 0, stream));
         // both branches read the same ln_1 output and are accumulated into the residual stream (attn + mlp + residual)
         SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
-        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
-        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, epi_resid, stream));
+        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, epi_resid,
                              stream));
       } else {  // BLOOM
         SGPT_TRY(sgpt_linear(m->xn, d, lw.w_qkv, d, lw.b_qkv, m->qkv, 3 * d, nullptr, T, 3 * d, d, SGPT_EPI_BF16, stream));
         SGPT_TRY(sgpt_attention(m->qkv, m->attn, cu_seqlens, B, T, H, hd, inv_sqrt_hd, 0, max_seqlen, m->alibi, 0, stream));
-        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, SGPT_EPI_RESID_F32, stream));
-        SGPT_TRY(sgpt_layernorm(m->resid, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
+        SGPT_TRY(sgpt_linear(m->attn, d, lw.w_o, d, lw.b_o, m->resid, d, m->resid, T, d, d, epi_resid, stream));
+        SGPT_TRY(sgpt_layernorm_ex(m->resid, rb, lw.ln2_g, lw.ln2_b, m->xn, T, d, c.ln_eps, stream));
         SGPT_TRY(sgpt_linear(m->xn, d, lw.w_fc, d, lw.b_fc, m->ffn, ff, nullptr, T, ff, d, SGPT_EPI_GELU_BF16, stream));
-        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, SGPT_EPI_RESID_F32,
+        SGPT_TRY(sgpt_linear(m->ffn, ff, lw.w_proj, ff, lw.b_proj, m->resid, d, m->resid, T, d, ff, epi_resid,
                              stream));
       }
     }
@@ -321,7 +328,7 @@ extern "C" int sgpt_encode(sgpt_model_t m, const int32_t* ids, const int32_t* po
                                 /*accumulate=*/all_layers && c.n_layer > 0, layer_scale, stream));
   } else {
     // (the partial sums are dead after the last block: the scratch only hosts the normalisation's per-row sums here)
-    SGPT_TRY(sgpt_pool_ex(m->resid, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr, c.ln_eps,
+    SGPT_TRY(sgpt_pool_ex2(m->resid, rb, pos, cu_seqlens, final_ln ? m->w.lnf_g : nullptr, final_ln ? m->w.lnf_b : nullptr, c.ln_eps,
                           pool_w, pool_w ? m->n_pool_w : 0, out, m->stats, B, T, d, base_mode, clamp_denominator, normalize,
                           /*accumulate=*/all_layers && c.n_layer > 0, layer_scale, stream));
   }
@@ -360,7 +367,8 @@ extern "C" int sgpt_lm_logprobs(sgpt_model_t m, const void* lm_head_w, const flo
   for (int m0 = 0; m0 < M; m0 += rows_per_chunk) {
     const int mc = (M - m0 < rows_per_chunk) ? M - m0 : rows_per_chunk;
     // hidden_states[-1] of the selected positions: ln_f of the residual stream the last sgpt_forward left behind
-    SGPT_TRY(sgpt_layernorm_gather(m->resid, rows + m0, m->w.lnf_g, m->w.lnf_b, xsel, mc, d, m->cfg.ln_eps, stream));
+    SGPT_TRY(sgpt_layernorm_gather_ex(m->resid, m->resid_bf16 ? 1 : 0, rows + m0, m->w.lnf_g, m->w.lnf_b, xsel, mc, d,
+                                      m->cfg.ln_eps, stream));
     SGPT_TRY(sgpt_scores(xsel, lm_head_w, nullptr, nullptr, logits, lds, mc, vocab, d, stream));
     SGPT_TRY(sgpt_token_logprobs(logits, lds, mc, vocab, lm_head_bias, targets + m0, token_logprobs + m0,
                                  greedy ? greedy + m0 : nullptr, stream));
@@ -383,6 +391,7 @@ extern "C" int sgpt_model_read_residual(sgpt_model_t m, float* dst, int64_t capa
   *d = m->cfg.d_model;
   const int64_t n = static_cast<int64_t>(m->last_T) * m->cfg.d_model;
   SGPT_REQUIRE(capacity_elems >= n, "sgpt_model_read_residual: destination too small");
+  if (m->resid_bf16) return sgpt_bf16_to_f32(m->resid, dst, n, stream);
   SGPT_CHECK_CUDA(cudaMemcpyAsync(dst, m->resid, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice,
                                   static_cast<cudaStream_t>(stream)));
   return SGPT_OK;

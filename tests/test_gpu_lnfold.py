@@ -137,3 +137,37 @@ def test_ln_fold_block_flow_matches_reference_fixture(golden_dir, monkeypatch):
     for k in outs["0"]:
         assert min_row_cosine(outs["1"][k], outs["0"][k]) > 1 - 2e-4, k
     assert torch.allclose(outs["1"]["norm"].norm(dim=1), torch.ones(len(ids)), atol=1e-5)
+
+
+def test_bf16_residual_stream_flow_matches_reference_fixture(golden_dir, monkeypatch):
+    """SGPT_RESID_BF16=1: the residual stream stored in bf16 (what HF does for a bf16 checkpoint) instead of fp32 —
+    pooled embeddings vs the HF fp32 fixture within the 1e-3 cosine bar, per-token residual tap still readable."""
+    import os
+
+    import numpy as np
+
+    from oracle import gpt_neo
+    from sgpt_b200 import Encoder
+    from tests.helpers import min_row_cosine
+    from tests.test_gpu_parity import _cfg_from_spec, _spec_from
+
+    z = np.load(os.path.join(golden_dir, "neo_tiny.npz"))
+    spec = _spec_from(z)
+    w = gpt_neo.init_weights(spec, seed=int(z["weight_seed"]))
+    ids, mask = z["input_ids"], z["attention_mask"]
+    monkeypatch.setenv("SGPT_RESID_BF16", "1")
+    enc = Encoder(_cfg_from_spec(spec), w, device="cuda:0", max_tokens=4096, max_batch=64)
+    for method, key in (("weightedmean", "pooled_weightedmean"), ("mean", "pooled_mean")):
+        got = enc.encode_tokens(ids, mask, method=method).cpu()
+        assert min_row_cosine(got, z[key]) > 1 - 1e-3, method
+    got = enc.encode_tokens(ids, mask, method="weightedmean", layer_idx=int(z["mid_layer"])).cpu()
+    assert min_row_cosine(got, z["pooled_weightedmean_mid"]) > 1 - 1e-3
+    sp = np.load(os.path.join(golden_dir, "script_pooling_neo_tiny.npz"))
+    for method in ("meanmean", "lasttokenmean", "lasttoken"):
+        assert min_row_cosine(enc.encode_tokens(ids, mask, method=method).cpu(), sp["pooled_" + method]) > 1 - 1e-3, method
+    enc.encode_tokens(ids, mask)
+    resid = enc.last_residual().cpu()
+    h = gpt_neo.layer_norm(resid, w["ln_f.weight"], w["ln_f.bias"], spec.ln_eps)
+    ref = torch.from_numpy(z["hidden_states"][-1])[torch.from_numpy(mask).bool()]
+    assert torch.nn.functional.cosine_similarity(h.double(), ref.double(), dim=1).min().item() > 1 - 1e-3
+    enc.close()
