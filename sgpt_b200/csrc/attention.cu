@@ -48,13 +48,12 @@ __device__ __forceinline__ RowVis make_row_vis(int qp0, int tid, int len, int wi
 
 // Softmax pass 1 over one 128-key tile whose scores sit in TMEM (thread = query row): the row maximum in the exp2
 // domain, i.e. of s * sl2 (+ slope2 * key_pos with ALiBi), -inf when no key of the tile is visible.
-template <int NCH = 4>
 __device__ __forceinline__ float softmax_tile_max(uint32_t tS_row, int kv0, const RowVis& rv, float sl2, float slope2) {
   const int vis_hi = rv.vis_hi, vis_lo = rv.vis_lo, w_hi_min = rv.w_hi_min, w_hi_max = rv.w_hi_max,
             w_lo_max = rv.w_lo_max, w_lo_min = rv.w_lo_min;
   float mx = -INFINITY, mxa = -INFINITY;  // raw-score maximum (no ALiBi) / scaled+biased maximum (ALiBi)
 #pragma unroll 1
-  for (int c = 0; c < NCH; ++c) {
+  for (int c = 0; c < 4; ++c) {
     const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
     if (c_lo > w_hi_max || c_hi < w_lo_min) continue;  // nothing visible for any row of this warp (warp-uniform)
     uint32_t v[32];
@@ -95,14 +94,13 @@ __device__ __forceinline__ float softmax_tile_max(uint32_t tS_row, int kv0, cons
 
 // Softmax pass 2: p = exp2(s * sl2 (+ ALiBi) - m_use) for the same tile, P -> bf16 -> the thread's row of the swizzled
 // [128 x 128] smem operand (two 64-key sub-tiles); returns the row sum of p.
-template <int NCH = 4>
 __device__ __forceinline__ float softmax_tile_exp(uint32_t tS_row, int kv0, const RowVis& rv, float sl2, float slope2,
                                                   float m_use, uint32_t sP_addr, int tid) {
   const int vis_hi = rv.vis_hi, vis_lo = rv.vis_lo, w_hi_min = rv.w_hi_min, w_hi_max = rv.w_hi_max,
             w_lo_max = rv.w_lo_max, w_lo_min = rv.w_lo_min;
   float lsum = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < NCH; ++c) {
+  for (int c = 0; c < 4; ++c) {
     const int c_lo = kv0 + c * 32, c_hi = c_lo + 31;
     uint32_t pk[16];
     if (c_lo > w_hi_max || c_hi < w_lo_min) {
@@ -408,19 +406,11 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
 template <int HD>
 struct AttnWsCfg {
   static constexpr int kSub = HD / 64;
-  static constexpr int kQBytes = kSub * kSubBytes;            // Q tile [128 x hd]
-  // key tile: 128 keys at hd 64; 64 keys at hd 128, where a 128-key K|V stage pair would leave room for ONE stage per slot
-  // and every tile would wait for its own loads (first version: 2.18 ms per SGPT-1.3B batch, load latency exposed)
-  static constexpr int kKT = (HD == 64) ? 128 : 64;
-  static constexpr int kKvSubBytes = kKT * 128;               // one [kKT keys x 64 dims] sub-tile
-  static constexpr int kKBytes = kSub * kKvSubBytes;          // K (or V) tile [kKT x hd]
-  static constexpr int kPBytes = (kKT / 64) * kSubBytes;      // P [128 x kKT] bf16
-  // hd 64: P over the K tile of its stage (K_j is dead once S_j has completed);  hd 128: P has its own buffer
-  static constexpr bool kPOverK = (HD == 64);
-  static constexpr int kStageBytes = (kPOverK ? (kPBytes > kKBytes ? kPBytes : kKBytes) : kKBytes) + kKBytes;  // { K (|P) , V }
-  static constexpr int kVOff = kStageBytes - kKBytes;
-  static constexpr int kNKV = 2;
-  static constexpr int kSlotBytes = kQBytes + kNKV * kStageBytes + (kPOverK ? 0 : kPBytes);
+  static constexpr int kQBytes = kSub * kSubBytes;            // Q / K / V tile bytes
+  static constexpr int kKPBytes = 2 * kSubBytes;              // K region also hosts P [128 x 128] bf16
+  static constexpr int kStageBytes = kKPBytes + kQBytes;      // { K|P , V }
+  static constexpr int kNKV = (HD == 64) ? 2 : 1;
+  static constexpr int kSlotBytes = kQBytes + kNKV * kStageBytes;
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = 1024 + 2 * kSlotBytes + kBarBytes;
   static constexpr int kTmemCols = 512;
@@ -436,7 +426,6 @@ struct AttnUnit {
 };
 
 // unit number -> work description; false when the unit does not exist (query tile beyond the sequence's length)
-template <int KT>
 __device__ __forceinline__ bool attn_unit(int u, int B, int H, int QT, int window, const int32_t* __restrict__ cu,
                                           AttnUnit& w) {
   const int bh = B * H;
@@ -449,14 +438,13 @@ __device__ __forceinline__ bool attn_unit(int u, int B, int H, int QT, int windo
   const int qp0 = w.qt * kAttnTile;
   if (qp0 >= w.len) return false;
   const int lo_pos = (window > 0) ? max(0, qp0 - window + 1) : 0;
-  w.j_lo = lo_pos / KT;
-  w.j_hi = min(qp0 + kAttnTile - 1, w.len - 1) / KT;  // last key tile any row of the query tile can see
+  w.j_lo = lo_pos / kAttnTile;
+  w.j_hi = w.qt;
   return true;
 }
 
 template <int HD>
 __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv,
-                                                               const __grid_constant__ CUtensorMap tma_kv,
                                                                __nv_bfloat16* __restrict__ out,
                                                                const int32_t* __restrict__ cu, int B, int H, int QT,
                                                                float sl2, int window, const float* __restrict__ alibi) {
@@ -472,13 +460,7 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
   enum { Q_FULL = 0, Q_EMPTY = 1, S_FULL = 2, P_FULL = 3, O_FULL = 4, K_FULL = 5, V_FULL = 5 + NKV, KV_EMPTY = 5 + 2 * NKV };
   auto slot_q = [&](int s) { return smem + s * Cfg::kSlotBytes; };
   auto slot_k = [&](int s, int st) { return smem + s * Cfg::kSlotBytes + Cfg::kQBytes + st * Cfg::kStageBytes; };
-  auto slot_v = [&](int s, int st) { return slot_k(s, st) + Cfg::kVOff; };
-  // P_j: over K_j (hd 64) or in the slot's own buffer behind the stages (hd 128: free again once P V_j has completed,
-  // which the next tile's softmax awaits through o_full before it writes P_{j+1})
-  auto slot_p = [&](int s, int st) {
-    return Cfg::kPOverK ? slot_k(s, st) : smem + s * Cfg::kSlotBytes + Cfg::kQBytes + NKV * Cfg::kStageBytes;
-  };
-  constexpr int KT = Cfg::kKT;
+  auto slot_v = [&](int s, int st) { return slot_k(s, st) + Cfg::kKPBytes; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = H * HD;
@@ -487,7 +469,6 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
-    tma_prefetch_desc(&tma_kv);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(s, Q_FULL), 1);
       mbar_init(bar(s, Q_EMPTY), 1);
@@ -531,7 +512,7 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
         for (int s = 0; s < 2; ++s) {
           if (done[s]) continue;
           if (!have[s]) {
-            while (u[s] < n_units && !attn_unit<Cfg::kKT>(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
+            while (u[s] < n_units && !attn_unit(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
             if (u[s] >= n_units) { done[s] = true; continue; }
             have[s] = true;
             q_sent[s] = false;
@@ -549,14 +530,14 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
           }
           const int st = static_cast<int>(nkv[s] % NKV);
           if (!mbar_try_wait(bar(s, KV_EMPTY + st), ((nkv[s] / NKV) & 1u) ^ 1u)) continue;
-          mbar_expect_tx(bar(s, K_FULL + st), Cfg::kKBytes);
+          mbar_expect_tx(bar(s, K_FULL + st), Cfg::kQBytes);
           for (int x = 0; x < Cfg::kSub; ++x)
-            tma_load_2d(slot_k(s, st) + x * Cfg::kKvSubBytes, &tma_kv, bar(s, K_FULL + st), d + w[s].h * HD + 64 * x,
-                        w[s].seq0 + j[s] * KT);
-          mbar_expect_tx(bar(s, V_FULL + st), Cfg::kKBytes);
+            tma_load_2d(slot_k(s, st) + x * kSubBytes, &tma_qkv, bar(s, K_FULL + st), d + w[s].h * HD + 64 * x,
+                        w[s].seq0 + j[s] * kAttnTile);
+          mbar_expect_tx(bar(s, V_FULL + st), Cfg::kQBytes);
           for (int x = 0; x < Cfg::kSub; ++x)
-            tma_load_2d(slot_v(s, st) + x * Cfg::kKvSubBytes, &tma_kv, bar(s, V_FULL + st), 2 * d + w[s].h * HD + 64 * x,
-                        w[s].seq0 + j[s] * KT);
+            tma_load_2d(slot_v(s, st) + x * kSubBytes, &tma_qkv, bar(s, V_FULL + st), 2 * d + w[s].h * HD + 64 * x,
+                        w[s].seq0 + j[s] * kAttnTile);
           ++nkv[s];
           idle = 0;
           if (++j[s] > w[s].j_hi) {
@@ -569,7 +550,7 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
   } else if (warp == 9) {
     // ===================== MMA issuer (both slots, non-blocking round robin) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, KT, false);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, true);
       int u[2] = {2 * static_cast<int>(blockIdx.x), 2 * static_cast<int>(blockIdx.x) + 1};
       int j[2] = {0, 0};
@@ -586,7 +567,7 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
         for (int s = 0; s < 2; ++s) {
           if (done[s]) continue;
           if (!have[s]) {
-            while (u[s] < n_units && !attn_unit<Cfg::kKT>(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
+            while (u[s] < n_units && !attn_unit(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
             if (u[s] >= n_units) { done[s] = true; continue; }
             have[s] = true;
             j[s] = w[s].j_lo;
@@ -603,8 +584,8 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
             const uint32_t aq = smem_u32(slot_q(s)), ak = smem_u32(slot_k(s, st));
 #pragma unroll
             for (int kk = 0; kk < HD / 16; ++kk) {
-              const uint32_t offq = (kk >> 2) * kSubBytes + (kk & 3) * 32, offk = (kk >> 2) * Cfg::kKvSubBytes + (kk & 3) * 32;
-              umma_bf16_ss(tS, make_smem_desc_sw128(aq + offq, 16, 1024), make_smem_desc_sw128(ak + offk, 16, 1024),
+              const uint32_t off = (kk >> 2) * kSubBytes + (kk & 3) * 32;
+              umma_bf16_ss(tS, make_smem_desc_sw128(aq + off, 16, 1024), make_smem_desc_sw128(ak + off, 16, 1024),
                            idesc_s, kk != 0);
             }
             umma_commit(bar(s, S_FULL));
@@ -619,11 +600,11 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
             if (!mbar_try_wait(bar(s, P_FULL), nt[s] & 1u)) continue;
             if (!mbar_try_wait(bar(s, V_FULL + st), st_par)) continue;
             tc_fence_after();
-            const uint32_t ap = smem_u32(slot_p(s, st)), av = smem_u32(slot_v(s, st));
+            const uint32_t ap = smem_u32(slot_k(s, st)), av = smem_u32(slot_v(s, st));
 #pragma unroll
-            for (int kk = 0; kk < KT / 16; ++kk) {
+            for (int kk = 0; kk < kAttnTile / 16; ++kk) {
               const uint64_t da = make_smem_desc_sw128(ap + (kk >> 2) * kSubBytes + (kk & 3) * 32, 16, 1024);
-              const uint64_t db = make_smem_desc_sw128(av + kk * 2048, Cfg::kKvSubBytes, 1024);
+              const uint64_t db = make_smem_desc_sw128(av + kk * 2048, kSubBytes, 1024);
               umma_bf16_ss(tO, da, db, idesc_o, (j[s] > w[s].j_lo) || (kk != 0));
             }
             umma_commit(bar(s, KV_EMPTY + st));  // the stage (P over K, and V) may be refilled
@@ -648,7 +629,7 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
     uint32_t nt = 0;                    // key tiles completed by this slot
     AttnUnit w;
     for (int u = 2 * static_cast<int>(blockIdx.x) + s; u < n_units; u += stride) {
-      if (!attn_unit<Cfg::kKT>(u, B, H, QT, window, cu, w)) continue;
+      if (!attn_unit(u, B, H, QT, window, cu, w)) continue;
       const int qp0 = w.qt * kAttnTile;
       const float slope2 = (alibi != nullptr) ? __ldg(alibi + w.h) * 1.4426950408889634f : 0.f;
       const RowVis rv = make_row_vis(qp0, row, w.len, window);
@@ -657,40 +638,29 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
         const int st = static_cast<int>(nt % NKV);
         mbar_wait(bar(s, S_FULL), nt & 1u);
         tc_fence_after();
-        const int kv0 = j * KT;
-        const float m_new = fmaxf(m_run, softmax_tile_max<KT / 32>(tS, kv0, rv, sl2, slope2));
+        const int kv0 = j * kAttnTile;
+        const float m_new = fmaxf(m_run, softmax_tile_max(tS, kv0, rv, sl2, slope2));
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
         const float alpha = exp2f(m_run - m_use);
-        // hd 128: the P buffer (and O) belong to the previous tile's P V until it has completed
-        const bool have_prev = j > w.j_lo;
-        if (!Cfg::kPOverK && have_prev) {
+        // P over the K tile of this stage: the S MMAs that read K_j have completed (s_full)
+        const float lsum = softmax_tile_exp(tS, kv0, rv, sl2, slope2, m_use, smem_u32(slot_k(s, st)), row);
+        l_run = l_run * alpha + lsum;
+        m_run = m_new;
+        if (j > w.j_lo) {
+          // O = alpha * O once the previous tile's P V has landed
           mbar_wait(bar(s, O_FULL), (nt - 1u) & 1u);
           tc_fence_after();
-        }
-        // hd 64: P over the K tile of this stage — the S MMAs that read K_j have completed (s_full)
-        const float lsum = softmax_tile_exp<KT / 32>(tS, kv0, rv, sl2, slope2, m_use, smem_u32(slot_p(s, st)), row);
-        l_run = l_run * alpha + lsum;
-        if (have_prev) {
-          // O = alpha * O once the previous tile's P V has landed; skipped by a warp whose 32 rows all kept their maximum
-          // (alpha == 1 exactly) — the usual case after the first key tiles of a row
-          if (Cfg::kPOverK) {
-            mbar_wait(bar(s, O_FULL), (nt - 1u) & 1u);
-            tc_fence_after();
-          }
-          if (__any_sync(0xffffffffu, m_new != m_run)) {
 #pragma unroll 1
-            for (int c = 0; c < HD / 32; ++c) {
-              uint32_t v[32];
-              tmem_ld_32x32(tO + c * 32, v);
-              tmem_ld_wait();
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st_32x32(tO + c * 32, v);
-            }
-            tmem_st_wait();
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(tO + c * 32, v);
           }
+          tmem_st_wait();
         }
-        m_run = m_new;
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
         tc_fence_before();
         mbar_arrive(bar(s, P_FULL));
@@ -735,10 +705,8 @@ template <int HD>
 static int launch_attention_ws(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale, int window,
                                int max_seqlen, const float* alibi, cudaStream_t stream) {
   using Cfg = AttnWsCfg<HD>;
-  CUtensorMap map, map_kv;
+  CUtensorMap map;
   int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
-  if (rc != SGPT_OK) return rc;
-  rc = make_tma_2d_bf16(&map_kv, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, Cfg::kKT, 64);
   if (rc != SGPT_OK) return rc;
   auto kern = attention_ws_kernel<HD>;
   static PerDeviceOnce attr_once;
@@ -751,7 +719,7 @@ static int launch_attention_ws(const void* qkv, void* out, const int32_t* cu, in
   if (ctas < 1) ctas = 1;
   const float sl2 = scale * 1.4426950408889634f;
   LaunchScope _ls(kCatAttention, stream);
-  SGPT_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(ctas)), dim3(320), Cfg::kSmemBytes, stream, map, map_kv,
+  SGPT_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(ctas)), dim3(320), Cfg::kSmemBytes, stream, map,
                                 static_cast<__nv_bfloat16*>(out), cu, B, H, QT, sl2, window, alibi));
   return SGPT_OK;
 }
@@ -872,7 +840,8 @@ extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seql
   if (impl == 0 && hd != 256 && max_seqlen > 128 && !attention_legacy_forced()) {
     // Warp-specialised persistent kernel (two work slots per CTA) for sequences of more than one key tile: measured
     // 1.5-1.7x the one-CTA-per-unit kernel (SGPT-1.3B 64 x 256: 3.76 -> 2.18 ms per batch, bloom-7b1 32 x 300: 8.74 ->
-    // 5.83 ms).  head_dim 256 (GPT-J: one slot would fill the SM's smem) and batches whose sequences all fit ONE key tile
+    // 5.83 ms; a variant with 64-key tiles double-buffered at hd 128 and a 4-slot single-tile variant both measured slower
+    // and were dropped).  head_dim 256 (GPT-J: one slot would fill the SM's smem) and batches whose sequences all fit ONE key tile
     // (there four co-resident single-tile CTAs per SM beat two slots: 0.745 vs 0.886 ms per 125M step) keep the
     // one-CTA-per-unit kernel.
     SGPT_REQUIRE(static_cast<long long>(B) * H * ((max_seqlen + 127) / 128) < (1ll << 30), "sgpt_attention: too many work units");

@@ -173,47 +173,19 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   __syncthreads();
   const bool cached = (src.G <= kMaxFlatLists) && (s_off[src.G <= kMaxFlatLists ? src.G : 0] <= cache_keys);
   const uint32_t flat_total = cached ? s_off[src.G] : 0u;
-  uint32_t loaded_valid = 0;
   if (cached) {
-    // Every 32-entry segment of the flat (padded) index space belongs to ONE list: a segment -> list table lets a warp
-    // fetch any segment with no search, and the segments of a warp (seg = warp, warp + 32, ...) are independent loads —
-    // eight are kept in flight per thread.  (One warp per LIST, the previous scheme, left the ~9 lists of a warp strictly
-    // one after the other: ~9 dependent L2 round trips per selection.)
-    uint16_t* seg_list = reinterpret_cast<uint16_t*>(hist);  // kBins * 4 B = 4096 segments; hist is cleared before use
+    // one warp per list; the iterations are independent, so the loads of several chunks are in flight together
     for (int g = warp; g < src.G; g += kTopkThreads / 32) {
-      const uint32_t s0 = s_off[g] >> 5, s1 = s_off[g + 1] >> 5;
-      for (uint32_t sgi = s0 + lane; sgi < s1; sgi += 32) seg_list[sgi] = static_cast<uint16_t>(g);
-    }
-    __syncthreads();
-    const uint32_t nseg = flat_total >> 5;
-#pragma unroll 1
-    for (uint32_t sg0 = warp; sg0 < nseg; sg0 += 8 * (kTopkThreads / 32)) {
-      uint32_t kk8[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const uint32_t sgi = sg0 + r * (kTopkThreads / 32);
-        kk8[r] = 0u;
-        if (sgi < nseg) {
-          const int g = seg_list[sgi];
-          const uint32_t i = (sgi << 5) - s_off[g] + lane;
-          if (i < s_len[g]) kk8[r] = load_elem(src, q, g, i).key;
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const uint32_t sgi = sg0 + r * (kTopkThreads / 32);
-        if (sgi < nseg) {
-          ckeys[(sgi << 5) + lane] = kk8[r];
-          loaded_valid += (kk8[r] != 0u);
-        }
-      }
+      const uint32_t len = s_len[g], base = s_off[g], end = (len + 31u) & ~31u;
+#pragma unroll 4
+      for (uint32_t i = lane; i < end; i += 32) ckeys[base + i] = (i < len) ? load_elem(src, q, g, i).key : 0u;
     }
     __syncthreads();
   }
   {
     uint32_t local = 0;
     if (cached) {
-      local = loaded_valid;
+      for (uint32_t j = tid; j < flat_total; j += kTopkThreads) local += (ckeys[j] != 0);
     } else if (src.ids == nullptr) {
       for (int g = tid; g < src.G; g += kTopkThreads) local += static_cast<uint32_t>(list_len(src, q, g));
     } else {
