@@ -382,6 +382,38 @@ def other_config_legs(dev, pk, lib, steps):
     return out
 
 
+def cublas_same_shapes(dev):
+    """CALIBRATION ONLY (not a product path): what the vendor library reaches on the four linear shapes of one SGPT-125M
+    block at batch 256 x 128 (torch.nn.functional.linear, bf16, bias only — no gelu, no residual), each shape looped back
+    to back for ~0.3 s so that it runs under the same sustained power state as the bench step.  MEASURED_PEAKS.json's
+    cuBLAS figure is an 8192^3 GEMM; K = 768 shapes cannot reach it in any implementation, so this is the like-for-like
+    denominator for `roofline.achieved`."""
+    M, d, ff = B * S, CFG["d_model"], CFG["d_ff"]
+    out, tot_flops, tot_s = {}, 0.0, 0.0
+    for name, N, K in (("qkv", 3 * d, d), ("out_proj", d, d), ("c_fc", ff, d), ("c_proj", d, ff)):
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.05
+        b = torch.randn(N, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            torch.nn.functional.linear(x, w, b)
+        torch.cuda.synchronize()
+        n = max(20, int(0.3 / (2.0 * M * N * K / 1.2e15)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            torch.nn.functional.linear(x, w, b)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) / 1e3 / n
+        out[name] = {"us": 1e6 * sec, "tflops": 2.0 * M * N * K / sec / 1e12}
+        tot_flops += 2.0 * M * N * K
+        tot_s += sec
+        del x, w, b
+    out["block_tflops"] = tot_flops / tot_s / 1e12
+    out["note"] = "torch F.linear (cuBLASLt) bf16 + bias, linear only; calibration of the denominator, never on the product path"
+    return out
+
+
 def fp32_overlap_leg(dev):
     """Top-k overlap of the bf16-storage search with the reference's pure-fp32 scoring (SURVEY.md §7 hard part 4, §8c):
     the reference scores fp32 embeddings with cos_sim (sentence_transformers/util.py:24-43) and torch.topk (XS:102-108);
@@ -659,9 +691,13 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
 
     enc_ms, sea_ms, tot_ms, e2e_s, e2e_enc_s = maxr(enc_ms), maxr(sea_ms), maxr(tot_ms), maxr(e2e_s), maxr(e2e_enc_s)
-    extra_legs, overlap = None, None
+    extra_legs, overlap, cublas_cal = None, None, None
     if world == 1 and args.other_configs:
         shard_keep = shard
+        try:
+            cublas_cal = cublas_same_shapes(dev)
+        except Exception as e:  # noqa: BLE001
+            cublas_cal = {"error": repr(e)[:300]}
         try:
             overlap = fp32_overlap_leg(dev)
         except Exception as e:  # noqa: BLE001
@@ -750,6 +786,10 @@ def run_b200(args, rank, world, local_rank):
         line["search_10m_strong_scaling"] = big
     e2e_search_ms = 1000 * e2e_s / KR - 1000 * e2e_enc_s / KR
     line["e2e"]["search_queries_per_s"] = NQ / (e2e_search_ms / 1e3) if e2e_search_ms > 0 else None
+    if cublas_cal is not None:
+        line["roofline"]["cublas_same_shapes"] = cublas_cal
+        if gemm_tflops and cublas_cal.get("block_tflops"):
+            line["roofline"]["frac_of_cublas_same_shapes"] = gemm_tflops / cublas_cal["block_tflops"]
     if overlap is not None:
         line["topk_overlap_vs_fp32_reference"] = overlap
     if extra_legs is not None:

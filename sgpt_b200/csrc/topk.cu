@@ -72,6 +72,38 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t (*buf)[32], u
   parity ^= 1u;
   return t;
 }
+// two sums at once (same single barrier)
+__device__ __forceinline__ uint2 block_sum2(uint32_t a, uint32_t b, uint2 (*buf)[32], uint32_t& parity, int lane, int warp) {
+  a = __reduce_add_sync(0xffffffffu, a);
+  b = __reduce_add_sync(0xffffffffu, b);
+  if (lane == 0) buf[parity][warp] = make_uint2(a, b);
+  __syncthreads();
+  const uint2 t = buf[parity][lane];
+  parity ^= 1u;
+  return make_uint2(__reduce_add_sync(0xffffffffu, t.x), __reduce_add_sync(0xffffffffu, t.y));
+}
+
+// One radix-4 step of the bitwise search for the rank-th largest key: with `pv` fixed above bit b+1, the counts of keys
+// >= pv|1<<b, >= pv|2<<b, >= pv|3<<b decide two bits per block-wide reduction (n1 and n2 travel packed in one word: both
+// are <= 49152 < 2^16).  NK keys per thread in registers.
+template <int NK>
+__device__ __forceinline__ uint32_t radix4_step(const uint32_t (&kr)[NK], uint32_t pv, int b, uint32_t rank, uint2 (*buf)[32],
+                                                uint32_t& parity, int lane, int warp) {
+  const uint32_t c1 = pv | (1u << b), c2 = pv | (2u << b), c3 = pv | (3u << b);
+  uint32_t n12 = 0, n3 = 0;
+#pragma unroll
+  for (int i = 0; i < NK; ++i) {
+    n12 += (kr[i] >= c1 ? 1u : 0u) + (kr[i] >= c2 ? 0x10000u : 0u);
+    n3 += (kr[i] >= c3 ? 1u : 0u);
+  }
+  const uint2 t = block_sum2(n12, n3, buf, parity, lane, warp);
+  const uint32_t n1 = t.x & 0xffffu, n2 = t.x >> 16;
+  if (t.y >= rank) return c3;
+  if (n2 >= rank) return c2;
+  if (n1 >= rank) return c1;
+  return pv;
+}
+
 constexpr int kBins = 2048;
 
 constexpr int kMaxFlatLists = 1024;
@@ -211,6 +243,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   uint2* sub_kj = reinterpret_cast<uint2*>(sub_key);  // (key, flat index) pairs, kSubCap / 2 entries
   constexpr uint32_t kSubPairs = kSubCap / 2;
   __shared__ uint32_t s_red[2][32];
+  __shared__ uint2 s_red2[2][32];
   uint32_t red_par = 0;
   bool fast_done = false;
   if (cached && kk > 0) {
@@ -222,13 +255,12 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       const float er = static_cast<float>(kk) * static_cast<float>(kTopkThreads) / static_cast<float>(total);
       const uint32_t rank = static_cast<uint32_t>(er + 4.0f * sqrtf(er) + 4.0f);
       if (rank < static_cast<uint32_t>(kTopkThreads)) {
+        // (the low 12 bits stay zero: a pivot up to 2^-11 (relative) lower keeps a handful of extra keys, nothing else)
         uint32_t pv = 0;
+        const uint32_t sk1[1] = {skeyv};
 #pragma unroll 1
-        for (int bit = 31; bit >= 0; --bit) {
-          const uint32_t cand = pv | (1u << bit);
-          if (block_sum(skeyv >= cand ? 1u : 0u, s_red, red_par, lane, warp) >= rank) pv = cand;
-        }
-        lo_key = pv > 0u ? pv : 1u;  // the rank-th largest sampled key
+        for (int b = 30; b >= 12; b -= 2) pv = radix4_step<1>(sk1, pv, b, rank, s_red2, red_par, lane, warp);
+        lo_key = pv > 0u ? pv : 1u;  // (a lower bound of) the rank-th largest sampled key
       }
     }
     // (2) compaction of the keys >= lo_key
@@ -251,7 +283,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
     sub_n = s_sub_n;
     if (sub_n >= kk && sub_n <= kSubPairs) {
       // (3) exact kk-th largest key of the short list: <= 4 keys per thread in registers
-      uint32_t kr[kSubPairs / kTopkThreads];
+      uint32_t kr[kSubPairs / kTopkThreads];  // (kSubPairs / kTopkThreads = 4)
 #pragma unroll
       for (uint32_t i = 0; i < kSubPairs / kTopkThreads; ++i) {
         const uint32_t e = tid + i * kTopkThreads;
@@ -259,13 +291,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       }
       uint32_t pv = 0;
 #pragma unroll 1
-      for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t cand = pv | (1u << bit);
-        uint32_t c = 0;
-#pragma unroll
-        for (uint32_t i = 0; i < kSubPairs / kTopkThreads; ++i) c += (kr[i] >= cand) ? 1u : 0u;
-        if (block_sum(c, s_red, red_par, lane, warp) >= kk) pv = cand;
-      }
+      for (int b = 30; b >= 0; b -= 2) pv = radix4_step<kSubPairs / kTopkThreads>(kr, pv, b, kk, s_red2, red_par, lane, warp);
       prefix = pv;
       uint32_t cgt = 0;
 #pragma unroll
@@ -407,8 +433,42 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
     }
   }
   __syncthreads();
-  // bitonic sort, descending by key then ascending by id (skipped when only the threshold / unordered seeds are wanted)
-  for (int size = 2; size <= KP && (out_scores != nullptr || extra.n_dst > 0); size <<= 1) {
+  // bitonic sort, descending by key then ascending by id (skipped when only the threshold / unordered seeds are wanted).
+  // KP <= 1024: one element per thread; partners closer than a warp are exchanged with shuffles (40 of the 55 stages at
+  // KP = 1024 need no barrier), the others through the sort buffers.
+  const bool want_sort = (out_scores != nullptr || extra.n_dst > 0);
+  if (want_sort && KP <= kTopkThreads) {
+    uint32_t ka = (tid < KP) ? skey[tid] : 0u;
+    long long ia = (tid < KP) ? sid[tid] : -1;
+    for (int size = 2; size <= KP; size <<= 1) {
+      const bool desc = ((tid & size) == 0);
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        uint32_t kb;
+        long long ib;
+        if (stride >= 32) {
+          __syncthreads();  // the previous round's readers are done
+          if (tid < KP) { skey[tid] = ka; sid[tid] = ia; }
+          __syncthreads();
+          const int pt = tid ^ stride;
+          kb = (tid < KP) ? skey[pt] : 0u;
+          ib = (tid < KP) ? sid[pt] : -1;
+        } else {
+          kb = __shfl_xor_sync(0xffffffffu, ka, stride);
+          const uint32_t lo32 = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(ia), stride);
+          const uint32_t hi32 = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(static_cast<unsigned long long>(ia) >> 32), stride);
+          ib = static_cast<long long>((static_cast<unsigned long long>(hi32) << 32) | lo32);
+        }
+        const bool is_lo = (tid & stride) == 0;
+        const bool mine_first = (ka > kb) || (ka == kb && ia <= ib);  // "mine before the partner's" in descending order
+        // the lower index keeps the element that comes first in a descending run, the last in an ascending run
+        if (mine_first != (is_lo == desc)) { ka = kb; ia = ib; }
+      }
+    }
+    __syncthreads();
+    if (tid < KP) { skey[tid] = ka; sid[tid] = ia; }
+    __syncthreads();
+  }
+  for (int size = 2; size <= KP && want_sort && KP > kTopkThreads; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = tid; i < KP / 2; i += kTopkThreads) {
         const int lo = 2 * i - (i & (stride - 1));
