@@ -39,7 +39,7 @@ struct sgpt_model {
   void* xn = nullptr;  // xb: bf16 copy of the residual stream
   int P = 0;           // statistics groups per row = ceil(d / 128)
   bool ln_fold = false;  // SGPT_LN_FOLD=1 at creation
-  bool resid_bf16 = false;  // SGPT_RESID_BF16=1 at creation: residual stream stored in bf16 (default flow only)
+  bool resid_bf16 = true;   // residual stream stored in bf16 (default; SGPT_RESID_BF16=0 at creation: fp32; default flow only)
   float* sumsq = nullptr;
   // LayerNorm-folded parameters per layer (library-owned)
   std::vector<void*> wq_f, wfc_f;
@@ -120,7 +120,7 @@ extern "C" int sgpt_model_create(const sgpt_model_config* cfg, const sgpt_model_
     const char* lf = getenv("SGPT_LN_FOLD");
     m->ln_fold = (lf != nullptr && lf[0] == '1');
     const char* rb = getenv("SGPT_RESID_BF16");
-    m->resid_bf16 = (rb != nullptr && rb[0] == '1') && !m->ln_fold;
+    m->resid_bf16 = !(rb != nullptr && rb[0] == '0') && !m->ln_fold;  // default ON; SGPT_RESID_BF16=0 keeps the stream in fp32
   }
   if (e == cudaSuccess) e = cudaMalloc(&m->stats, (2 * T * m->P + static_cast<size_t>(cfg->max_batch)) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&m->sumsq, static_cast<size_t>(cfg->max_batch) * 4);

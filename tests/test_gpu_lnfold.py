@@ -139,9 +139,11 @@ def test_ln_fold_block_flow_matches_reference_fixture(golden_dir, monkeypatch):
     assert torch.allclose(outs["1"]["norm"].norm(dim=1), torch.ones(len(ids)), atol=1e-5)
 
 
-def test_bf16_residual_stream_flow_matches_reference_fixture(golden_dir, monkeypatch):
-    """SGPT_RESID_BF16=1: the residual stream stored in bf16 (what HF does for a bf16 checkpoint) instead of fp32 —
-    pooled embeddings vs the HF fp32 fixture within the 1e-3 cosine bar, per-token residual tap still readable."""
+@pytest.mark.parametrize("resid_bf16", ["1", "0"])
+def test_residual_stream_dtype_flows_match_reference_fixture(golden_dir, monkeypatch, resid_bf16):
+    """The residual stream is stored in bf16 by default (what HF does for a bf16 checkpoint) and in fp32 with
+    SGPT_RESID_BF16=0: both against the HF fp32 fixture — pooled embeddings within the 1e-3 cosine bar, per-token residual
+    tap readable."""
     import os
 
     import numpy as np
@@ -155,7 +157,7 @@ def test_bf16_residual_stream_flow_matches_reference_fixture(golden_dir, monkeyp
     spec = _spec_from(z)
     w = gpt_neo.init_weights(spec, seed=int(z["weight_seed"]))
     ids, mask = z["input_ids"], z["attention_mask"]
-    monkeypatch.setenv("SGPT_RESID_BF16", "1")
+    monkeypatch.setenv("SGPT_RESID_BF16", resid_bf16)
     enc = Encoder(_cfg_from_spec(spec), w, device="cuda:0", max_tokens=4096, max_batch=64)
     for method, key in (("weightedmean", "pooled_weightedmean"), ("mean", "pooled_mean")):
         got = enc.encode_tokens(ids, mask, method=method).cpu()
