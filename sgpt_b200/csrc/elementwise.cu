@@ -478,6 +478,121 @@ __global__ void __launch_bounds__(128) pool_kernel(const void* __restrict__ x, c
   }
 }
 
+// F7 + P1 (+ P2) in ONE pass over the residual stream for rows of at most 1024 elements: one CTA per sequence, one warp per
+// token row.  A warp loads the row (registers), takes its mean / variance with shuffles (exact two-pass), and adds
+// w_t r_t (x_t - mu_t) to per-lane accumulators of the columns it owns; the eight warps' accumulators meet in shared
+// memory, gamma / beta / the weight sum are applied once, and the L2 normalisation (the CTA holds the whole output row)
+// needs no second kernel.  (The two-kernel form — row statistics, then pooling — reads the stream twice.)
+__global__ void __launch_bounds__(256) pool_lnf_fused_kernel(const void* __restrict__ x, int x_bf16,
+                                                             const int32_t* __restrict__ pos, const float* __restrict__ pw,
+                                                             int n_pw, const int32_t* __restrict__ cu,
+                                                             const float4* __restrict__ g, const float4* __restrict__ bta,
+                                                             float4* __restrict__ out, int d4, float eps, int mode,
+                                                             int clamp_den, int normalize, int accumulate, float out_scale) {
+  pdl_sync();  // programmatic dependent launch: see common.cuh
+  __shared__ float4 part[8][256];
+  __shared__ float wpart[8];
+  __shared__ float s_ss[8];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = __ldg(cu + b), t1 = __ldg(cu + b + 1);
+  float4 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float wsum = 0.f;
+  const float inv_d = 0.25f / static_cast<float>(d4);
+  // two token rows per iteration: both rows' loads are in flight before the first reduction
+  for (int tb = t0 + warp; tb < t1; tb += 16) {
+    float w[2];
+    float4 v[2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int t = tb + 8 * r;
+      w[r] = 0.f;
+      if (t < t1) {
+        if (mode == SGPT_POOL_WEIGHTEDMEAN) {
+          const int p = __ldg(pos + t);
+          w[r] = pw != nullptr ? __ldg(pw + min(p, n_pw - 1)) : static_cast<float>(p + 1);
+        } else if (mode == SGPT_POOL_LASTTOKEN) {
+          w[r] = (t == t1 - 1) ? 1.f : 0.f;
+        } else {
+          w[r] = 1.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = lane + 32 * i;
+        v[r][i] = (w[r] != 0.f && c < d4) ? ld_row4(x, static_cast<size_t>(t) * d4 + c, x_bf16) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      wsum += w[r];
+      if (w[r] == 0.f) continue;  // warp-uniform
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+      const float mean = warp_sum(s) * inv_d;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (lane + 32 * i < d4) {
+          const float a0 = v[r][i].x - mean, a1 = v[r][i].y - mean, a2 = v[r][i].z - mean, a3 = v[r][i].w - mean;
+          q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+      }
+      const float wr = w[r] * rsqrtf(warp_sum(q) * inv_d + eps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (lane + 32 * i < d4) {
+          acc[i].x += wr * (v[r][i].x - mean); acc[i].y += wr * (v[r][i].y - mean);
+          acc[i].z += wr * (v[r][i].z - mean); acc[i].w += wr * (v[r][i].w - mean);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (lane + 32 * i < d4) part[warp][lane + 32 * i] = acc[i];
+  if (lane == 0) wpart[warp] = wsum;
+  __syncthreads();
+  float W = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) W += wpart[i];
+  float den = W;
+  if (clamp_den) den = fmaxf(den, 1e-9f);
+  float ss = 0.f;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int col = threadIdx.x;  // one float4 column group per thread (d4 <= 256)
+  if (col < d4) {
+    float4 a = part[0][col];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 p = part[i][col];
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    const float4 gg = __ldg(g + col), bb = __ldg(bta + col);
+    o.x = (gg.x * a.x + bb.x * W) / den; o.y = (gg.y * a.y + bb.y * W) / den;
+    o.z = (gg.z * a.z + bb.z * W) / den; o.w = (gg.w * a.w + bb.w * W) / den;
+    o.x *= out_scale; o.y *= out_scale; o.z *= out_scale; o.w *= out_scale;
+    if (accumulate) {
+      const float4 prev = out[static_cast<size_t>(b) * d4 + col];
+      o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+    }
+    ss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+  }
+  if (normalize) {
+    ss = warp_sum(ss);
+    if (lane == 0) s_ss[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += s_ss[i];
+    const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+  }
+  if (col < d4) out[static_cast<size_t>(b) * d4 + col] = o;
+}
+
 // P2: x[b,:] /= max(sqrt(sumsq[b]), 1e-12)      (F.normalize(p=2, dim=1))
 __global__ void __launch_bounds__(256) l2_scale_rows_kernel(float4* __restrict__ x, const float* __restrict__ sumsq,
                                                             int B, int d4) {
@@ -746,6 +861,14 @@ extern "C" int sgpt_pool_ex2(const void* x, int x_bf16, const int32_t* pos, cons
   if (B == 0) return SGPT_OK;
   LaunchScope _ls(kCatPool, stream);
   const int d4 = d / 4;
+  if (gamma != nullptr && d4 <= 256) {
+    // ln_f + pooling (+ normalisation) in one pass over the residual stream
+    SGPT_CHECK_CUDA(launch_kernel(pool_lnf_fused_kernel, dim3(B), dim3(256), 0, stream, x, x_bf16, pos, pos_weights,
+                                  n_pos_weights, cu_seqlens, reinterpret_cast<const float4*>(gamma),
+                                  reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(out), d4, eps, mode,
+                                  clamp_denominator, normalize, accumulate, out_scale));
+    return SGPT_OK;
+  }
   const float2* stats = nullptr;
   if (gamma != nullptr && T > 0) {
     SGPT_ROW_DISPATCH(row_stats_kernel, d4, T, stream, x,
