@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* x, const flo
 // bf16 residual stream -> bf16 normalised row with 16-byte accesses (8 elements per load / store; the generic kernel above
 // would read a bf16 row with 8-byte loads and write with 8-byte stores: measured 1.2x SLOWER than its fp32-input form
 // although it moves a third fewer bytes).  May run in place (a thread rewrites only the chunks it read).
-template <int TPR, int V8>
-__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const uint4* x, const float4* __restrict__ g,
+template <int TPR, int V8, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) layernorm_bf16_kernel(const uint4* x, const float4* __restrict__ g,
                                                              const float4* __restrict__ b, uint4* y, int T, int d8,
                                                              float eps) {
   pdl_sync();  // programmatic dependent launch: see common.cuh
@@ -699,8 +699,12 @@ extern "C" int sgpt_layernorm_ex(const void* x, int x_bf16, const float* gamma, 
     const uint4* xi = static_cast<const uint4*>(x);
     const float4 *gi = reinterpret_cast<const float4*>(gamma), *bi = reinterpret_cast<const float4*>(beta);
     uint4* yo = static_cast<uint4*>(y);
-    // (a variant with 4 rows per warp and all loads issued up front measured slower: 0.82 vs 0.71 ms per 125M step)
-    if (d8 <= 32 * 4)
+    // The pass is latency x occupancy bound (3.4 TB/s at 32 rows in flight per SM): rows of <= 768 elements take the
+    // 3-chunk instance compiled for 6 CTAs per SM.  (A variant with 4 rows per warp and all loads issued up front
+    // measured slower: 0.82 vs 0.71 ms per 125M step.)
+    if (d8 <= 32 * 3)
+      SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_kernel<32, 3, 6>, dim3((T + 7) / 8), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));
+    else if (d8 <= 32 * 4)
       SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_kernel<32, 4>, dim3((T + 7) / 8), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));
     else if (d8 <= 128 * 4)
       SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_kernel<128, 4>, dim3((T + 1) / 2), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));
