@@ -155,6 +155,14 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUte
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous bytes; size and both addresses multiples of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // thread-block cluster helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -2,6 +2,7 @@
 // position-weighted masked pooling with ln_f fused in (P1/P2).  All reductions accumulate in fp32; all global
 // accesses are 16-byte vectorised and coalesced along d.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/sgpt_b200.h"
 #include "common.cuh"
@@ -193,6 +194,91 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bf16_kernel(const uint4* 
           make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
     }
   }
+}
+
+// bf16 -> bf16 LayerNorm with the rows staged through shared memory by bulk async copies (UBLKCP): a CTA owns 8 * NS
+// consecutive rows and issues the copies of ALL its stages (8 rows = one contiguous 8 * d * 2-byte chunk each) before it
+// touches the first one, so every SM has ~190 KB of reads in flight regardless of register pressure.  One warp per row:
+// sum, centred sum of squares and the normalised output are three sweeps over the row IN SHARED MEMORY (16-byte, conflict-
+// free), the output leaves with 16-byte global stores.  The register-resident kernels above are latency x occupancy
+// bound at 3.4 TB/s (32 rows in flight per SM).  May run in place (a stage is read completely before its rows are written;
+// stages of different CTAs are disjoint).
+template <int NS>
+__global__ void __launch_bounds__(256) layernorm_bf16_bulk_kernel(const uint4* x, const float4* __restrict__ g,
+                                                                  const float4* __restrict__ b, uint4* y, int T, int d8,
+                                                                  float eps) {
+  extern __shared__ uint8_t ln_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);          // NS barriers (128 bytes reserved)
+  uint4* rows = reinterpret_cast<uint4*>(smem + 128);          // [NS][8][d8]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_base = blockIdx.x * 8 * NS;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_sync();  // programmatic dependent launch: the residual stream is read only below this line
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      const int r0 = row_base + 8 * s;
+      if (r0 >= T) break;
+      const int nr = min(8, T - r0);
+      const uint32_t bytes = static_cast<uint32_t>(nr) * static_cast<uint32_t>(d8) * 16u;
+      mbar_expect_tx(&bars[s], bytes);
+      bulk_load_1d(rows + static_cast<size_t>(s) * 8 * d8, x + static_cast<size_t>(r0) * d8, bytes, &bars[s]);
+    }
+  }
+  const float inv_d = 1.0f / static_cast<float>(d8 * 8);
+#pragma unroll 1
+  for (int s = 0; s < NS; ++s) {
+    const int row = row_base + 8 * s + warp;
+    if (row_base + 8 * s >= T) break;  // CTA-uniform
+    mbar_wait(&bars[s], 0);
+    if (row >= T) continue;            // warp-uniform
+    const uint4* r = rows + (static_cast<size_t>(s) * 8 + warp) * d8;
+    float sum = 0.f;
+    for (int c = lane; c < d8; c += 32) {
+      const uint4 u = r[c];
+      sum += ((bf16_lo(u.x) + bf16_hi(u.x)) + (bf16_lo(u.y) + bf16_hi(u.y))) +
+             ((bf16_lo(u.z) + bf16_hi(u.z)) + (bf16_lo(u.w) + bf16_hi(u.w)));
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float q = 0.f;
+    for (int c = lane; c < d8; c += 32) {
+      const uint4 u = r[c];
+      const float e[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = e[i] - mean;
+        q = fmaf(a, a, q);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    uint4* yo = y + static_cast<size_t>(row) * d8;
+    for (int c = lane; c < d8; c += 32) {
+      const uint4 u = r[c];
+      const float e[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+      const float4 g0 = __ldg(g + 2 * c), g1 = __ldg(g + 2 * c + 1), b0 = __ldg(b + 2 * c), b1 = __ldg(b + 2 * c + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (e[i] - mean) * rstd * gg[i] + bb[i];
+      yo[c] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+}
+
+template <int NS>
+static int launch_layernorm_bulk(const uint4* x, const float4* g, const float4* b, uint4* y, int T, int d8, float eps,
+                                 cudaStream_t stream) {
+  const size_t smem = 128 + 128 + static_cast<size_t>(NS) * 8 * d8 * 16;
+  auto kern = layernorm_bf16_bulk_kernel<NS>;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SGPT_CHECK_CUDA(launch_kernel(kern, dim3((T + 8 * NS - 1) / (8 * NS)), dim3(256), smem, stream, x, g, b, y, T, d8, eps));
+  return SGPT_OK;
 }
 
 // LayerNorm of a gathered subset of rows: y[m,:] = LN(x[rows[m],:]) (the LM-head input of the cross-encoder scorer)
@@ -699,6 +785,14 @@ extern "C" int sgpt_layernorm_ex(const void* x, int x_bf16, const float* gamma, 
     const uint4* xi = static_cast<const uint4*>(x);
     const float4 *gi = reinterpret_cast<const float4*>(gamma), *bi = reinterpret_cast<const float4*>(beta);
     uint4* yo = static_cast<uint4*>(y);
+    static const bool bulk = [] { const char* e = getenv("SGPT_LN_BULK"); return !(e != nullptr && e[0] == '0'); }();
+    if (bulk) {
+      // stages of 8 rows; as many per CTA as ~48 KB hold (d 768: 4, d 2048: 1, d 4096: 1)
+      const size_t stage = static_cast<size_t>(8) * d8 * 16;
+      if (4 * stage <= 56 * 1024) return launch_layernorm_bulk<4>(xi, gi, bi, yo, T, d8, eps, stream);
+      if (2 * stage <= 56 * 1024) return launch_layernorm_bulk<2>(xi, gi, bi, yo, T, d8, eps, stream);
+      return launch_layernorm_bulk<1>(xi, gi, bi, yo, T, d8, eps, stream);
+    }
     // The pass is latency x occupancy bound (3.4 TB/s at 32 rows in flight per SM): rows of <= 768 elements take the
     // 3-chunk instance compiled for 6 CTAs per SM.  (A variant with 4 rows per warp and all loads issued up front
     // measured slower: 0.82 vs 0.71 ms per 125M step.)
