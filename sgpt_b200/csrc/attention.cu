@@ -403,20 +403,27 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
 // units of different lengths do not stall each other.  The old one-CTA-per-unit kernel serialised load -> MMA ->
 // softmax -> MMA inside a CTA and relied on 2-4 co-resident CTAs for overlap.
 // ---------------------------------------------------------------------------------------------------------------
-template <int HD>
+// kSingle: every sequence fits one 128-key tile (max_seqlen <= 128: configs 1-2 and all NLI models).  Then a unit is ONE
+// key tile: Q and K are dead once S = Q K^T has completed, so P re-uses Q|K and O re-uses S's TMEM columns — 48 KB of smem
+// and 128 TMEM columns per slot at hd 64, i.e. FOUR slots per CTA (four softmax warpgroups): with ~2 us of load latency
+// per unit and only ~2 us of work, four units in flight per SM are what keeps the HBM stream busy.
+template <int HD, bool kSingle>
 struct AttnWsCfg {
   static constexpr int kSub = HD / 64;
   static constexpr int kQBytes = kSub * kSubBytes;            // Q / K / V tile bytes
-  static constexpr int kKPBytes = 2 * kSubBytes;              // K region also hosts P [128 x 128] bf16
-  static constexpr int kStageBytes = kKPBytes + kQBytes;      // { K|P , V }
-  static constexpr int kNKV = (HD == 64) ? 2 : 1;
-  static constexpr int kSlotBytes = kQBytes + kNKV * kStageBytes;
-  static constexpr int kBarBytes = 512;
-  static constexpr int kSmemBytes = 1024 + 2 * kSlotBytes + kBarBytes;
+  static constexpr int kKPBytes = 2 * kSubBytes;              // multi-tile: the K region also hosts P [128 x 128] bf16
+  static constexpr int kStageBytes = kKPBytes + kQBytes;      // multi-tile stage { K|P , V }
+  static constexpr int kNKV = kSingle ? 1 : ((HD == 64) ? 2 : 1);
+  static constexpr int kSlots = (kSingle && HD == 64) ? 4 : 2;
+  static constexpr int kSlotBytes = kSingle ? 3 * kQBytes : kQBytes + kNKV * kStageBytes;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = 1024 + kSlots * kSlotBytes + kBarBytes;
   static constexpr int kTmemCols = 512;
-  static constexpr int kTmemSlot = 256;                       // columns per slot: S at +0, O at +128
+  static constexpr int kTmemSlot = kSingle ? 128 : 256;       // columns per slot: S at +0, O at +128 (single: O over S)
+  static constexpr int kThreads = 32 * (4 * kSlots + 2);
   static_assert(kSmemBytes <= 232448, "attention: exceeds the 227 KB per-CTA shared memory limit");
   static_assert(HD == 64 || HD == 128, "warp-specialised attention: head_dim 64 or 128");
+  static_assert(!kSingle || 2 * kQBytes >= 2 * kSubBytes, "P must fit into Q|K");
 };
 
 struct AttnUnit {
@@ -443,38 +450,46 @@ __device__ __forceinline__ bool attn_unit(int u, int B, int H, int QT, int windo
   return true;
 }
 
-template <int HD>
-__global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv,
-                                                               __nv_bfloat16* __restrict__ out,
-                                                               const int32_t* __restrict__ cu, int B, int H, int QT,
-                                                               float sl2, int window, const float* __restrict__ alibi) {
-  using Cfg = AttnWsCfg<HD>;
-  constexpr int NKV = Cfg::kNKV;
+template <int HD, bool kSingle>
+__global__ void __launch_bounds__(AttnWsCfg<HD, kSingle>::kThreads, 1)
+attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16* __restrict__ out,
+                    const int32_t* __restrict__ cu, int B, int H, int QT, float sl2, int window,
+                    const float* __restrict__ alibi) {
+  using Cfg = AttnWsCfg<HD, kSingle>;
+  constexpr int NKV = Cfg::kNKV, NS = Cfg::kSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // barriers, per slot: q_full q_empty s_full p_full o_full | k_full[NKV] v_full[NKV] kv_empty[NKV]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * Cfg::kSlotBytes);
-  constexpr int kBarsPerSlot = 5 + 3 * NKV;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kBarsPerSlot);
+  // barriers, per slot: q_full q_empty s_full p_full o_full o_empty | k_full[NKV] v_full[NKV] kv_empty[NKV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kSlotBytes);
+  constexpr int kBarsPerSlot = 6 + 3 * NKV;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + NS * kBarsPerSlot);
   auto bar = [&](int s, int i) { return bars + s * kBarsPerSlot + i; };
-  enum { Q_FULL = 0, Q_EMPTY = 1, S_FULL = 2, P_FULL = 3, O_FULL = 4, K_FULL = 5, V_FULL = 5 + NKV, KV_EMPTY = 5 + 2 * NKV };
+  enum { Q_FULL = 0, Q_EMPTY = 1, S_FULL = 2, P_FULL = 3, O_FULL = 4, O_EMPTY = 5, K_FULL = 6, V_FULL = 6 + NKV,
+         KV_EMPTY = 6 + 2 * NKV };
+  // smem: single  [Q | K | V] per slot, P over Q|K;   multi  [Q | NKV x {K (P) | V}]
   auto slot_q = [&](int s) { return smem + s * Cfg::kSlotBytes; };
-  auto slot_k = [&](int s, int st) { return smem + s * Cfg::kSlotBytes + Cfg::kQBytes + st * Cfg::kStageBytes; };
-  auto slot_v = [&](int s, int st) { return slot_k(s, st) + Cfg::kKPBytes; };
+  auto slot_k = [&](int s, int st) {
+    return kSingle ? smem + s * Cfg::kSlotBytes + Cfg::kQBytes
+                   : smem + s * Cfg::kSlotBytes + Cfg::kQBytes + st * Cfg::kStageBytes;
+  };
+  auto slot_v = [&](int s, int st) { return kSingle ? smem + s * Cfg::kSlotBytes + 2 * Cfg::kQBytes : slot_k(s, st) + Cfg::kKPBytes; };
+  auto slot_p = [&](int s, int st) { return kSingle ? slot_q(s) : slot_k(s, st); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarpProducer = 4 * NS, kWarpMma = 4 * NS + 1;
   const int d = H * HD;
   const int n_units = QT * B * H;
-  const int stride = 2 * static_cast<int>(gridDim.x);
+  const int stride = NS * static_cast<int>(gridDim.x);
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(bar(s, Q_FULL), 1);
       mbar_init(bar(s, Q_EMPTY), 1);
       mbar_init(bar(s, S_FULL), 1);
       mbar_init(bar(s, P_FULL), 128);
       mbar_init(bar(s, O_FULL), 1);
+      mbar_init(bar(s, O_EMPTY), 128);
       for (int i = 0; i < NKV; ++i) {
         mbar_init(bar(s, K_FULL + i), 1);
         mbar_init(bar(s, V_FULL + i), 1);
@@ -483,7 +498,7 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
     }
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == kWarpMma) {
     tmem_alloc(tmem_holder, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -493,34 +508,45 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_holder;
   pdl_sync();  // cu_seqlens is written by a copy, qkv by the previous kernel: nothing global is read above this line
 
-  if (warp == 8) {
-    // ===================== TMA producer (both slots, non-blocking round robin) =====================
+  if (warp == kWarpProducer) {
+    // ===================== TMA producer (all slots, non-blocking round robin) =====================
     if (lane == 0) {
-      int u[2] = {2 * static_cast<int>(blockIdx.x), 2 * static_cast<int>(blockIdx.x) + 1};
-      int j[2] = {0, 0};          // next key tile to load of the current unit (valid when have[s])
-      bool have[2] = {false, false}, q_sent[2] = {false, false};
-      AttnUnit w[2];
-      uint32_t nq[2] = {0, 0}, nkv[2] = {0, 0};  // Q tiles / KV tiles issued so far per slot
-      bool done[2] = {false, false};
+      int u[NS], j[NS];
+      bool have[NS], q_sent[NS], done[NS];
+      AttnUnit w[NS];
+      uint32_t nq[NS], nkv[NS];  // Q tiles / KV tiles issued so far per slot
+      int n_done = 0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        u[s] = NS * static_cast<int>(blockIdx.x) + s;
+        j[s] = 0; have[s] = false; q_sent[s] = false; done[s] = false; nq[s] = 0; nkv[s] = 0;
+      }
       uint32_t idle = 0;  // consecutive polls without progress: a protocol bug traps instead of hanging the GPU
-      while (!(done[0] && done[1])) {
+      while (n_done < NS) {
         if (++idle > (1u << 26)) {
           printf("sgpt: attention producer stalled (block %d)\n", blockIdx.x);
           __trap();
         }
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NS; ++s) {
           if (done[s]) continue;
           if (!have[s]) {
             while (u[s] < n_units && !attn_unit(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
-            if (u[s] >= n_units) { done[s] = true; continue; }
+            if (u[s] >= n_units) { done[s] = true; ++n_done; continue; }
             have[s] = true;
             q_sent[s] = false;
             j[s] = w[s].j_lo;
           }
-          if (!q_sent[s]) {
+          const int st = static_cast<int>(nkv[s] % NKV);
+          if (kSingle) {
+            // one stage holds Q, K and V of the unit; it is free once the previous unit's P V (which read P over Q|K, and V)
+            // has completed
+            if (!mbar_try_wait(bar(s, KV_EMPTY), (nkv[s] & 1u) ^ 1u)) continue;
+          } else if (!q_sent[s]) {
             // the Q buffer is free once every S MMA of the previous unit has completed
             if (!mbar_try_wait(bar(s, Q_EMPTY), (nq[s] & 1u) ^ 1u)) continue;
+          }
+          if (!q_sent[s]) {
             mbar_expect_tx(bar(s, Q_FULL), Cfg::kQBytes);
             for (int x = 0; x < Cfg::kSub; ++x)
               tma_load_2d(slot_q(s) + x * kSubBytes, &tma_qkv, bar(s, Q_FULL), w[s].h * HD + 64 * x,
@@ -528,8 +554,7 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
             ++nq[s];
             q_sent[s] = true;
           }
-          const int st = static_cast<int>(nkv[s] % NKV);
-          if (!mbar_try_wait(bar(s, KV_EMPTY + st), ((nkv[s] / NKV) & 1u) ^ 1u)) continue;
+          if (!kSingle && !mbar_try_wait(bar(s, KV_EMPTY + st), ((nkv[s] / NKV) & 1u) ^ 1u)) continue;
           mbar_expect_tx(bar(s, K_FULL + st), Cfg::kQBytes);
           for (int x = 0; x < Cfg::kSub; ++x)
             tma_load_2d(slot_k(s, st) + x * kSubBytes, &tma_qkv, bar(s, K_FULL + st), d + w[s].h * HD + 64 * x,
@@ -547,39 +572,46 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer (both slots, non-blocking round robin) =====================
+  } else if (warp == kWarpMma) {
+    // ===================== MMA issuer (all slots, non-blocking round robin) =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, true);
-      int u[2] = {2 * static_cast<int>(blockIdx.x), 2 * static_cast<int>(blockIdx.x) + 1};
-      int j[2] = {0, 0};
-      bool have[2] = {false, false}, want_pv[2] = {false, false}, done[2] = {false, false};
-      AttnUnit w[2];
-      uint32_t nq[2] = {0, 0}, nt[2] = {0, 0};  // units started / key tiles completed per slot
+      int u[NS], j[NS];
+      bool have[NS], want_pv[NS], done[NS];
+      AttnUnit w[NS];
+      uint32_t nq[NS], nt[NS];  // units started / key tiles completed per slot
+      int n_done = 0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        u[s] = NS * static_cast<int>(blockIdx.x) + s;
+        j[s] = 0; have[s] = false; want_pv[s] = false; done[s] = false; nq[s] = 0; nt[s] = 0;
+      }
       uint32_t idle = 0;
-      while (!(done[0] && done[1])) {
+      while (n_done < NS) {
         if (++idle > (1u << 26)) {
           printf("sgpt: attention MMA issuer stalled (block %d)\n", blockIdx.x);
           __trap();
         }
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NS; ++s) {
           if (done[s]) continue;
           if (!have[s]) {
             while (u[s] < n_units && !attn_unit(u[s], B, H, QT, window, cu, w[s])) u[s] += stride;
-            if (u[s] >= n_units) { done[s] = true; continue; }
+            if (u[s] >= n_units) { done[s] = true; ++n_done; continue; }
             have[s] = true;
             j[s] = w[s].j_lo;
             want_pv[s] = false;
           }
           const int st = static_cast<int>(nt[s] % NKV);
           const uint32_t st_par = (nt[s] / NKV) & 1u;
-          const uint32_t tS = tmem_base + s * Cfg::kTmemSlot, tO = tS + 128;
+          const uint32_t tS = tmem_base + s * Cfg::kTmemSlot, tO = kSingle ? tS : tS + 128;
           if (!want_pv[s]) {
-            // ---- S = Q K_j^T ---- (the S columns are free: this slot's previous P V waited for p_full of the previous tile)
+            // ---- S = Q K_j^T ---- (multi: the S columns are free, this slot's previous P V waited for p_full of the previous
+            // tile; single: S shares its columns with O, which the epilogue of the previous unit must have read)
             if (j[s] == w[s].j_lo && !mbar_try_wait(bar(s, Q_FULL), nq[s] & 1u)) continue;
             if (!mbar_try_wait(bar(s, K_FULL + st), st_par)) continue;
+            if (kSingle && !mbar_try_wait(bar(s, O_EMPTY), (nq[s] & 1u) ^ 1u)) continue;
             tc_fence_after();
             const uint32_t aq = smem_u32(slot_q(s)), ak = smem_u32(slot_k(s, st));
 #pragma unroll
@@ -590,8 +622,8 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
             }
             umma_commit(bar(s, S_FULL));
             idle = 0;
-            if (j[s] == w[s].j_hi) {  // last S of the unit: Q may be overwritten once these MMAs are done
-              umma_commit(bar(s, Q_EMPTY));
+            if (j[s] == w[s].j_hi) {  // last S of the unit: (multi) Q may be overwritten once these MMAs are done
+              if (!kSingle) umma_commit(bar(s, Q_EMPTY));
               ++nq[s];
             }
             want_pv[s] = true;
@@ -600,14 +632,14 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
             if (!mbar_try_wait(bar(s, P_FULL), nt[s] & 1u)) continue;
             if (!mbar_try_wait(bar(s, V_FULL + st), st_par)) continue;
             tc_fence_after();
-            const uint32_t ap = smem_u32(slot_k(s, st)), av = smem_u32(slot_v(s, st));
+            const uint32_t ap = smem_u32(slot_p(s, st)), av = smem_u32(slot_v(s, st));
 #pragma unroll
             for (int kk = 0; kk < kAttnTile / 16; ++kk) {
               const uint64_t da = make_smem_desc_sw128(ap + (kk >> 2) * kSubBytes + (kk & 3) * 32, 16, 1024);
               const uint64_t db = make_smem_desc_sw128(av + kk * 2048, kSubBytes, 1024);
               umma_bf16_ss(tO, da, db, idesc_o, (j[s] > w[s].j_lo) || (kk != 0));
             }
-            umma_commit(bar(s, KV_EMPTY + st));  // the stage (P over K, and V) may be refilled
+            umma_commit(bar(s, KV_EMPTY + st));  // the stage (P, and V; single: Q|K too) may be refilled
             umma_commit(bar(s, O_FULL));
             idle = 0;
             ++nt[s];
@@ -625,10 +657,10 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
     const int s = warp >> 2;            // slot
     const int row = tid & 127;          // query row of the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + s * Cfg::kTmemSlot + lane_off, tO = tS + 128;
+    const uint32_t tS = tmem_base + s * Cfg::kTmemSlot + lane_off, tO = kSingle ? tS : tS + 128;
     uint32_t nt = 0;                    // key tiles completed by this slot
     AttnUnit w;
-    for (int u = 2 * static_cast<int>(blockIdx.x) + s; u < n_units; u += stride) {
+    for (int u = NS * static_cast<int>(blockIdx.x) + s; u < n_units; u += stride) {
       if (!attn_unit(u, B, H, QT, window, cu, w)) continue;
       const int qp0 = w.qt * kAttnTile;
       const float slope2 = (alibi != nullptr) ? __ldg(alibi + w.h) * 1.4426950408889634f : 0.f;
@@ -636,31 +668,35 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = w.j_lo; j <= w.j_hi; ++j, ++nt) {
         const int st = static_cast<int>(nt % NKV);
+        const uint32_t sP = smem_u32(slot_p(s, st));
         mbar_wait(bar(s, S_FULL), nt & 1u);
         tc_fence_after();
         const int kv0 = j * kAttnTile;
         const float m_new = fmaxf(m_run, softmax_tile_max(tS, kv0, rv, sl2, slope2));
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
         const float alpha = exp2f(m_run - m_use);
-        // P over the K tile of this stage: the S MMAs that read K_j have completed (s_full)
-        const float lsum = softmax_tile_exp(tS, kv0, rv, sl2, slope2, m_use, smem_u32(slot_k(s, st)), row);
+        // P over the K tile of this stage (single: over Q|K): the S MMAs that read them have completed (s_full)
+        const float lsum = softmax_tile_exp(tS, kv0, rv, sl2, slope2, m_use, sP, row);
         l_run = l_run * alpha + lsum;
-        m_run = m_new;
-        if (j > w.j_lo) {
-          // O = alpha * O once the previous tile's P V has landed
+        if (!kSingle && j > w.j_lo) {
+          // O = alpha * O once the previous tile's P V has landed; skipped by a warp whose rows all kept their maximum
+          // (alpha == 1 exactly): the usual case after the first key tiles
           mbar_wait(bar(s, O_FULL), (nt - 1u) & 1u);
           tc_fence_after();
+          if (__any_sync(0xffffffffu, m_new != m_run)) {
 #pragma unroll 1
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tO + c * 32, v);
-            tmem_ld_wait();
+            for (int c = 0; c < HD / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32(tO + c * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32(tO + c * 32, v);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32(tO + c * 32, o);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
         }
+        m_run = m_new;
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
         tc_fence_before();
         mbar_arrive(bar(s, P_FULL));
@@ -673,55 +709,65 @@ __global__ void __launch_bounds__(320, 1) attention_ws_kernel(const __grid_const
       __nv_bfloat16* dst = out + static_cast<size_t>(w.seq0 + qp0 + row) * d + w.h * HD;
 #pragma unroll 1
       for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tO + c * 32, v);
+        uint32_t o[32];
+        tmem_ld_32x32(tO + c * 32, o);
         tmem_ld_wait();
         if (row_ok) {
           uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t o[4];
+            uint32_t pk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              o[i] = pack_bf16(__uint_as_float(v[8 * q4 + 2 * i]) * inv_l, __uint_as_float(v[8 * q4 + 2 * i + 1]) * inv_l);
-            d4[q4] = make_uint4(o[0], o[1], o[2], o[3]);
+              pk[i] = pack_bf16(__uint_as_float(o[8 * q4 + 2 * i]) * inv_l, __uint_as_float(o[8 * q4 + 2 * i + 1]) * inv_l);
+            d4[q4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
       }
-      // the next unit's first P V (accumulate = 0) overwrites O only after this warpgroup's p_full arrivals, which
-      // follow these loads in program order
       tc_fence_before();
+      // single: O shares its TMEM columns with the next unit's S — tell the MMA issuer they have been read.  (multi: the
+      // next unit's first P V (accumulate = 0) overwrites O only after this warpgroup's p_full arrivals, which follow
+      // these loads in program order.)
+      if (kSingle) mbar_arrive(bar(s, O_EMPTY));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int HD>
-static int launch_attention_ws(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale, int window,
-                               int max_seqlen, const float* alibi, cudaStream_t stream) {
-  using Cfg = AttnWsCfg<HD>;
-  CUtensorMap map;
-  int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
-  if (rc != SGPT_OK) return rc;
-  auto kern = attention_ws_kernel<HD>;
+template <int HD, bool kSingle>
+static int launch_attention_ws_impl(const CUtensorMap& map, void* out, const int32_t* cu, int B, int H, float scale,
+                                    int window, int max_seqlen, const float* alibi, cudaStream_t stream) {
+  using Cfg = AttnWsCfg<HD, kSingle>;
+  auto kern = attention_ws_kernel<HD, kSingle>;
   static PerDeviceOnce attr_once;
   if (attr_once.first())
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int QT = (max_seqlen + kAttnTile - 1) / kAttnTile;
   const long long units = static_cast<long long>(QT) * B * H;
-  long long ctas = (units + 1) / 2;
+  long long ctas = (units + Cfg::kSlots - 1) / Cfg::kSlots;
   if (ctas > sm_count()) ctas = sm_count();
   if (ctas < 1) ctas = 1;
   const float sl2 = scale * 1.4426950408889634f;
   LaunchScope _ls(kCatAttention, stream);
-  SGPT_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(ctas)), dim3(320), Cfg::kSmemBytes, stream, map,
+  SGPT_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(ctas)), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, map,
                                 static_cast<__nv_bfloat16*>(out), cu, B, H, QT, sl2, window, alibi));
   return SGPT_OK;
+}
+
+template <int HD>
+static int launch_attention_ws(const void* qkv, void* out, const int32_t* cu, int B, int T, int H, float scale, int window,
+                               int max_seqlen, const float* alibi, cudaStream_t stream) {
+  CUtensorMap map;
+  int rc = make_tma_2d_bf16(&map, qkv, static_cast<uint64_t>(T), 3ull * H * HD, 3ull * H * HD, kAttnTile, 64);
+  if (rc != SGPT_OK) return rc;
+  if (max_seqlen <= kAttnTile)
+    return launch_attention_ws_impl<HD, true>(map, out, cu, B, H, scale, window, max_seqlen, alibi, stream);
+  return launch_attention_ws_impl<HD, false>(map, out, cu, B, H, scale, window, max_seqlen, alibi, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -827,6 +873,15 @@ static bool attention_legacy_forced() {
   return v;
 }
 
+// SGPT_ATTN_WS_SINGLE=1 routes batches whose sequences all fit one key tile to the persistent 4-slot variant (A/B)
+static bool attention_ws_single() {
+  static const bool v = [] {
+    const char* e = getenv("SGPT_ATTN_WS_SINGLE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
+
 extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seqlens, int B, int T, int H, int hd,
                               float scale, int window, int max_seqlen, const float* alibi_slopes, int impl,
                               sgpt_stream_t stream_) {
@@ -837,7 +892,7 @@ extern "C" int sgpt_attention(const void* qkv, void* out, const int32_t* cu_seql
   SGPT_REQUIRE(window >= 0, "sgpt_attention: window must be >= 0");
   SGPT_REQUIRE(max_seqlen > 0 || T == 0, "sgpt_attention: max_seqlen must be positive");
   if (B == 0 || T == 0) return SGPT_OK;
-  if (impl == 0 && hd != 256 && max_seqlen > 128 && !attention_legacy_forced()) {
+  if (impl == 0 && hd != 256 && (max_seqlen > 128 || attention_ws_single()) && !attention_legacy_forced()) {
     // Warp-specialised persistent kernel (two work slots per CTA) for sequences of more than one key tile: measured
     // 1.5-1.7x the one-CTA-per-unit kernel (SGPT-1.3B 64 x 256: 3.76 -> 2.18 ms per batch, bloom-7b1 32 x 300: 8.74 ->
     // 5.83 ms; a variant with 64-key tiles double-buffered at hd 128 and a 4-slot single-tile variant both measured slower
