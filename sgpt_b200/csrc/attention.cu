@@ -541,10 +541,10 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16* 
           if (kSingle) {
             // one stage holds Q, K and V of the unit; it is free once the previous unit's P V (which read P over Q|K, and V)
             // has completed
-            if (!mbar_try_wait(bar(s, KV_EMPTY), (nkv[s] & 1u) ^ 1u)) continue;
+            if (!mbar_test_wait(bar(s, KV_EMPTY), (nkv[s] & 1u) ^ 1u)) continue;
           } else if (!q_sent[s]) {
             // the Q buffer is free once every S MMA of the previous unit has completed
-            if (!mbar_try_wait(bar(s, Q_EMPTY), (nq[s] & 1u) ^ 1u)) continue;
+            if (!mbar_test_wait(bar(s, Q_EMPTY), (nq[s] & 1u) ^ 1u)) continue;
           }
           if (!q_sent[s]) {
             mbar_expect_tx(bar(s, Q_FULL), Cfg::kQBytes);
@@ -554,7 +554,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16* 
             ++nq[s];
             q_sent[s] = true;
           }
-          if (!kSingle && !mbar_try_wait(bar(s, KV_EMPTY + st), ((nkv[s] / NKV) & 1u) ^ 1u)) continue;
+          if (!kSingle && !mbar_test_wait(bar(s, KV_EMPTY + st), ((nkv[s] / NKV) & 1u) ^ 1u)) continue;
           mbar_expect_tx(bar(s, K_FULL + st), Cfg::kQBytes);
           for (int x = 0; x < Cfg::kSub; ++x)
             tma_load_2d(slot_k(s, st) + x * kSubBytes, &tma_qkv, bar(s, K_FULL + st), d + w[s].h * HD + 64 * x,
@@ -609,9 +609,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16* 
           if (!want_pv[s]) {
             // ---- S = Q K_j^T ---- (multi: the S columns are free, this slot's previous P V waited for p_full of the previous
             // tile; single: S shares its columns with O, which the epilogue of the previous unit must have read)
-            if (j[s] == w[s].j_lo && !mbar_try_wait(bar(s, Q_FULL), nq[s] & 1u)) continue;
-            if (!mbar_try_wait(bar(s, K_FULL + st), st_par)) continue;
-            if (kSingle && !mbar_try_wait(bar(s, O_EMPTY), (nq[s] & 1u) ^ 1u)) continue;
+            if (j[s] == w[s].j_lo && !mbar_test_wait(bar(s, Q_FULL), nq[s] & 1u)) continue;
+            if (!mbar_test_wait(bar(s, K_FULL + st), st_par)) continue;
+            if (kSingle && !mbar_test_wait(bar(s, O_EMPTY), (nq[s] & 1u) ^ 1u)) continue;
             tc_fence_after();
             const uint32_t aq = smem_u32(slot_q(s)), ak = smem_u32(slot_k(s, st));
 #pragma unroll
@@ -629,8 +629,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16* 
             want_pv[s] = true;
           } else {
             // ---- O += P V_j ----
-            if (!mbar_try_wait(bar(s, P_FULL), nt[s] & 1u)) continue;
-            if (!mbar_try_wait(bar(s, V_FULL + st), st_par)) continue;
+            if (!mbar_test_wait(bar(s, P_FULL), nt[s] & 1u)) continue;
+            if (!mbar_test_wait(bar(s, V_FULL + st), st_par)) continue;
             tc_fence_after();
             const uint32_t ap = smem_u32(slot_p(s, st)), av = smem_u32(slot_v(s, st));
 #pragma unroll
