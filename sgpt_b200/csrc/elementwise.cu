@@ -196,6 +196,110 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bf16_kernel(const uint4* 
   }
 }
 
+// Persistent form of the kernel above (the default for d <= 768 and 1024 < d <= 4096).  tools/ln_bench.cu measured what
+// the one-row-per-group kernel spends its time on: with the gamma / beta loads removed it runs at the speed of a plain copy
+// (d 768: 18.6 us against 26.7 us per 32768-row pass; d 2048: 25.5 / 39.0; d 4096: 28.9 / 45.1) — every row re-reads
+// 8 bytes of gamma / beta per element through the L1 against 2 bytes of x.  Here a thread group keeps its gamma / beta
+// chunks in registers and walks over rows (grid = MINB CTAs per SM), with the next row's loads issued as soon as the
+// current row is unpacked: 22.4 / 28.6 / 32.8 us.  May run in place (a group rewrites only rows it has already read, and
+// the row it prefetches is a different one).
+template <int TPR, bool kWholeCta>
+__device__ __forceinline__ float group_sum_once(float v, float* scratch /* [ROWS][TPR/32] of one parity */, int row_in_cta,
+                                                int lane_in_row) {
+  v = warp_sum(v);
+  if (TPR == 32) return v;
+  constexpr int W = TPR / 32;
+  if ((lane_in_row & 31) == 0) scratch[row_in_cta * W + (lane_in_row >> 5)] = v;
+  // one barrier per reduction: the two reductions of a row use two scratch parities, and a group can only come back to
+  // a parity after every thread of the group has passed the barrier of the other one
+  if (kWholeCta) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(row_in_cta + 1), "r"(TPR) : "memory");
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < W; ++i) s += scratch[row_in_cta * W + i];
+  return s;
+}
+
+template <int TPR, int V8, int MINB>
+__global__ void __launch_bounds__(256, MINB) layernorm_bf16_persist_kernel(const uint4* x, const float4* __restrict__ g,
+                                                                           const float4* __restrict__ b, uint4* y, int T,
+                                                                           int d8, float eps) {
+  constexpr int ROWS = 256 / TPR;
+  constexpr int W = TPR / 32;
+  __shared__ float scratch[2][ROWS * W + 1];
+  const int rg = threadIdx.x / TPR;
+  const int l = threadIdx.x % TPR;
+  // weights: never written by a preceding kernel, so they are fetched before the programmatic-dependency wait
+  float gg[V8][8], bb[V8][8];
+#pragma unroll
+  for (int i = 0; i < V8; ++i) {
+    const int c = l + i * TPR;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, b0 = g0, b1 = g0;
+    if (c < d8) {
+      g0 = __ldg(g + 2 * c); g1 = __ldg(g + 2 * c + 1); b0 = __ldg(b + 2 * c); b1 = __ldg(b + 2 * c + 1);
+    }
+    gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w;
+    gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
+    bb[i][0] = b0.x; bb[i][1] = b0.y; bb[i][2] = b0.z; bb[i][3] = b0.w;
+    bb[i][4] = b1.x; bb[i][5] = b1.y; bb[i][6] = b1.z; bb[i][7] = b1.w;
+  }
+  pdl_sync();  // programmatic dependent launch: the residual stream is read only below this line
+  const int stride = gridDim.x * ROWS;
+  const int cta_row0 = blockIdx.x * ROWS;
+  const int n_iter = cta_row0 < T ? (T - cta_row0 + stride - 1) / stride : 0;  // CTA-uniform (the barriers need that)
+  const float inv_d = 1.0f / static_cast<float>(d8 * 8);
+  uint4 buf[V8];
+  auto load_row = [&](int row) {
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+      const int c = l + i * TPR;
+      buf[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < T && c < d8) buf[i] = x[static_cast<size_t>(row) * d8 + c];
+    }
+  };
+  int row = cta_row0 + rg;
+  load_row(row);
+  for (int it = 0; it < n_iter; ++it, row += stride) {
+    float v[V8][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+      const uint4 u = buf[i];
+      v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
+      v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
+      s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+    }
+    load_row(row + stride);  // the raw registers are free: the next row's loads overlap this row's arithmetic
+    const float mean = group_sum_once<TPR, TPR == 256>(s, scratch[0], rg, l) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+      if (l + i * TPR < d8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float a = v[i][e] - mean;
+          q = fmaf(a, a, q);
+        }
+      }
+    }
+    const float var = group_sum_once<TPR, TPR == 256>(q, scratch[1], rg, l) * inv_d;
+    const float rstd = rsqrtf(var + eps);
+    if (row < T) {
+#pragma unroll
+      for (int i = 0; i < V8; ++i) {
+        const int c = l + i * TPR;
+        if (c < d8) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gg[i][e] + bb[i][e];
+          y[static_cast<size_t>(row) * d8 + c] =
+              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+      }
+    }
+  }
+}
+
 // bf16 -> bf16 LayerNorm with the rows staged through shared memory by bulk async copies (UBLKCP): a CTA owns 8 * NS
 // consecutive rows and issues the copies of ALL its stages (8 rows = one contiguous 8 * d * 2-byte chunk each) before it
 // touches the first one, so every SM has ~190 KB of reads in flight regardless of register pressure.  One warp per row:
@@ -795,10 +899,21 @@ extern "C" int sgpt_layernorm_ex(const void* x, int x_bf16, const float* gamma, 
       if (2 * stage <= 56 * 1024) return launch_layernorm_bulk<2>(xi, gi, bi, yo, T, d8, eps, stream);
       return launch_layernorm_bulk<1>(xi, gi, bi, yo, T, d8, eps, stream);
     }
-    // The pass is latency x occupancy bound (3.4 TB/s at 32 rows in flight per SM): rows of <= 768 elements take the
-    // 3-chunk instance compiled for 6 CTAs per SM.  (A variant with 4 rows per warp and all loads issued up front
-    // measured slower: 0.82 vs 0.71 ms per 125M step.)
-    if (d8 <= 32 * 3)
+    // Persistent groups with gamma / beta in registers (see layernorm_bf16_persist_kernel); SGPT_LN_PERSIST=0 selects the
+    // one-row-per-group kernels.  Widths without a persistent instance (768 < d <= 1024, d > 4096) use those as well.
+    static const bool persist = [] { const char* e = getenv("SGPT_LN_PERSIST"); return !(e != nullptr && e[0] == '0'); }();
+    const int sms = sm_count();
+    auto grid_for_rows = [&](int rows_per_cta, int ctas_per_sm) {
+      const int need = (T + rows_per_cta - 1) / rows_per_cta;
+      return dim3(static_cast<unsigned>(need < sms * ctas_per_sm ? need : sms * ctas_per_sm));
+    };
+    if (persist && d8 <= 32 * 3)
+      SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_persist_kernel<32, 3, 2>, grid_for_rows(8, 2), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));
+    else if (persist && d8 > 32 * 4 && d8 <= 128 * 2)
+      SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_persist_kernel<128, 2, 3>, grid_for_rows(2, 3), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));
+    else if (persist && d8 > 128 * 2 && d8 <= 256 * 2)
+      SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_persist_kernel<256, 2, 3>, grid_for_rows(1, 3), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));
+    else if (d8 <= 32 * 3)
       SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_kernel<32, 3, 6>, dim3((T + 7) / 8), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));
     else if (d8 <= 32 * 4)
       SGPT_CHECK_CUDA(launch_kernel(layernorm_bf16_kernel<32, 4>, dim3((T + 7) / 8), dim3(256), 0, stream, xi, gi, bi, yo, T, d8, eps));

@@ -31,7 +31,8 @@ static int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, i
   }
   const int m_tiles = ((M + kGemmBM - 1) / kGemmBM + CL - 1) / CL;
   const int n_tiles = tmap.count((N + BN - 1) / BN);
-  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;  // tile groups (one per cluster iteration)
+  // work units (one per cluster iteration): tile groups x K slices
+  const long long tiles = static_cast<long long>(m_tiles) * n_tiles * tmap.ksplit;
   if (tiles == 0) return SGPT_OK;
   long long clusters = sm_count() / CL;
   cudaLaunchConfig_t cfg = {};
@@ -102,15 +103,48 @@ static bool cl4_enabled() {
 // tile by multicast (another quarter less L2->SM traffic) when there are at least four M-tiles and 256-wide tiles.
 template <class Epi>
 static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
-                         const typename Epi::Params& p, int bn, cudaStream_t stream) {
+                         const typename Epi::Params& p, int bn, cudaStream_t stream, int ksplit = 1) {
   const bool pair = M > kGemmBM;
+  TileMap tm;
+  tm.ksplit = ksplit;
   if (bn == 256) {
-    if (M >= 4 * kGemmBM && cl4_enabled()) return launch_gemm<256, Epi, 4>(x, ldx, w, ldw, M, N, K, p, stream);
-    return pair ? launch_gemm<256, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream)
-                : launch_gemm<256, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream);
+    if (M >= 4 * kGemmBM && cl4_enabled() && ksplit == 1)
+      return launch_gemm<256, Epi, 4>(x, ldx, w, ldw, M, N, K, p, stream);
+    return pair ? launch_gemm<256, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm)
+                : launch_gemm<256, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm);
   }
-  return pair ? launch_gemm<128, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream)
-              : launch_gemm<128, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream);
+  return pair ? launch_gemm<128, Epi, 2>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm)
+              : launch_gemm<128, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm);
+}
+
+// Split-K for the reduce-add (residual) epilogues.  These GEMMs have few, long tiles (N = d_model): 384 tile groups on 74
+// CTA pairs (125M c_proj) run as 6 rounds of which the last is 19 % full.  With S K-slices per tile the same work is
+// S x as many units of 1/S the length: the tail shrinks to a fraction of a slice.  The price is S reduce-adds per
+// output element instead of one, so a slice must stay long enough to hide its epilogue (>= 16 k-blocks = 1024 of K).
+// SGPT_GEMM_SPLITK=0 turns it off, =2/3/4 forces the factor (experiments).
+static int pick_ksplit(int M, int N, int K, int bn) {
+  const char* env = getenv("SGPT_GEMM_SPLITK");  // read per call: the GPU tests flip it in-process
+  const int forced = env != nullptr ? atoi(env) : -1;
+  const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+  if (forced == 0) return 1;
+  if (forced > 0) return (forced <= 4 && num_kb / forced >= 16) ? forced : 1;
+  const int cl = M > kGemmBM ? 2 : 1;
+  const long long clusters = sm_count() / cl;
+  const long long tiles = static_cast<long long>(((M + kGemmBM - 1) / kGemmBM + cl - 1) / cl) * ((N + bn - 1) / bn);
+  int best = 1;
+  double best_cost = 0;
+  for (int s = 1; s <= 4; ++s) {
+    const int kb_per = (num_kb + s - 1) / s;
+    if (s > 1 && (kb_per < 16 || kb_per * (s - 1) >= num_kb)) break;
+    const long long rounds = (tiles * s + clusters - 1) / clusters;
+    // a round costs its mainloop (kb_per) plus a fixed per-unit overhead of ~3 k-blocks (pipeline fill, epilogue tail)
+    const double cost = static_cast<double>(rounds) * (kb_per + 3);
+    if (s == 1 || cost < best_cost * 0.97) {
+      best = s;
+      best_cost = cost;
+    }
+  }
+  return best;
 }
 
 // Tile-width heuristic: BN=256 halves the smem bytes the tensor core must read per FLOP, but with few tiles the
@@ -205,7 +239,7 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
                                static_cast<uint64_t>(ldo), 32, 32);
       if (rc != SGPT_OK) return rc;
       EpiResidualF32::Params p{om, bias, out, static_cast<int>(ldo)};
-      return launch_linear<EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+      return launch_linear<EpiResidualF32>(x, ldx, w, ldw, M, N, K, p, bn, stream, pick_ksplit(M, N, K, bn));
     }
     case SGPT_EPI_RESID_BF16: {
       SGPT_REQUIRE(resid != nullptr && static_cast<const void*>(resid) == out,
@@ -216,7 +250,7 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
                                 static_cast<uint64_t>(ldo), 32, 64);
       if (rc != SGPT_OK) return rc;
       EpiResidualBF16::Params p{om, bias, out, static_cast<int>(ldo)};
-      return launch_linear<EpiResidualBF16>(x, ldx, w, ldw, M, N, K, p, bn, stream);
+      return launch_linear<EpiResidualBF16>(x, ldx, w, ldw, M, N, K, p, bn, stream, pick_ksplit(M, N, K, bn));
     }
     case 102:
     case 103:

@@ -57,6 +57,12 @@ struct EpiHasPrefetch { static constexpr bool value = false; };
 template <class Epi>
 struct EpiHasPrefetch<Epi, decltype((void)&Epi::prefetch_next)> { static constexpr bool value = true; };
 
+// Epilogue states with a `ks` member are told which K slice of a split-K launch the current work unit covers
+template <class State, class = void>
+struct StateHasKs { static constexpr bool value = false; };
+template <class State>
+struct StateHasKs<State, decltype((void)State::ks)> { static constexpr bool value = true; };
+
 // Epilogues may state a total staging size (kStagingBytes member); 0 / absent = the default rule of GemmCfg.
 template <class Epi, class = void>
 struct EpiStaging { static constexpr int value = 0; };
@@ -77,6 +83,9 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 struct TileMap {
   int mode = 0;
   int stride = 1;
+  // split-K (reduce-add epilogues only): every output tile is computed as `ksplit` work units over disjoint K ranges,
+  // each adding its partial sum into the output; unit index = tile * ksplit + k-slice
+  int ksplit = 1;
   __host__ __device__ int count(int n_tiles) const {
     if (mode == 0) return n_tiles;
     const int sampled = (n_tiles + stride - 1) / stride;
@@ -140,8 +149,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;      // cluster index / number of clusters
   const int m_tiles = ((M + kGemmBM - 1) / kGemmBM + CL - 1) / CL;  // M-tile groups (CL tiles each)
   const int n_tiles = tmap.count((N + BN - 1) / BN);                // N-tiles this launch visits
-  const int num_tiles = m_tiles * n_tiles;
+  const int ksplit = tmap.ksplit;
+  const int num_tiles = m_tiles * n_tiles * ksplit;  // work units
   const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;  // k-blocks per slice (the host keeps every slice non-empty)
 
   if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -182,10 +193,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cid; tile < num_tiles; tile += ncl) {
+      for (int unit = cid; unit < num_tiles; unit += ncl) {
+        const int tile = unit / ksplit, ks = unit - tile * ksplit;
         const int m0 = ((tile / n_tiles) * CL + static_cast<int>(crank)) * kGemmBM;
         const int n0 = tmap.map(tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_end = min(num_kb, (ks + 1) * kb_per);
+        for (int kb = ks * kb_per; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -224,11 +237,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cid; tile < num_tiles; tile += ncl) {
+      for (int unit = cid; unit < num_tiles; unit += ncl) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = unit % ksplit;
+        const int kb_begin = ks * kb_per, kb_end = min(num_kb, kb_begin + kb_per);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::kStageBytes);
@@ -238,8 +253,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-            if (kPair) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (kPair) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
+            else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
           if (kPair) umma_commit_pair(&empty_bar[stage], stage_mask);
@@ -266,14 +281,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     Epi::init(st, ep, ew * 32 + lane, epi_bars + 2 * warp);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cid; tile < num_tiles; tile += ncl) {
+    for (int unit = cid; unit < num_tiles; unit += ncl) {
+      const int tile = unit / ksplit;
+      if constexpr (StateHasKs<typename Epi::State>::value) st.ks = static_cast<uint32_t>(unit - tile * ksplit);
       const int m0 = ((tile / n_tiles) * CL + static_cast<int>(crank)) * kGemmBM + ew * 32;  // this warp's 32-row slab
       const int n0 = tmap.map(tile % n_tiles) * BN + half * kColsPerWarp;
       // work that does not depend on the accumulator (EpiResidLn: the first residual loads, and an L2 prefetch of the
       // residual boxes of the tile after this one) overlaps the mainloop
       if constexpr (EpiHasPrefetch<Epi>::value) {
-        const int nt = tile + ncl;
-        if (nt < num_tiles)
+        const int nt = (unit + ncl) / ksplit;  // (split-K is never combined with a prefetching epilogue)
+        if (unit + ncl < num_tiles)
           Epi::prefetch_next(ep, ((nt / n_tiles) * CL + static_cast<int>(crank)) * kGemmBM + ew * 32,
                              tmap.map(nt % n_tiles) * BN + half * kColsPerWarp, lane, M, N);
       }
@@ -313,9 +330,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 template <class Row>
 struct EpiTmaState {
   uint32_t it;  // boxes issued so far by this warp (selects the double buffer)
+  uint32_t ks;  // K slice of the current work unit (split-K launches; 0 otherwise): only slice 0 adds the bias
   Row row;      // per-row constants of the CURRENT tile (LayerNorm mean / rstd), fetched in pre_tile: the loads overlap
                 // the wait for the accumulator instead of sitting at the head of the epilogue's critical path
 };
+
+// Ops whose result is ADDED to the output (TMA reduce-add) can run split-K: they declare kSplitK and take a flag that
+// tells whether this K slice contributes the bias.
+template <class Op, class = void>
+struct OpSplitK { static constexpr bool value = false; };
+template <class Op>
+struct OpSplitK<Op, decltype((void)Op::kSplitK)> { static constexpr bool value = true; };
 
 template <class Op, int kDebug = 0>  // kDebug: 1 = skip the TMA store (timing experiment), 2 = skip the smem-reuse wait
 struct EpiTma {
@@ -323,7 +348,7 @@ struct EpiTma {
   using State = EpiTmaState<typename Op::Row>;
   static constexpr int kEpiWarps = 8;                 // 2 warps per TMEM lane quarter; each owns ONE 4 KB smem box
   static constexpr int kCols = 128 / Op::kElemBytes;  // columns per 128-byte row segment: 64 (bf16) or 32 (fp32)
-  static __device__ __forceinline__ void init(State& st, const Params&, int, uint64_t*) { st.it = 0; }
+  static __device__ __forceinline__ void init(State& st, const Params&, int, uint64_t*) { st.it = 0; st.ks = 0; }
   template <int BN, int kSlabBytes>
   static __device__ __forceinline__ void pre_tile(State& st, const Params& p, int m0, int, int lane, float*, int M, int) {
     if (m0 < M) st.row = Op::row_init(p, m0 + lane, M);
@@ -362,7 +387,12 @@ struct EpiTma {
       const uint32_t row_addr = box + lane * 128u;
       uint32_t o[8][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) Op::chunk(p, rc, &v[j * (kCols / 8)], n + j * (kCols / 8), N, m0 + lane, o[j]);
+      for (int j = 0; j < 8; ++j) {
+        if constexpr (OpSplitK<Op>::value)
+          Op::chunk(p, rc, &v[j * (kCols / 8)], n + j * (kCols / 8), N, m0 + lane, o[j], st.ks == 0);
+        else
+          Op::chunk(p, rc, &v[j * (kCols / 8)], n + j * (kCols / 8), N, m0 + lane, o[j]);
+      }
       if (kDebug == 4) {  // experiment: straight 16-byte global stores from the thread = row layout (no smem, no TMA)
         if (m0 + lane < M) {
           uint4* g = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out_ptr) +
@@ -484,17 +514,19 @@ struct OpTmaResidAddF32 {
   struct Row {};
   static __device__ __forceinline__ Row row_init(const Params&, int, int) { return Row(); }
   // 4 consecutive columns -> 16 bytes
+  static constexpr bool kSplitK = true;
   static __device__ __forceinline__ void chunk(const Params& p, const Row&, const uint32_t* acc, int col, int N,
-                                               int /*row*/, uint32_t (&o)[4]) {
-    if (p.bias && col + 4 <= N) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                                               int /*row*/, uint32_t (&o)[4], bool add_bias) {
+    const float* bias = add_bias ? p.bias : nullptr;
+    if (bias && col + 4 <= N) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
       o[0] = __float_as_uint(__uint_as_float(acc[0]) + b.x);
       o[1] = __float_as_uint(__uint_as_float(acc[1]) + b.y);
       o[2] = __float_as_uint(__uint_as_float(acc[2]) + b.z);
       o[3] = __float_as_uint(__uint_as_float(acc[3]) + b.w);
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = __float_as_uint(__uint_as_float(acc[i]) + bias_at(p.bias, col + i, N));
+      for (int i = 0; i < 4; ++i) o[i] = __float_as_uint(__uint_as_float(acc[i]) + bias_at(bias, col + i, N));
     }
   }
   static __device__ __forceinline__ void issue(const Params& p, const void* box, int n, int m0) {
@@ -514,18 +546,20 @@ struct OpTmaResidAddBF16 {
   };
   struct Row {};
   static __device__ __forceinline__ Row row_init(const Params&, int, int) { return Row(); }
+  static constexpr bool kSplitK = true;
   static __device__ __forceinline__ void chunk(const Params& p, const Row&, const uint32_t* acc, int col, int N,
-                                               int /*row*/, uint32_t (&o)[4]) {
+                                               int /*row*/, uint32_t (&o)[4], bool add_bias) {
+    const float* bias = add_bias ? p.bias : nullptr;
     float x[8];
-    if (p.bias && col + 8 <= N) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+    if (bias && col + 8 <= N) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col) + 1);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + bb[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + bias_at(p.bias, col + i, N);
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + bias_at(bias, col + i, N);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
