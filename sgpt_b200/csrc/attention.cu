@@ -188,9 +188,13 @@ template <int HD, bool kSingle>
 __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv,
                                                            __nv_bfloat16* __restrict__ out,
                                                            const int32_t* __restrict__ cu, int H, float sl2,
-                                                           int window, const float* __restrict__ alibi) {
+                                                           int window, const float* __restrict__ alibi,
+                                                           int head_major) {
   using Cfg = AttnCfg<HD, kSingle>;
-  const int qt = blockIdx.x, b = blockIdx.y, h = blockIdx.z;
+  // Heads vary fastest over the grid (x = head, y = sequence, z = query tile; head_major == 0 is the round-1 order with
+  // heads slowest): the CTAs resident at the same time then read ALL heads' 128-byte q / k / v pieces of the same token
+  // rows — whole 3 d-element rows of the qkv matrix — instead of one piece out of every row of the whole batch.
+  const int qt = head_major ? blockIdx.z : blockIdx.x, b = blockIdx.y, h = head_major ? blockIdx.x : blockIdx.z;
   const int seq0 = __ldg(cu + b);
   const int len = __ldg(cu + b + 1) - seq0;
   const int qp0 = qt * kAttnTile;
@@ -830,11 +834,14 @@ static int launch_attention_tc_impl(const CUtensorMap& map, void* out, const int
   if (attr_once.first()) {
     SGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   }
-  dim3 grid((max_seqlen + kAttnTile - 1) / kAttnTile, B, H);
+  // SGPT_ATTN_HEAD_MAJOR=0: round-1 grid order (query tile fastest, heads slowest)
+  static const int head_major = [] { const char* e = getenv("SGPT_ATTN_HEAD_MAJOR"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  const int QT = (max_seqlen + kAttnTile - 1) / kAttnTile;
+  dim3 grid = head_major ? dim3(H, B, QT) : dim3(QT, B, H);
   const float sl2 = scale * 1.4426950408889634f;
   LaunchScope _ls(kCatAttention, stream);
   SGPT_CHECK_CUDA(launch_kernel(kern, grid, dim3(128), Cfg::kSmemBytes, stream, map, static_cast<__nv_bfloat16*>(out), cu,
-                                H, sl2, window, alibi));
+                                H, sl2, window, alibi, head_major));
   return SGPT_OK;
 }
 

@@ -117,34 +117,21 @@ static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw,
               : launch_gemm<128, Epi, 1>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm);
 }
 
-// Split-K for the reduce-add (residual) epilogues.  These GEMMs have few, long tiles (N = d_model): 384 tile groups on 74
-// CTA pairs (125M c_proj) run as 6 rounds of which the last is 19 % full.  With S K-slices per tile the same work is
-// S x as many units of 1/S the length: the tail shrinks to a fraction of a slice.  The price is S reduce-adds per
-// output element instead of one, so a slice must stay long enough to hide its epilogue (>= 16 k-blocks = 1024 of K).
-// SGPT_GEMM_SPLITK=0 turns it off, =2/3/4 forces the factor (experiments).
+// Split-K for the reduce-add (residual) epilogues: OFF unless SGPT_GEMM_SPLITK=2/3/4 asks for it (experiments, tests).
+// The idea: these GEMMs have few, long tiles (N = d_model) — 384 tile groups on 74 CTA pairs (125M c_proj) run as 6 rounds
+// of which the last is 19 % full — and S K-slices per tile give S x as many units of 1/S the length, so the tail shrinks
+// to a fraction of a slice.  Measured on B200 (tools/bench_splitk.py, isolated launches, us, unsplit / 2 / 3 / 4 slices):
+// 125M c_proj 117 / 115 / 121 / 117, 1.3B c_proj 328 / 339 / 379 / 403, 5.8B c_proj 874 / 907 / 953 / 1175 — the second
+// reduce-add per output element costs what the shorter tail saves.  And it is not free semantically: with S > 1 the order
+// in which the slices' partial sums reach the bf16 residual stream varies from run to run, so the encoder is no longer
+// bit-reproducible (tests/test_gpu_full_depth.py caught it).  A slice is at least 16 k-blocks (1024 of K).
 static int pick_ksplit(int M, int N, int K, int bn) {
   const char* env = getenv("SGPT_GEMM_SPLITK");  // read per call: the GPU tests flip it in-process
   const int forced = env != nullptr ? atoi(env) : -1;
   const int num_kb = (K + kGemmBK - 1) / kGemmBK;
-  if (forced == 0) return 1;
-  if (forced > 0) return (forced <= 4 && num_kb / forced >= 16) ? forced : 1;
-  const int cl = M > kGemmBM ? 2 : 1;
-  const long long clusters = sm_count() / cl;
-  const long long tiles = static_cast<long long>(((M + kGemmBM - 1) / kGemmBM + cl - 1) / cl) * ((N + bn - 1) / bn);
-  int best = 1;
-  double best_cost = 0;
-  for (int s = 1; s <= 4; ++s) {
-    const int kb_per = (num_kb + s - 1) / s;
-    if (s > 1 && (kb_per < 16 || kb_per * (s - 1) >= num_kb)) break;
-    const long long rounds = (tiles * s + clusters - 1) / clusters;
-    // a round costs its mainloop (kb_per) plus a fixed per-unit overhead of ~3 k-blocks (pipeline fill, epilogue tail)
-    const double cost = static_cast<double>(rounds) * (kb_per + 3);
-    if (s == 1 || cost < best_cost * 0.97) {
-      best = s;
-      best_cost = cost;
-    }
-  }
-  return best;
+  if (forced >= 2) return (forced <= 4 && num_kb / forced >= 16) ? forced : 1;
+  (void)M; (void)N; (void)bn;
+  return 1;
 }
 
 // Tile-width heuristic: BN=256 halves the smem bytes the tensor core must read per FLOP, but with few tiles the
@@ -208,7 +195,11 @@ extern "C" int sgpt_linear(const void* x, int64_t ldx, const void* w, int64_t ld
   SGPT_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "sgpt_linear: K, ldx, ldw must be multiples of 8");
   SGPT_REQUIRE(ldx >= K && ldw >= K && ldo >= N, "sgpt_linear: row pitch smaller than the row");
   if (M == 0) return SGPT_OK;
-  const int bn = pick_bn(M, N);
+  int bn = pick_bn(M, N);
+  if (const char* e = getenv("SGPT_GEMM_BN")) {  // experiments: force the tile width (128 / 256)
+    const int v = atoi(e);
+    if (v == 128 || (v == 256 && N > 128)) bn = v;
+  }
   switch (epilogue) {
     case SGPT_EPI_BF16:
     case SGPT_EPI_GELU_BF16: {

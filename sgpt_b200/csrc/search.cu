@@ -40,7 +40,10 @@ Plan make_plan(int nq, int64_t n, int k) {
   // two-pass only pays off when the sample is a small fraction of the shard and can hold k documents
   p.two_pass = n_tiles >= 8ll * sms && static_cast<int64_t>(sms) * kSimBN >= 2ll * k && nq <= 128;
   if (!p.two_pass) return p;
-  p.stride = static_cast<int>(n_tiles / sms);
+  // at most one sampled tile per SM, so that pass A is a single round (with the stride rounded DOWN a 1 M-document shard
+  // sampled 151 tiles on 148 SMs: three CTAs ran a second tile and the whole pass waited for them); the sample still holds
+  // >= 8/9 sms tiles >= k documents (two_pass condition above)
+  p.stride = static_cast<int>((n_tiles + sms - 1) / sms);
   const int64_t sampled_tiles = (n_tiles + p.stride - 1) / p.stride;
   p.ga = filter_geometry(sampled_tiles);
   p.gb = filter_geometry(n_tiles - sampled_tiles);
