@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
                                                            __nv_bfloat16* __restrict__ out,
                                                            const int32_t* __restrict__ cu, int H, float sl2,
                                                            int window, const float* __restrict__ alibi,
-                                                           int head_major) {
+                                                           int head_major, int prefetch_ahead) {
   using Cfg = AttnCfg<HD, kSingle>;
   // Heads vary fastest over the grid (x = head, y = sequence, z = query tile; head_major == 0 is the round-1 order with
   // heads slowest): the CTAs resident at the same time then read ALL heads' 128-byte q / k / v pieces of the same token
@@ -230,23 +230,11 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
     fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_holder, Cfg::kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-  const uint32_t tS = tmem_base;
-  const uint32_t tO = kSingle ? tmem_base : tmem_base + 128;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-
-  // barrier init and TMEM allocation above overlapped the previous kernel's tail (cu_seqlens is written by a copy, never
-  // by a kernel, so reading it earlier is safe); qkv is touched only from here on
-  pdl_sync();
-  if (tid == 0) {
+    // The first loads leave before the TMEM allocation and the CTA-wide barrier below: only this thread arms and issues
+    // them, everybody else meets them through the mbarriers after the __syncthreads.  (Barrier init overlapped the previous
+    // kernel's tail; cu_seqlens is written by a copy, never by a kernel, so reading it earlier is safe; qkv is touched only
+    // after the programmatic-dependency wait.)
+    pdl_sync();
     mbar_expect_tx(bar_q, Cfg::kQBytes);
     for (int s = 0; s < Cfg::kSub; ++s) tma_load_2d(sQ + s * kSubBytes, &tma_qkv, bar_q, h * HD + 64 * s, seq0 + qp0);
     mbar_expect_tx(bar_k, Cfg::kQBytes);
@@ -256,6 +244,45 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     for (int s = 0; s < Cfg::kSub; ++s)
       tma_load_2d(sV + s * kSubBytes, &tma_qkv, bar_v, 2 * d + h * HD + 64 * s, seq0 + j_lo * kAttnTile);
   }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (prefetch_ahead > 0 && head_major && tid == 64) {
+    // L2 prefetch of the first Q / K / V tiles of the unit `prefetch_ahead` CTAs further down the launch order (= the CTA
+    // that will take this one's place on some SM): its own loads then meet the L2 instead of the DRAM.  A CTA lives for a
+    // handful of microseconds, two thirds of which used to be this first wait (ncu: 38 % of the warp samples).
+    const long long lin = static_cast<long long>(blockIdx.x) +
+                          static_cast<long long>(gridDim.x) * (blockIdx.y + static_cast<long long>(gridDim.y) * blockIdx.z) +
+                          prefetch_ahead;
+    const int h2 = static_cast<int>(lin % gridDim.x);
+    const long long r2 = lin / gridDim.x;
+    const int b2 = static_cast<int>(r2 % gridDim.y);
+    const int qt2 = static_cast<int>(r2 / gridDim.y);
+    if (qt2 < static_cast<int>(gridDim.z)) {
+      const int s2 = __ldg(cu + b2);
+      const int len2 = __ldg(cu + b2 + 1) - s2;
+      const int qp2 = qt2 * kAttnTile;
+      if (qp2 < len2) {
+        const int lo2 = (window > 0) ? max(0, qp2 - window + 1) : 0;
+        const int j2 = kSingle ? 0 : lo2 / kAttnTile;
+        pdl_sync();
+        for (int s = 0; s < Cfg::kSub; ++s) {
+          tma_prefetch_l2_2d(&tma_qkv, h2 * HD + 64 * s, s2 + qp2);
+          tma_prefetch_l2_2d(&tma_qkv, d + h2 * HD + 64 * s, s2 + j2 * kAttnTile);
+          tma_prefetch_l2_2d(&tma_qkv, 2 * d + h2 * HD + 64 * s, s2 + j2 * kAttnTile);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tS = tmem_base;
+  const uint32_t tO = kSingle ? tmem_base : tmem_base + 128;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  pdl_sync();
 
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, true);
@@ -840,8 +867,23 @@ static int launch_attention_tc_impl(const CUtensorMap& map, void* out, const int
   dim3 grid = head_major ? dim3(H, B, QT) : dim3(QT, B, H);
   const float sl2 = scale * 1.4426950408889634f;
   LaunchScope _ls(kCatAttention, stream);
+  // SGPT_ATTN_PREFETCH=0 turns the L2 prefetch of the successor unit off; the distance is one full set of resident CTAs
+  static const bool prefetch_on = [] { const char* e = getenv("SGPT_ATTN_PREFETCH"); return !(e != nullptr && e[0] == '0'); }();
+  static PerDeviceOnce occ_once;
+  static int resident_per_sm = 1;
+  if (occ_once.first()) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, Cfg::kSmemBytes) == cudaSuccess && n > 0) {
+      // (TMEM: 512 columns per SM bound the co-resident CTAs as well)
+      const int by_tmem = 512 / Cfg::kTmemCols;
+      resident_per_sm = n < by_tmem ? n : by_tmem;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  const int prefetch_ahead = (prefetch_on && head_major) ? resident_per_sm * sm_count() : 0;
   SGPT_CHECK_CUDA(launch_kernel(kern, grid, dim3(128), Cfg::kSmemBytes, stream, map, static_cast<__nv_bfloat16*>(out), cu,
-                                H, sl2, window, alibi, head_major));
+                                H, sl2, window, alibi, head_major, prefetch_ahead));
   return SGPT_OK;
 }
 
