@@ -371,6 +371,11 @@ int sgpt_profile_read(double* ms_by_cat, int64_t* timed_launches_by_cat, int64_t
  * since the previous call (cycles / ns = GHz under load, which nvidia-smi sampling cannot resolve) and resets them.
  * Synchronises the device. */
 int sgpt_profile_gemm_clock(double* sm_cycles, double* nanoseconds);
+/* Phase timeline of the most recent exact-selection launch (topk.cu): %globaltimer nanoseconds stamped by CTA 0 at
+ * [0] kernel entry, [1] predecessor complete, [2] front/back decision, [3] list offsets, [4] keys in shared memory,
+ * [5] sample pivot, [6] compaction, [7] exact k-th key, [8] winners placed + ids fetched, [9] sorted, [10] outputs
+ * written.  n <= 16.  Synchronises the device.  A measurement aid, not part of any reference interface. */
+int sgpt_debug_topk_timeline(uint64_t* stamps_ns, int n);
 
 #ifdef __cplusplus
 }

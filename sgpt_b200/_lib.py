@@ -9,7 +9,9 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgpt_b200.so")
+# SGPT_B200_LIB: explicit path of another build of the SAME library (A/B measurements of two builds on one GPU box); it is
+# subject to the same symbol and ABI-version checks — there is still no fallback of any kind
+LIB_PATH = os.environ.get("SGPT_B200_LIB") or os.path.join(_HERE, "libsgpt_b200.so")
 
 SGPT_OK = 0
 EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_RESID_BF16 = 0, 1, 2, 3
@@ -72,6 +74,7 @@ _SIGNATURES = {
     "sgpt_profile_enable": (i32, [i32]),
     "sgpt_profile_read": (i32, [vp, vp, vp]),
     "sgpt_profile_gemm_clock": (i32, [vp, vp]),
+    "sgpt_debug_topk_timeline": (i32, [vp, i32]),
     "sgpt_search": (i32, [vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, vp, vp, i64, vp]),
     "sgpt_embed_tokens_ex": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "sgpt_layernorm_ex": (i32, [vp, i32, vp, vp, vp, i32, i32, f32, vp]),

@@ -159,8 +159,9 @@ FilterGeometry filter_geometry(long long tiles) {
 }
 
 int launch_filter_candidates(const void* Q, const void* C, const float* q_scale, const float* c_scale,
-                             const float* tau, uint2* cand, int* counts, long long stride_q, int L, int group0, int nq,
-                             int n, int D, int tile_mode, int tile_stride, cudaStream_t stream) {
+                             const float* tau, const float* tau_hi, uint2* cand, int* counts, int* counts_back,
+                             long long stride_q, int L, int group0, int nq, int n, int D, int tile_mode, int tile_stride,
+                             cudaStream_t stream) {
   SGPT_REQUIRE(nq <= kGemmBM, "filter GEMM: at most %d queries per launch (got %d)", kGemmBM, nq);
   TileMap tm;
   tm.mode = tile_mode;
@@ -168,7 +169,20 @@ int launch_filter_candidates(const void* Q, const void* C, const float* q_scale,
   const FilterGeometry g = filter_geometry(tm.count((n + kSimBN - 1) / kSimBN));
   SGPT_REQUIRE(L >= g.L && (L % 2) == 0 && (stride_q % 2) == 0, "filter GEMM: candidate lists too small (L=%d < %d)", L,
                g.L);
-  EpiFilterRows::Params p{q_scale, c_scale, tau, cand, counts, stride_q, L, group0, nq};
+  EpiFilterRows::Params p{q_scale, c_scale, tau, tau_hi, cand, counts, counts_back, stride_q, L, group0, nq, nullptr, 0, 0};
+  return launch_gemm<kSimBN, EpiFilterRows>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
+}
+
+int launch_sample_maxima(const void* Q, const void* C, const float* q_scale, const float* c_scale, float* pool,
+                         long long stride_p, int Lp, int nq, int n, int D, int tile_stride, cudaStream_t stream) {
+  SGPT_REQUIRE(nq <= kGemmBM, "sample GEMM: at most %d queries per launch (got %d)", kGemmBM, nq);
+  TileMap tm;
+  tm.mode = 1;
+  tm.stride = tile_stride;
+  const FilterGeometry g = filter_geometry(tm.count((n + kSimBN - 1) / kSimBN));
+  SGPT_REQUIRE(Lp >= g.L / 4 && (Lp % 8) == 0 && (stride_p % 8) == 0 && stride_p >= static_cast<long long>(g.groups) * Lp,
+               "sample GEMM: maxima lists too small (Lp=%d < %d)", Lp, g.L / 4);
+  EpiFilterRows::Params p{q_scale, c_scale, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nq, pool, stride_p, Lp};
   return launch_gemm<kSimBN, EpiFilterRows>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
 }
 

@@ -890,7 +890,7 @@ struct OpScoresF32 {
 };
 
 // Threshold filter of the fused search (search.cu): score = fixnan(acc * row_scale[q] * col_scale[doc]); every score
-// > tau[q] is appended as a packed (score bits, local doc index) pair to a candidate list; the score matrix itself is
+// >= tau[q] is appended as a packed (score bits, local doc index) pair to a candidate list; the score matrix itself is
 // never written to HBM.
 //
 // In the accumulator's native layout thread r of a warp owns query row r, i.e. ONE admission threshold: the compare
@@ -901,30 +901,77 @@ struct OpScoresF32 {
 // L2 and, not the HBM stream, set the kernel's duration.)  L is sized for the worst case (every score of every tile the
 // CTA visits admitted), so there is no overflow path; only the touched prefix of each list generates memory traffic.
 // 8 epilogue warps (two per TMEM lane quarter, half the tile's documents each); no shared memory.
+//
+// Sample mode (Params::pool != nullptr; pass A of the search): nothing is filtered; the thread writes the MAXIMUM of
+// every 4 consecutive documents' scores (32 floats per query and tile half) to pool[q][group][Lp].  Each maximum is the
+// score of a distinct real document, so the k-th largest of a query's maxima is a valid lower bound of its final k-th
+// best score — at a quarter of the entries (and no document indices) the full sample would need.  Slots this thread never
+// fills are written as 0xffffffff (maps to the invalid key 0 of the selection kernels).
 struct EpiFilterRows {
   struct Params {
     const float* row_scale;  // [M] or null
     const float* col_scale;  // [N] or null
-    const float* tau;        // [M] per-query admission threshold; null -> admit everything (dense, vectorised stores)
+    const float* tau;        // [M] per-query admission threshold; null -> admit everything
+    const float* tau_hi;     // [M] upper threshold (>= tau) or null: scores >= tau_hi are appended at the FRONT of the list,
+                             // scores in [tau, tau_hi) at its BACK (filled downwards from slot L - 1); null -> all front
     uint2* cand;             // [M][groups][L]
-    int* counts;             // [groups][M]
+    int* counts;             // [groups][M] front entries
+    int* counts_back;        // [groups][M] back entries (only with tau_hi)
     long long stride_q;      // entries between consecutive queries' list blocks
     int L;                   // entries per (query, group) list
-    int group0;              // first group index this launch writes (groups below it belong to the caller: seeds)
+    int group0;              // first group index this launch writes
     int nq;
+    float* pool;             // sample mode: [M][groups][Lp] block maxima (cand / counts / tau unused)
+    long long stride_p;      // floats between consecutive queries' blocks of `pool`
+    int Lp;                  // floats per (query, group): 32 x tiles per CTA
   };
   struct State {
-    int cnt;
+    int cnt;    // front entries (sample mode: maxima written)
+    int cnt_b;  // back entries
+    // per-tile constants fetched in pre_tile, i.e. BEFORE the wait for the accumulator: lane l holds the inverse norms of
+    // documents n0 + 4 l .. + 3 of this warp's 128-document half tile (broadcast by shuffles below), the query's scale and
+    // its admission threshold.  (Fetched inside the chunk loop, the norms cost one exposed HBM round trip per 32 documents
+    // — 4 B per document that nobody else has touched — while the TMA stream saturates the memory system: ~4 serial
+    // misses per tile per warp against a tile time of 9 us.)
+    float4 cs;
+    float rs, tau, tau_hi;
   };
   static constexpr int kEpiWarps = 8;
   static __device__ __forceinline__ int group_of(const Params& p) {
     return p.group0 + static_cast<int>(blockIdx.x) * 2 + static_cast<int>(threadIdx.x >> 7);
   }
-  static __device__ __forceinline__ void init(State& st, const Params&, int, uint64_t*) { st.cnt = 0; }
-  template <int BN, int kSlabBytes>
-  static __device__ __forceinline__ void pre_tile(State&, const Params&, int, int, int, float*, int, int) {}
+  static __device__ __forceinline__ void init(State& st, const Params&, int, uint64_t*) { st.cnt = 0; st.cnt_b = 0; }
+  template <int COLS, int kSlabBytes>
+  static __device__ __forceinline__ void pre_tile(State& st, const Params& p, int m0, int n0, int lane, float*, int M, int N) {
+    static_assert(COLS == 128, "one float4 of document scales per lane covers the warp's half tile");
+    const int q = m0 + lane;
+    const bool qok = q < M;
+    st.rs = (qok && p.row_scale) ? __ldg(p.row_scale + q) : 1.f;
+    st.tau = (qok && p.tau != nullptr) ? __ldg(p.tau + q) : -INFINITY;
+    st.tau_hi = (qok && p.tau_hi != nullptr) ? fmaxf(__ldg(p.tau_hi + q), st.tau) : st.tau;
+    st.cs = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.col_scale != nullptr && m0 < M) {
+      const int c = n0 + 4 * lane;
+      if (c + 4 <= N) {
+        st.cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + c));
+      } else if (N > 0) {
+        st.cs.x = __ldg(p.col_scale + min(c, N - 1));
+        st.cs.y = __ldg(p.col_scale + min(c + 1, N - 1));
+        st.cs.z = __ldg(p.col_scale + min(c + 2, N - 1));
+        st.cs.w = __ldg(p.col_scale + min(c + 3, N - 1));
+      }
+    }
+  }
   static __device__ __forceinline__ void finish(State& st, const Params& p, int lane_row) {
-    if (lane_row < p.nq) p.counts[static_cast<long long>(group_of(p)) * p.nq + lane_row] = min(st.cnt, p.L);
+    if (lane_row >= p.nq) return;
+    if (p.pool != nullptr) {
+      uint32_t* d = reinterpret_cast<uint32_t*>(p.pool + static_cast<long long>(lane_row) * p.stride_p +
+                                               static_cast<long long>(group_of(p)) * p.Lp);
+      for (int i = st.cnt; i < p.Lp; ++i) d[i] = 0xffffffffu;  // CTAs that visited fewer tiles than the longest
+    } else {
+      p.counts[static_cast<long long>(group_of(p)) * p.nq + lane_row] = st.cnt;  // cnt + cnt_b <= L by construction
+      if (p.counts_back != nullptr) p.counts_back[static_cast<long long>(group_of(p)) * p.nq + lane_row] = st.cnt_b;
+    }
   }
 
   template <int COLS, int kSlabBytes>
@@ -933,29 +980,23 @@ struct EpiFilterRows {
     if (m0 >= M) return;  // warp-uniform
     const int q = m0 + lane;
     const bool qok = q < M;
-    const float rs = (qok && p.row_scale) ? __ldg(p.row_scale + q) : 1.f;
-    const bool dense = (p.tau == nullptr);
-    const float tau = (qok && !dense) ? __ldg(p.tau + q) : -INFINITY;
+    const float rs = st.rs;
+    const bool pooled = (p.pool != nullptr);
+    const float tau = st.tau, tau_hi = st.tau_hi;
+    const float csv[4] = {st.cs.x, st.cs.y, st.cs.z, st.cs.w};
     uint2* dst = p.cand + static_cast<long long>(qok ? q : 0) * p.stride_q + static_cast<long long>(group_of(p)) * p.L;
-    int cnt = st.cnt;
+    int cnt = st.cnt, cnt_b = st.cnt_b;
 #pragma unroll 1
     for (int c = 0; c < COLS; c += 32) {
       const int n = n0 + c;
       if (n >= N) break;  // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32(trow + c, v);
-      float cs[32];
       const bool full = (n + 32 <= N);
-      if (p.col_scale != nullptr && full) {
+      // scale of column c + i: component i % 4 of lane (c + i) / 4 (all lanes take part: the loop is warp-uniform)
+      float cs[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.col_scale + n) + i);  // same address in all lanes
-          cs[4 * i] = t.x; cs[4 * i + 1] = t.y; cs[4 * i + 2] = t.z; cs[4 * i + 3] = t.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) cs[i] = (p.col_scale != nullptr) ? __ldg(p.col_scale + min(n + i, N - 1)) : 1.f;
-      }
+      for (int i = 0; i < 32; ++i) cs[i] = __shfl_sync(0xffffffffu, csv[i & 3], (c >> 2) + (i >> 2));
       tmem_ld_wait();
       float x[32];
 #pragma unroll
@@ -963,27 +1004,37 @@ struct EpiFilterRows {
         const float s = __uint_as_float(v[i]) * rs * cs[i];
         x[i] = (s != s) ? -1.f : s;  // XS:99 NaN -> -1
       }
-      if (dense && full && (cnt & 1) == 0) {
-        // sample pass: every score is kept; 16-byte stores of two consecutive entries (lists are 16-byte aligned)
-        if (qok && cnt + 32 <= p.L) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + cnt);
+      if (pooled) {
+        // sample pass: maxima of 4 consecutive documents, two 16-byte stores (cnt is a multiple of 8, the lists 32-byte
+        // aligned); documents beyond the shard never win
+        float m[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            d4[i] = make_uint4(__float_as_uint(x[2 * i]), static_cast<uint32_t>(n + 2 * i),
-                               __float_as_uint(x[2 * i + 1]), static_cast<uint32_t>(n + 2 * i + 1));
+        for (int j = 0; j < 8; ++j) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx = (full || n + 4 * j + u < N) ? fmaxf(mx, x[4 * j + u]) : mx;
+          m[j] = mx;
         }
-        cnt += qok ? 32 : 0;
+        if (qok && cnt + 8 <= p.Lp) {
+          float4* d4 = reinterpret_cast<float4*>(p.pool + static_cast<long long>(q) * p.stride_p +
+                                                 static_cast<long long>(group_of(p)) * p.Lp + cnt);
+          d4[0] = make_float4(m[0], m[1], m[2], m[3]);
+          d4[1] = make_float4(m[4], m[5], m[6], m[7]);
+        }
+        cnt += 8;
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (qok && n + i < N && x[i] > tau) {
-            if (cnt < p.L) dst[cnt] = make_uint2(__float_as_uint(x[i]), static_cast<uint32_t>(n + i));
-            ++cnt;
+          if (qok && n + i < N && x[i] >= tau && cnt + cnt_b < p.L) {  // (the bound holds by construction: L = every
+            const uint2 e = make_uint2(__float_as_uint(x[i]), static_cast<uint32_t>(n + i));  //  score of every tile)
+            if (x[i] >= tau_hi) dst[cnt++] = e;
+            else dst[p.L - 1 - cnt_b++] = e;
           }
         }
       }
     }
     st.cnt = cnt;
+    st.cnt_b = cnt_b;
   }
 };
 using EpiFilterCandidates = EpiFilterRows;

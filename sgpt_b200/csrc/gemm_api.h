@@ -15,12 +15,20 @@ struct FilterGeometry {
 };
 FilterGeometry filter_geometry(long long tiles);
 
-// Similarity GEMM whose epilogue appends every score > tau[q] (tau == nullptr: every score) as (score bits, local doc
-// index) to cand[q * stride_q + (group0 + g) * L + ...] and writes counts[(group0 + g) * nq + q] for the groups g of this
-// launch (filter_geometry of the visited tile count).  tile_mode/tile_stride select the corpus tiles visited
+// Similarity GEMM whose epilogue appends every score >= tau[q] (tau == nullptr: every score) as (score bits, local doc
+// index) to the list cand[q * stride_q + (group0 + g) * L + ...] — scores >= tau_hi[q] at its front, the others at its
+// back (tau_hi == nullptr: all at the front) — and writes counts / counts_back[(group0 + g) * nq + q] for the groups g of
+// this launch (filter_geometry of the visited tile count).  tile_mode/tile_stride select the corpus tiles visited
 // (gemm.cuh TileMap).  nq <= 128.
 int launch_filter_candidates(const void* Q, const void* C, const float* q_scale, const float* c_scale,
-                             const float* tau, uint2* cand, int* counts, long long stride_q, int L, int group0, int nq,
-                             int n, int D, int tile_mode, int tile_stride, cudaStream_t stream);
+                             const float* tau, const float* tau_hi, uint2* cand, int* counts, int* counts_back,
+                             long long stride_q, int L, int group0, int nq, int n, int D, int tile_mode, int tile_stride,
+                             cudaStream_t stream);
+
+// The same GEMM over every tile_stride-th corpus tile in sample mode: pool[q * stride_p + g * Lp + ...] receives the
+// maximum score of every 4 consecutive documents the group visited (filter_geometry(sampled tiles).L / 4 floats per list,
+// unused slots = 0xffffffff).  Input of launch_tau_select (topk.cuh).
+int launch_sample_maxima(const void* Q, const void* C, const float* q_scale, const float* c_scale, float* pool,
+                         long long stride_p, int Lp, int nq, int n, int D, int tile_stride, cudaStream_t stream);
 
 }  // namespace sgpt

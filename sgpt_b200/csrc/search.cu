@@ -1,13 +1,20 @@
 // S1+S2 for one corpus shard without materialising the [nq, n] score matrix.
 //
-// Two passes of the same tcgen05 similarity GEMM (corpus streamed from HBM exactly once in total):
-//   pass A  scans a strided SAMPLE of the corpus tiles (every s-th 256-document tile, ~one tile per SM) and keeps all of
-//           its scores; a radix select turns them into (i) the query's admission threshold tau[q] = its k-th best
-//           sampled score and (ii) the k sampled winners, which seed the candidate lists (group 0).
-//           tau[q] is a valid lower bound of the final k-th best score because k real documents already reach it.
-//   pass B  scans all remaining tiles; the epilogue keeps only scores > tau[q] (expected k * n / n_sample survivors per
-//           query) — the score matrix never reaches HBM.
-//   final   radix select + sort over each query's candidate lists -> exact top-k.
+// Two passes of the same tcgen05 similarity GEMM:
+//   pass A  scans a strided SAMPLE of the corpus tiles (every s-th 256-document tile, at most one tile per SM, so the pass
+//           is a single round) and keeps, per query, the maximum score of every 4 consecutive documents (gemm.cuh
+//           EpiFilterRows, sample mode).  tau[q] = the k-th largest of those maxima (tau_select_kernel: ten block-wide
+//           counting steps over register-resident keys) is a valid lower bound of the final k-th best score, because each
+//           maximum is the score of a distinct real document.
+//           A second, higher threshold tau_hi[q] = the k_hi-th largest maximum, k_hi = 2.5 k x (sample fraction), is the
+//           level above which ~2.5 k documents of the WHOLE shard are expected.
+//   pass B  scans ALL tiles — the sampled ones again: 1/s <= 1/8 of the shard, cheaper than carrying the sample's winners
+//           along as a seed list through a full selection — and its epilogue keeps only scores >= tau[q] (expected
+//           ~1.1 k s survivors per query), those >= tau_hi[q] at the front of the thread's list and the others at its back;
+//           the score matrix never reaches HBM.
+//   final   exact selection + sort -> top-k.  It reads the FRONT parts only (~2.5 k entries per query instead of ~30 k) and
+//           touches the back parts only for a query whose front parts hold fewer than k entries (tau_hi is a statistical
+//           estimate; tau is the guarantee), so the result is exact either way.
 // Candidates live in per-(query, group) lists, one group per (CTA, tile half) of the GEMM (gemm.cuh EpiFilterRows): no
 // atomics, and every list is sized for the worst case (every score admitted), so no overflow path exists; only the
 // touched prefix of each list ever generates memory traffic.  Small shards take the direct path (dense scores + select).
@@ -16,6 +23,7 @@
 #include "host_utils.h"
 #include "topk.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 using namespace sgpt;
@@ -28,28 +36,42 @@ inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 struct Plan {
   bool two_pass;
   int stride;          // tile stride of the sample
-  FilterGeometry ga;   // pass-A lists: groups x L entries per query
-  FilterGeometry gb;   // pass-B lists (group 0 of the block is the seed list, so gb.groups + 1 lists per query)
-  int64_t stride_a, stride_b;  // entries per query block
+  int Lp;              // sampled maxima per (query, group)
+  int64_t stride_p;    // sampled maxima per query (= groups of pass A x Lp)
+  FilterGeometry gb;   // pass-B candidate lists
+  int64_t stride_b;    // candidate entries per query block
+  int k_hi;            // rank (among the sampled maxima) of the upper threshold
 };
 
 Plan make_plan(int nq, int64_t n, int k) {
   Plan p{};
   const int64_t n_tiles = (n + kSimBN - 1) / kSimBN;
   const int sms = sm_count();
-  // two-pass only pays off when the sample is a small fraction of the shard and can hold k documents
-  p.two_pass = n_tiles >= 8ll * sms && static_cast<int64_t>(sms) * kSimBN >= 2ll * k && nq <= 128;
-  if (!p.two_pass) return p;
-  // at most one sampled tile per SM, so that pass A is a single round (with the stride rounded DOWN a 1 M-document shard
-  // sampled 151 tiles on 148 SMs: three CTAs ran a second tile and the whole pass waited for them); the sample still holds
-  // >= 8/9 sms tiles >= k documents (two_pass condition above)
+  // the sample: every `stride`-th tile, at most one per SM (one round) and at most an eighth of the shard (it is scanned
+  // twice); a sampled tile yields kSimBN / 4 maxima per query and the sample must hold 2 k of them
   p.stride = static_cast<int>((n_tiles + sms - 1) / sms);
+  if (p.stride < 8) p.stride = 8;
   const int64_t sampled_tiles = (n_tiles + p.stride - 1) / p.stride;
-  p.ga = filter_geometry(sampled_tiles);
-  p.gb = filter_geometry(n_tiles - sampled_tiles);
-  if (p.gb.L < k) p.gb.L = (k + 1) & ~1;  // the seed list must hold k entries
-  p.stride_a = static_cast<int64_t>(p.ga.groups) * p.ga.L;
-  p.stride_b = static_cast<int64_t>(p.gb.groups + 1) * p.gb.L;
+  const FilterGeometry ga = filter_geometry(sampled_tiles);  // one tile per CTA: L = kSimBN / 2
+  p.Lp = ga.L / 4;
+  p.stride_p = static_cast<int64_t>(ga.groups) * p.Lp;
+  // (below two tiles per SM the dense score matrix is small and two launches beat four)
+  p.two_pass = nq <= 128 && n_tiles >= 2ll * sms && sampled_tiles * (kSimBN / 4) >= 2ll * k &&
+               p.stride_p <= kMaxTauSample && (p.Lp % 8) == 0;
+  if (!p.two_pass) return p;
+  p.gb = filter_geometry(n_tiles);
+  p.stride_b = static_cast<int64_t>(p.gb.groups) * p.gb.L;
+  // upper threshold: ~2.5 k documents of the whole shard expected above it (relative sd 1 / sqrt(k_hi): with k_hi >= 24
+  // the front lists hold k entries in all but a negligible share of the queries; the others take the back lists too)
+  const double frac = static_cast<double>(sampled_tiles) / static_cast<double>(n_tiles);
+  int64_t k_hi = static_cast<int64_t>(2.5 * k * frac + 0.5);
+  if (k_hi < 24) k_hi = 24;
+  if (const char* e = getenv("SGPT_SEARCH_K_HI")) {  // tests: 1 forces the back-list path, k disables the split
+    const long v = atol(e);
+    if (v >= 1) k_hi = v;
+  }
+  if (k_hi > k) k_hi = k;
+  p.k_hi = static_cast<int>(k_hi);
   return p;
 }
 
@@ -61,9 +83,8 @@ extern "C" int64_t sgpt_search_workspace_bytes(int nq, int64_t n, int k) {
   if (nq > kQueryBlock) nq = kQueryBlock;  // larger batches are processed in blocks that reuse the workspace
   const Plan p = make_plan(nq, n, k);
   if (!p.two_pass) return static_cast<int64_t>(nq) * padded_cols(n) * 4 + 256;
-  return align256(static_cast<int64_t>(nq) * p.stride_a * 8) + align256(static_cast<int64_t>(nq) * p.stride_b * 8) +
-         align256(static_cast<int64_t>(p.ga.groups) * nq * 4) + align256(static_cast<int64_t>(p.gb.groups + 1) * nq * 4) +
-         align256(nq * 4) + 256;
+  return align256(static_cast<int64_t>(nq) * p.stride_p * 4) + align256(static_cast<int64_t>(nq) * p.stride_b * 8) +
+         2 * align256(static_cast<int64_t>(p.gb.groups) * nq * 4) + 2 * align256(nq * 4) + 256;
 }
 
 // One shard, all query blocks.  `fin` carries the packed destinations of the final selection (TopkExtra::dst/flag:
@@ -111,52 +132,34 @@ static int search_impl(const void* Q, const void* Cm, const float* q_scale, cons
   }
 
   uint8_t* w = static_cast<uint8_t*>(ws);
-  uint2* cand_a = reinterpret_cast<uint2*>(w);
-  w += align256(static_cast<int64_t>(nq) * p.stride_a * 8);
-  uint2* cand_b = reinterpret_cast<uint2*>(w);
+  float* pool = reinterpret_cast<float*>(w);
+  w += align256(static_cast<int64_t>(nq) * p.stride_p * 4);
+  uint2* cand = reinterpret_cast<uint2*>(w);
   w += align256(static_cast<int64_t>(nq) * p.stride_b * 8);
-  int* cnt_a = reinterpret_cast<int*>(w);
-  const int64_t cnt_a_bytes = align256(static_cast<int64_t>(p.ga.groups) * nq * 4);
-  w += cnt_a_bytes;
-  int* cnt_b = reinterpret_cast<int*>(w);
-  const int64_t cnt_b_bytes = align256(static_cast<int64_t>(p.gb.groups + 1) * nq * 4);
-  w += cnt_b_bytes;
+  int* cnt = reinterpret_cast<int*>(w);  // every group of the pass-B launch writes its own counts (groups = 2 x its CTAs)
+  w += align256(static_cast<int64_t>(p.gb.groups) * nq * 4);
+  int* cnt_back = reinterpret_cast<int*>(w);
+  w += align256(static_cast<int64_t>(p.gb.groups) * nq * 4);
   float* tau = reinterpret_cast<float*>(w);
+  w += align256(nq * 4);
+  float* tau_hi = reinterpret_cast<float*>(w);
 
-  // every group of a launch writes its own counts; the memset covers groups of CTAs that do not exist (tiny grids)
-  SGPT_CHECK_CUDA(cudaMemsetAsync(cnt_a, 0, cnt_a_bytes + cnt_b_bytes, stream));
-  // pass A: every score of the sampled tiles
-  int rc = launch_filter_candidates(Q, Cm, q_scale, c_scale, nullptr, cand_a, cnt_a, p.stride_a, p.ga.L, 0, nq,
-                                    static_cast<int>(n), D, /*tile_mode=*/1, p.stride, stream);
+  // pass A: block maxima of the sampled tiles -> admission thresholds
+  int rc = launch_sample_maxima(Q, Cm, q_scale, c_scale, pool, p.stride_p, p.Lp, nq, static_cast<int>(n), D, p.stride, stream);
   if (rc != SGPT_OK) return rc;
-  // thresholds + seed winners (group 0 of the pass-B lists)
-  {
-    TopkSrc src{};
-    src.packed = cand_a;
-    src.counts = cnt_a;
-    src.G = p.ga.groups;
-    src.nq = nq;
-    src.L = p.ga.L;
-    src.stride_g = p.ga.L;
-    src.stride_q = p.stride_a;
-    TopkExtra ex{};
-    ex.packed = cand_b;
-    ex.count = cnt_b;
-    ex.cap = p.stride_b;
-    ex.tau = tau;
-    rc = launch_topk_select(src, nq, k, nullptr, nullptr, stream, ex);
-    if (rc != SGPT_OK) return rc;
-  }
-  // pass B: the rest of the shard, admission threshold tau[q]
-  rc = launch_filter_candidates(Q, Cm, q_scale, c_scale, tau, cand_b, cnt_b, p.stride_b, p.gb.L, 1, nq,
-                                static_cast<int>(n), D, /*tile_mode=*/2, p.stride, stream);
+  rc = launch_tau_select(pool, p.stride_p, static_cast<int>(p.stride_p), nq, k, p.k_hi, tau, tau_hi, stream);
+  if (rc != SGPT_OK) return rc;
+  // pass B: the whole shard, admission threshold tau[q], front / back split at tau_hi[q]
+  rc = launch_filter_candidates(Q, Cm, q_scale, c_scale, tau, tau_hi, cand, cnt, cnt_back, p.stride_b, p.gb.L, 0, nq,
+                                static_cast<int>(n), D, /*tile_mode=*/0, 1, stream);
   if (rc != SGPT_OK) return rc;
   // final exact selection over the candidates
   TopkSrc src{};
-  src.packed = cand_b;
-  src.counts = cnt_b;
+  src.packed = cand;
+  src.counts = cnt;
+  src.counts_back = cnt_back;
   src.id_base = id_base;
-  src.G = p.gb.groups + 1;
+  src.G = p.gb.groups;
   src.nq = nq;
   src.L = p.gb.L;
   src.stride_g = p.gb.L;

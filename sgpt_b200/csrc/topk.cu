@@ -28,9 +28,26 @@ struct Elem {
   long long id;
 };
 
-__device__ __forceinline__ Elem load_elem(const TopkSrc& s, int q, int g, long long i) {
+__device__ __forceinline__ long long list_len(const TopkSrc& s, int q, int g) {
+  if (g >= s.G) {  // back part of list g - G (two-sided candidate lists, topk.cuh)
+    long long c = s.counts_back[(g - s.G) * s.nq + q];
+    return c < s.L ? c : s.L;
+  }
+  if (s.counts != nullptr) {
+    long long c = s.counts[g * s.nq + q];
+    return c < s.L ? c : s.L;
+  }
+  return s.L;
+}
+
+// offset of entry 0 of list g of query q (`len` = its length, needed for back parts only: they END at the list's end)
+__device__ __forceinline__ long long list_base(const TopkSrc& s, int q, int g, long long len) {
+  if (g >= s.G) return (g - s.G) * s.stride_g + q * s.stride_q + (s.L - len);
+  return g * s.stride_g + q * s.stride_q;
+}
+
+__device__ __forceinline__ Elem load_elem_at(const TopkSrc& s, int q, long long off, long long i) {
   Elem e;
-  const long long off = g * s.stride_g + q * s.stride_q + i;
   if (s.packed != nullptr) {
     const uint2 p = s.packed[off];
     e.key = score_key(__uint_as_float(p.x));
@@ -52,15 +69,22 @@ __device__ __forceinline__ Elem load_elem(const TopkSrc& s, int q, int g, long l
   return e;
 }
 
-__device__ __forceinline__ long long list_len(const TopkSrc& s, int q, int g) {
-  if (s.counts != nullptr) {
-    long long c = s.counts[g * s.nq + q];
-    return c < s.L ? c : s.L;
-  }
-  return s.L;
+__device__ __forceinline__ Elem load_elem(const TopkSrc& s, int q, int g, long long i) {
+  return load_elem_at(s, q, list_base(s, q, g, g >= s.G ? list_len(s, q, g) : 0) + i, i);
 }
 
 constexpr int kTopkThreads = 1024;
+
+// Phase timeline of the selection kernel (sgpt_debug_topk_timeline): thread 0 of CTA 0 stamps %globaltimer at the phase
+// boundaries of every launch; the last launch's stamps stay readable.  One store per phase: no measurable cost.
+__device__ unsigned long long g_topk_timeline[16];
+__device__ __forceinline__ void timeline_mark(int slot) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_topk_timeline[slot] = t;
+  }
+}
 
 // Sum of `v` over the 1024 threads of the CTA, returned to every thread; ONE barrier per call (scratch double-buffered by
 // call parity: a buffer is rewritten two calls later, i.e. after the barrier of the call in between).
@@ -116,12 +140,12 @@ constexpr int kSubCap = 8192;  // cached mode: keys sharing the k-th key's first
 // (cross-shard merges) or hundreds of short ones (the per-(CTA, half) candidate lists of the fused search).
 // kPad also visits the padding (valid = false) so that warps stay converged for __match_any_sync.
 template <bool kPad, class F>
-__device__ __forceinline__ void for_each_elem(const TopkSrc& s, int q, int tid, const uint32_t* off,
+__device__ __forceinline__ void for_each_elem(const TopkSrc& s, int nl, int q, int tid, const uint32_t* off,
                                               const uint32_t* len, F&& f) {
-  if (s.G <= kMaxFlatLists) {
-    const uint32_t total = off[s.G];
+  if (nl <= kMaxFlatLists) {
+    const uint32_t total = off[nl];
     for (uint32_t j = tid; j < total; j += kTopkThreads) {
-      int lo = 0, hi = s.G;
+      int lo = 0, hi = nl;
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (off[mid] <= j) lo = mid; else hi = mid;
@@ -131,7 +155,7 @@ __device__ __forceinline__ void for_each_elem(const TopkSrc& s, int q, int tid, 
       if (kPad || valid) f(lo, static_cast<long long>(i), valid);
     }
   } else {
-    for (int g = 0; g < s.G; ++g) {
+    for (int g = 0; g < nl; ++g) {
       const long long n = list_len(s, q, g);
       const long long end = kPad ? ((n + 31) & ~31ll) : n;
       for (long long i = tid; i < end; i += kTopkThreads) f(g, i, i < n);
@@ -158,12 +182,16 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   __shared__ uint32_t s_len[kMaxFlatLists];
   __shared__ uint32_t s_bin, s_need, s_cnt_gt, s_cnt_eq;
   __shared__ uint32_t s_total;  // < 2^32 (checked by the launcher)
+  __shared__ uint32_t s_red[2][32];
+  __shared__ uint2 s_red2[2][32];
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
+  timeline_mark(0);
   pdl_sync();  // programmatic dependent launch: see common.cuh
+  timeline_mark(1);
   if (src.wait_flag != nullptr) {
     // cross-GPU gather: the lists of this query are complete once every rank has signalled (topk.cuh TopkExtra::flag)
     if (tid == 0) {
@@ -180,9 +208,21 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
     }
     __syncthreads();
   }
+  uint32_t red_par = 0;
+  // Two-sided candidate lists (topk.cuh TopkSrc::counts_back): the front parts hold the scores above the search's upper
+  // threshold; when they alone contain k entries the back parts cannot contribute a winner and are never touched.
+  int nl = src.G;  // lists this selection reads
+  if (src.counts_back != nullptr) {
+    uint32_t f = 0;
+    for (int g = tid; g < src.G; g += kTopkThreads) f += static_cast<uint32_t>(list_len(src, q, g));
+    if (block_sum(f, s_red, red_par, lane, warp) < static_cast<uint32_t>(k)) nl = 2 * src.G;
+  }
+  timeline_mark(2);
+  const bool pk_local = (src.packed != nullptr) && !src.packed_global;  // every stored entry is valid
   // flat index space over the lists: s_len[g], s_off[g] = sum of the padded lengths of lists < g (block-wide scan)
-  if (src.G <= kMaxFlatLists) {
-    const uint32_t mylen = (tid < src.G) ? static_cast<uint32_t>(list_len(src, q, tid)) : 0u;
+  uint32_t sum_len = 0;
+  if (nl <= kMaxFlatLists) {
+    const uint32_t mylen = (tid < nl) ? static_cast<uint32_t>(list_len(src, q, tid)) : 0u;
     const uint32_t mypad = (mylen + 31u) & ~31u;
     uint32_t incl = mypad;
 #pragma unroll
@@ -191,10 +231,14 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       if (lane >= o) incl += v;
     }
     if (lane == 31) warp_tot[warp] = incl;
+    sum_len = __reduce_add_sync(0xffffffffu, mylen);
+    if (lane == 0) s_red[red_par][warp] = sum_len;  // (the barrier below serves both reductions)
     __syncthreads();
+    sum_len = __reduce_add_sync(0xffffffffu, s_red[red_par][lane]);
+    red_par ^= 1u;
     uint32_t base = 0;
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
-    if (tid < src.G) {
+    if (tid < nl) {
       s_len[tid] = mylen;
       s_off[tid + 1] = base + incl;
     }
@@ -203,31 +247,74 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   // number of valid elements (needed to cap k)
   if (tid == 0) s_total = 0;
   __syncthreads();
-  const bool cached = (src.G <= kMaxFlatLists) && (s_off[src.G <= kMaxFlatLists ? src.G : 0] <= cache_keys);
-  const uint32_t flat_total = cached ? s_off[src.G] : 0u;
+  timeline_mark(3);
+  const bool cached = (nl <= kMaxFlatLists) && (s_off[nl <= kMaxFlatLists ? nl : 0] <= cache_keys);
+  const uint32_t flat_total = cached ? s_off[nl] : 0u;
   if (cached) {
-    // one warp per list; the iterations are independent, so the loads of several chunks are in flight together
-    for (int g = warp; g < src.G; g += kTopkThreads / 32) {
-      const uint32_t len = s_len[g], base = s_off[g], end = (len + 31u) & ~31u;
+    // One warp per list, THREE lists per warp iteration with all their loads issued before the first store: the phase is
+    // a chain of L2 round trips (hundreds of short lists per query), so lists in flight are what shortens it.  Lists of
+    // at most 128 packed entries — the normal case of the fused search — are fetched as two 16-byte loads per lane.
+    for (int g0 = warp; g0 < nl; g0 += 3 * (kTopkThreads / 32)) {
+      uint32_t len[3], base[3];
+      long long lb[3];
+      bool fast = pk_local;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int g = g0 + u * (kTopkThreads / 32);
+        len[u] = (g < nl) ? s_len[g] : 0u;
+        base[u] = (g < nl) ? s_off[g] : 0u;
+        lb[u] = (g < nl) ? list_base(src, q, g, len[u]) : 0ll;
+        fast = fast && len[u] <= 128u && (lb[u] & 1ll) == 0;
+      }
+      if (fast) {
+        uint4 v[3][2];
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t idx = 2u * lane + 64u * h;
+            v[u][h] = (idx < len[u]) ? *reinterpret_cast<const uint4*>(src.packed + lb[u] + idx) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t idx = 2u * lane + 64u * h;
+            if (idx < ((len[u] + 31u) & ~31u))
+              *reinterpret_cast<uint2*>(&ckeys[base[u] + idx]) =
+                  make_uint2(idx < len[u] ? score_key(__uint_as_float(v[u][h].x)) : 0u,
+                             idx + 1u < len[u] ? score_key(__uint_as_float(v[u][h].z)) : 0u);
+          }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const uint32_t end = (len[u] + 31u) & ~31u;
 #pragma unroll 4
-      for (uint32_t i = lane; i < end; i += 32) ckeys[base + i] = (i < len) ? load_elem(src, q, g, i).key : 0u;
+          for (uint32_t i = lane; i < end; i += 32)
+            ckeys[base[u] + i] = (i < len[u]) ? load_elem_at(src, q, lb[u] + i, i).key : 0u;
+        }
+      }
     }
     __syncthreads();
   }
-  {
+  uint32_t total;
+  if (pk_local && nl <= kMaxFlatLists) {
+    total = sum_len;
+  } else {
     uint32_t local = 0;
     if (cached) {
       for (uint32_t j = tid; j < flat_total; j += kTopkThreads) local += (ckeys[j] != 0);
-    } else if (src.ids == nullptr) {
-      for (int g = tid; g < src.G; g += kTopkThreads) local += static_cast<uint32_t>(list_len(src, q, g));
+    } else if (src.ids == nullptr && src.packed == nullptr) {
+      for (int g = tid; g < nl; g += kTopkThreads) local += static_cast<uint32_t>(list_len(src, q, g));
     } else {
-      for_each_elem<false>(src, q, tid, s_off, s_len, [&](int g, long long i, bool) { local += (load_elem(src, q, g, i).key != 0); });
+      for_each_elem<false>(src, nl, q, tid, s_off, s_len, [&](int g, long long i, bool) { local += (load_elem(src, q, g, i).key != 0); });
     }
     local = __reduce_add_sync(0xffffffffu, local);  // 64-bit shared atomics are CAS loops: one 32-bit add per warp
     if (lane == 0 && local) atomicAdd(&s_total, local);
+    __syncthreads();
+    total = s_total;
   }
-  __syncthreads();
-  const uint32_t total = s_total;
+  timeline_mark(4);
   const uint32_t kk = total < static_cast<uint32_t>(k) ? total : static_cast<uint32_t>(k);
 
   uint32_t prefix = 0, mask = 0, need = kk;
@@ -242,9 +329,6 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   // exact k-th key is found by the same bitwise search on the short list (<= 4 keys per thread, in registers).
   uint2* sub_kj = reinterpret_cast<uint2*>(sub_key);  // (key, flat index) pairs, kSubCap / 2 entries
   constexpr uint32_t kSubPairs = kSubCap / 2;
-  __shared__ uint32_t s_red[2][32];
-  __shared__ uint2 s_red2[2][32];
-  uint32_t red_par = 0;
   bool fast_done = false;
   if (cached && kk > 0) {
     uint32_t lo_key = 1u;  // smallest valid key: keeps everything
@@ -263,6 +347,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
         lo_key = pv > 0u ? pv : 1u;  // (a lower bound of) the rank-th largest sampled key
       }
     }
+    timeline_mark(5);
     // (2) compaction of the keys >= lo_key
     if (tid == 0) s_sub_n = 0;
     __syncthreads();
@@ -281,6 +366,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
     }
     __syncthreads();
     sub_n = s_sub_n;
+    timeline_mark(6);
     if (sub_n >= kk && sub_n <= kSubPairs) {
       // (3) exact kk-th largest key of the short list: <= 4 keys per thread in registers
       uint32_t kr[kSubPairs / kTopkThreads];  // (kSubPairs / kTopkThreads = 4)
@@ -320,7 +406,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       } else if (cached) {
         for (uint32_t j = tid; j < flat_total; j += kTopkThreads) tally(ckeys[j]);
       } else {
-        for_each_elem<true>(src, q, tid, s_off, s_len, [&](int g, long long i, bool valid) {
+        for_each_elem<true>(src, nl, q, tid, s_off, s_len, [&](int g, long long i, bool valid) {
           tally(valid ? load_elem(src, q, g, i).key : 0u);
         });
       }
@@ -369,6 +455,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       __syncthreads();
     }
   }
+  timeline_mark(7);
   // prefix == key of the kk-th largest element; `need` of the elements equal to it are winners.
   if (tid == 0) { s_cnt_gt = 0; s_cnt_eq = 0; }
   for (int i = tid; i < KP; i += kTopkThreads) { skey[i] = 0; sid[i] = -1; }
@@ -407,7 +494,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       __syncthreads();
       for (uint32_t t = tid; t < kk; t += kTopkThreads) {
         const uint32_t j = static_cast<uint32_t>(sid[t]);
-        int lo = 0, hi = src.G;
+        int lo = 0, hi = nl;
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
           if (s_off[mid] <= j) lo = mid; else hi = mid;
@@ -418,7 +505,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       for (uint32_t j = tid; j < flat_total; j += kTopkThreads) {
         const uint32_t key = ckeys[j];
         if (key == 0 || key < prefix) continue;
-        int lo = 0, hi = src.G;
+        int lo = 0, hi = nl;
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
           if (s_off[mid] <= j) lo = mid; else hi = mid;
@@ -426,13 +513,14 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
         place(key, lo, static_cast<long long>(j - s_off[lo]));
       }
     } else {
-      for_each_elem<false>(src, q, tid, s_off, s_len, [&](int g, long long i, bool) {
+      for_each_elem<false>(src, nl, q, tid, s_off, s_len, [&](int g, long long i, bool) {
         const uint32_t key = load_elem(src, q, g, i).key;
         if (key != 0 && key >= prefix) place(key, g, i);
       });
     }
   }
   __syncthreads();
+  timeline_mark(8);
   // bitonic sort, descending by key then ascending by id (skipped when only the threshold / unordered seeds are wanted).
   // KP <= 1024: one element per thread; partners closer than a warp are exchanged with shuffles (40 of the 55 stages at
   // KP = 1024 need no barrier), the others through the sort buffers.
@@ -486,6 +574,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
       __syncthreads();
     }
   }
+  timeline_mark(9);
   if (out_scores != nullptr) {
     for (int i = tid; i < k; i += kTopkThreads) {
       const uint32_t key = skey[i];
@@ -522,6 +611,69 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   }
   if (extra.tau != nullptr && tid == 0)
     extra.tau[q] = (kk >= static_cast<uint32_t>(k)) ? key_score(prefix) : -INFINITY;  // key of the k-th best
+  timeline_mark(10);
+}
+
+// Admission thresholds of the two-pass search (search.cu) from the sampled block maxima (gemm.cuh EpiFilterRows, sample
+// mode): tau_lo[q] = a lower bound, tight to 2^-11 relative, of the k-th largest of the `total` floats at pool + q *
+// stride_q (0xffffffff = unused slot), tau_hi[q] the same for rank k_hi <= k; -inf when fewer than k (k_hi) are valid.
+// All keys of a query live in registers (<= 12 per thread), so each threshold is ten block-wide radix-4 counting steps
+// and nothing else: no histogram, no compaction, no winners, no sort — the sample is only ever used for its thresholds.
+constexpr int kTauKeys = 12;
+static_assert(kTauKeys * kTopkThreads == kMaxTauSample, "topk.cuh kMaxTauSample");
+
+__global__ void __launch_bounds__(kTopkThreads, 1) tau_select_kernel(const float* __restrict__ pool, long long stride_q,
+                                                                  int total, int k, int k_hi, float* __restrict__ tau_lo,
+                                                                  float* __restrict__ tau_hi) {
+  __shared__ uint32_t s_red[2][32];
+  __shared__ uint2 s_red2[2][32];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  pdl_sync();
+  const uint4* src = reinterpret_cast<const uint4*>(pool + static_cast<long long>(q) * stride_q);
+  const int n4 = total >> 2;
+  uint32_t kr[kTauKeys];
+  uint32_t valid = 0;
+#pragma unroll
+  for (int i = 0; i < kTauKeys / 4; ++i) {
+    const int j = tid + i * kTopkThreads;
+    const uint4 v = (j < n4) ? __ldg(src + j) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    kr[4 * i] = score_key(__uint_as_float(v.x));
+    kr[4 * i + 1] = score_key(__uint_as_float(v.y));
+    kr[4 * i + 2] = score_key(__uint_as_float(v.z));
+    kr[4 * i + 3] = score_key(__uint_as_float(v.w));
+  }
+#pragma unroll
+  for (int i = 0; i < kTauKeys; ++i) valid += (kr[i] != 0u) ? 1u : 0u;
+  uint32_t red_par = 0;
+  const uint32_t n_valid = block_sum(valid, s_red, red_par, lane, warp);
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {
+    const uint32_t rank = static_cast<uint32_t>(t == 0 ? k : k_hi);
+    float* out = (t == 0) ? tau_lo : tau_hi;
+    if (out == nullptr) continue;  // (block-uniform)
+    uint32_t pv = 0;
+    if (n_valid >= rank) {  // (block-uniform)
+#pragma unroll 1
+      for (int b = 30; b >= 12; b -= 2) pv = radix4_step<kTauKeys>(kr, pv, b, rank, s_red2, red_par, lane, warp);
+    }
+    // pv = the largest key with 12 zero low bits that at least `rank` keys reach: <= the rank-th largest key
+    if (tid == 0) out[q] = pv != 0u ? key_score(pv) : -INFINITY;
+  }
+}
+
+int launch_tau_select(const float* pool, long long stride_q, int total, int nq, int k, int k_hi, float* tau_lo,
+                      float* tau_hi, cudaStream_t stream) {
+  if (total <= 0 || (total & 7) != 0 || total > kMaxTauSample || (stride_q & 3) != 0 || k_hi < 1 || k_hi > k) {
+    set_error("tau select: %d sampled maxima per query (must be a multiple of 8, at most %d), ranks %d / %d", total,
+              kMaxTauSample, k, k_hi);
+    return SGPT_ERR_INVALID;
+  }
+  LaunchScope _ls(kCatTopk, stream);
+  SGPT_CHECK_CUDA(launch_kernel(tau_select_kernel, dim3(nq), dim3(kTopkThreads), 0, stream, pool, stride_q, total, k, k_hi,
+                                tau_lo, tau_hi));
+  return SGPT_OK;
 }
 
 int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
@@ -532,6 +684,10 @@ int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int
   }
   if (static_cast<long long>(src.G) * ((src.L + 31) & ~31ll) >= (1ll << 32)) {
     set_error("top-k: %d lists of %lld entries exceed the 2^32-entry selection space", src.G, src.L);
+    return SGPT_ERR_INVALID;
+  }
+  if (src.counts_back != nullptr && (src.packed == nullptr || src.packed_global || src.counts == nullptr)) {
+    set_error("top-k: two-sided lists need packed local entries with front counts");
     return SGPT_ERR_INVALID;
   }
   int KP = 2;
@@ -560,6 +716,15 @@ int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int
 }  // namespace sgpt
 
 using namespace sgpt;
+
+extern "C" int sgpt_debug_topk_timeline(uint64_t* stamps_ns, int n) {
+  SGPT_REQUIRE(stamps_ns != nullptr && n >= 1 && n <= 16, "sgpt_debug_topk_timeline: bad arguments");
+  unsigned long long h[16];
+  SGPT_CHECK_CUDA(cudaDeviceSynchronize());
+  SGPT_CHECK_CUDA(cudaMemcpyFromSymbol(h, g_topk_timeline, sizeof(h)));
+  for (int i = 0; i < n; ++i) stamps_ns[i] = h[i];
+  return SGPT_OK;
+}
 
 extern "C" int64_t sgpt_topk_workspace_bytes(int nq, int64_t n, int k) {
   (void)nq; (void)n; (void)k;

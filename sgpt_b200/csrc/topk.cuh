@@ -17,6 +17,10 @@ struct TopkSrc {
   const unsigned int* wait_flag = nullptr;
   unsigned int wait_target = 0;
   const int32_t* counts = nullptr;   // per-(list, query) valid length (clamped to L); null -> L
+  // Two-sided lists (packed local entries only): list g additionally holds counts_back[g * nq + q] entries at its END
+  // (slots L - count .. L - 1) — the candidates between the search's lower and upper admission thresholds.  The
+  // selection reads them (as lists G .. 2G-1) only when the front parts together hold fewer than k entries.
+  const int32_t* counts_back = nullptr;
   long long id_base = 0;
   int G = 1;                         // lists per query
   int nq = 0;
@@ -46,5 +50,12 @@ struct TopkExtra {
 // out_scores / out_ids may be null when only the side outputs are wanted.
 int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
                        const TopkExtra& extra = TopkExtra());
+
+// tau_lo[q] / tau_hi[q] = lower bounds (tight to 2^-11 relative) of the k-th / k_hi-th largest of the `total` floats at
+// pool + q * stride_q (0xffffffff = unused slot; total % 8 == 0, total <= kMaxTauSample, 1 <= k_hi <= k); -inf when fewer
+// than k (k_hi) are valid.
+constexpr int kMaxTauSample = 12 * 1024;
+int launch_tau_select(const float* pool, long long stride_q, int total, int nq, int k, int k_hi, float* tau_lo,
+                      float* tau_hi, cudaStream_t stream);
 
 }  // namespace sgpt

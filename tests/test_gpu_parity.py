@@ -411,6 +411,24 @@ def test_semantic_search_matches_reference_util_and_shard_roundtrip(golden_dir, 
     assert torch.equal(s0, s1) and torch.equal(i0, i1)
 
 
+@pytest.mark.parametrize("k_hi", ["1", "24", "1001"])
+def test_search_two_pass_front_and_back_lists(k_hi, monkeypatch):
+    """The two-pass path keeps candidates above the upper threshold at the front of its lists and the rest at the back;
+    the selection reads the back parts only when the front parts hold fewer than k entries.  SGPT_SEARCH_K_HI=1 puts the
+    upper threshold at the sample's best score (front parts nearly empty: every query takes the back-list path), = k makes
+    both thresholds equal (everything at the front); the result must be the oracle's either way.  130 k documents = the
+    stride-8 sample of a shard with ~3 tiles per SM (the 125 k x 4096 shape of config 4 on 8 GPUs)."""
+    from sgpt_b200 import CorpusShard
+
+    monkeypatch.setenv("SGPT_SEARCH_K_HI", k_hi)
+    nq, n, D, k = 37, 130001, 128, 1001
+    q, c = planted_corpus(n, D, nq, seed=77)
+    shard = CorpusShard.from_embeddings(c.cuda(), device="cuda:0", id_base=7)
+    s, i = shard.search(q.cuda(), k, "cos_sim")
+    full = _oracle_topk_on_stored(q, c, k, "cos_sim")
+    _assert_same_topk(s, i, full, k, id_base=7)
+
+
 def test_search_two_pass_with_massive_ties():
     """Two-pass filter path on a corpus with only 40 distinct vectors (every score value is shared by ~7750 documents):
     the admission threshold sits inside a tie group, which must not lose candidates."""
