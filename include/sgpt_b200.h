@@ -286,7 +286,10 @@ int sgpt_search_packed(const void* Q, const void* C, const float* q_scale, const
                        int D, int k, int64_t id_base, uint64_t* out_packed, void* ws, int64_t ws_bytes,
                        sgpt_stream_t stream);
 /* S3 on packed lists: in_packed uint64[G,nq,k] (the all-gathered sgpt_search_packed outputs; chunk = shard in
- *     XS:121-132) -> out_scores fp32[nq,k], out_ids int64[nq,k]; ids < 0 and ids == exclude_ids[q] (XS:118) dropped. */
+ *     XS:121-132) -> out_scores fp32[nq,k], out_ids int64[nq,k]; ids < 0 and ids == exclude_ids[q] (XS:118) dropped.
+ *     Every input list must be in the order sgpt_search_packed writes (score descending, id ascending on ties, empty
+ *     slots last) and ids must be unique across the lists (disjoint shards): the merge ranks entries by binary search
+ *     instead of selecting and sorting again. */
 int sgpt_topk_merge_packed(const uint64_t* in_packed, int G, int nq, int k, float* out_scores, int64_t* out_ids,
                            const int64_t* exclude_ids, sgpt_stream_t stream);
 

@@ -101,12 +101,22 @@ static bool cl4_enabled() {
 // nn.Linear dispatch: tile width by wave efficiency; CTA pairs (cta_group::2, M = 256) whenever there are at least two
 // M-tiles — a third less L2->SM and smem traffic per FLOP than independent CTAs; two pairs per cluster sharing the weight
 // tile by multicast (another quarter less L2->SM traffic) when there are at least four M-tiles and 256-wide tiles.
+// Tile rasterisation (gemm.cuh TileMap::band): banded M-fastest order once the weight matrix no longer fits in the L2
+// next to the activations.  SGPT_GEMM_BAND=<g> forces a band height (0 = N fastest) for A/B measurements; read per call.
+static int pick_band(int M, int N, int K) {
+  if (const char* e = getenv("SGPT_GEMM_BAND")) return atoi(e);
+  const long long w_bytes = 2ll * N * K;
+  const int m_groups = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  return (w_bytes >= (64ll << 20) && m_groups >= 16) ? 8 : 0;
+}
+
 template <class Epi>
 static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                          const typename Epi::Params& p, int bn, cudaStream_t stream, int ksplit = 1) {
   const bool pair = M > kGemmBM;
   TileMap tm;
   tm.ksplit = ksplit;
+  tm.band = pick_band(M, N, K);
   if (bn == 256) {
     if (M >= 4 * kGemmBM && cl4_enabled() && ksplit == 1)
       return launch_gemm<256, Epi, 4>(x, ldx, w, ldw, M, N, K, p, stream);

@@ -297,6 +297,7 @@ extern "C" int sgpt_search_gather(sgpt_gather_t g, const void* Q, const void* Cm
   TopkSrc src{};
   src.packed = reinterpret_cast<const uint2*>(g->local + static_cast<size_t>(par) * g->parity_bytes);
   src.packed_global = 1;
+  src.lists_sorted = 1;  // written by the final selection kernels of the ranks
   src.exclude = reinterpret_cast<const long long*>(exclude_ids);
   src.G = g->world;
   src.nq = nq;
@@ -316,6 +317,7 @@ extern "C" int sgpt_topk_merge_packed(const uint64_t* in_packed, int G, int nq, 
   TopkSrc src{};
   src.packed = reinterpret_cast<const uint2*>(in_packed);
   src.packed_global = 1;
+  src.lists_sorted = 1;  // contract of the entry point (include/sgpt_b200.h)
   src.exclude = reinterpret_cast<const long long*>(exclude_ids);
   src.G = G;
   src.nq = nq;

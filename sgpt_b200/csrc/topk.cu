@@ -212,9 +212,11 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   // Two-sided candidate lists (topk.cuh TopkSrc::counts_back): the front parts hold the scores above the search's upper
   // threshold; when they alone contain k entries the back parts cannot contribute a winner and are never touched.
   int nl = src.G;  // lists this selection reads
+  uint32_t len_pre = 0;  // length of list `tid` (front parts, then back parts), fetched in ONE round of loads
   if (src.counts_back != nullptr) {
-    uint32_t f = 0;
-    for (int g = tid; g < src.G; g += kTopkThreads) f += static_cast<uint32_t>(list_len(src, q, g));
+    if (tid < 2 * src.G) len_pre = static_cast<uint32_t>(list_len(src, q, tid));
+    uint32_t f = (tid < src.G) ? len_pre : 0u;
+    for (int g = tid + kTopkThreads; g < src.G; g += kTopkThreads) f += static_cast<uint32_t>(list_len(src, q, g));
     if (block_sum(f, s_red, red_par, lane, warp) < static_cast<uint32_t>(k)) nl = 2 * src.G;
   }
   timeline_mark(2);
@@ -222,7 +224,8 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   // flat index space over the lists: s_len[g], s_off[g] = sum of the padded lengths of lists < g (block-wide scan)
   uint32_t sum_len = 0;
   if (nl <= kMaxFlatLists) {
-    const uint32_t mylen = (tid < nl) ? static_cast<uint32_t>(list_len(src, q, tid)) : 0u;
+    const uint32_t mylen = (tid >= nl) ? 0u
+                           : (src.counts_back != nullptr) ? len_pre : static_cast<uint32_t>(list_len(src, q, tid));
     const uint32_t mypad = (mylen + 31u) & ~31u;
     uint32_t incl = mypad;
 #pragma unroll
@@ -676,11 +679,121 @@ int launch_tau_select(const float* pool, long long stride_q, int total, int nq, 
   return SGPT_OK;
 }
 
+// S3 for lists that are already SORTED (the packed per-shard results of sgpt_search_packed / the peer gather buffers:
+// descending score, ascending id on ties, empty slots (-inf, -1) at the tail): no selection and no sort — the final
+// position of an entry is the number of entries that precede it, i.e. its index in its own list plus one binary search
+// per other list; entries whose position is below k are written straight to that position.  All lists of a query are
+// staged in shared memory as 64-bit composites (order key << 32 | ~id: larger = earlier; 0 = empty slot); the self-match
+// (exclude[q], XS:118) is found while staging and every entry it precedes moves up by one.  One CTA per query.
+__global__ void __launch_bounds__(kTopkThreads, 1) merge_sorted_kernel(TopkSrc src, int k, float* __restrict__ out_scores,
+                                                                    long long* __restrict__ out_ids) {
+  extern __shared__ uint8_t dsm[];
+  unsigned long long* comp = reinterpret_cast<unsigned long long*>(dsm);  // [G][L]
+  __shared__ unsigned long long s_excl;  // composite of the excluded entry (0 = none among the lists)
+  __shared__ uint32_t s_red[2][32];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int G = src.G, L = static_cast<int>(src.L);
+  pdl_sync();
+  if (src.wait_flag != nullptr) {  // cross-GPU gather: see topk_select_kernel
+    if (tid == 0) {
+      unsigned int v, polls = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src.wait_flag + q) : "memory");
+        if (static_cast<int>(v - src.wait_target) >= 0) break;
+        if (++polls > (1u << 26)) {
+          printf("sgpt: cross-GPU gather timed out (query %d: flag %u, waiting for %u)\n", q, v, src.wait_target);
+          __trap();
+        }
+        __nanosleep(64);
+      } while (true);
+    }
+  }
+  if (tid == 0) s_excl = 0ull;
+  __syncthreads();
+  const long long excl = (src.exclude != nullptr) ? src.exclude[q] : -1;
+  const int total = G * L;
+  uint32_t n_valid = 0;
+  for (int j = tid; j < total; j += kTopkThreads) {
+    const int g = j / L, i = j - g * L;
+    const uint2 p = src.packed[g * src.stride_g + q * src.stride_q + i];
+    const int32_t id = static_cast<int32_t>(p.y);
+    unsigned long long c = 0ull;
+    if (id >= 0) {
+      c = (static_cast<unsigned long long>(score_key(__uint_as_float(p.x))) << 32) | static_cast<uint32_t>(~id);
+      if (static_cast<long long>(id) == excl) s_excl = c;  // ids are unique across shards: at most one writer
+      else ++n_valid;
+    }
+    comp[j] = c;
+  }
+  uint32_t red_par = 0;
+  n_valid = block_sum(n_valid, s_red, red_par, lane, warp);  // (its barrier also publishes comp[] and s_excl)
+  const unsigned long long cx = s_excl;
+  for (int j = tid; j < total; j += kTopkThreads) {
+    const unsigned long long c = comp[j];
+    if (c == 0ull || c == cx) continue;
+    const int g = j / L;
+    int rank = (j - g * L) - ((cx > c) ? 1 : 0);  // entries ahead of it in its own list; the self-match does not count
+    for (int h = 0; h < G && rank < k; ++h) {
+      if (h == g) continue;
+      // number of entries of list h that precede c: first index whose composite is <= c (descending list)
+      const unsigned long long* lst = comp + h * L;
+      int lo = 0, hi = L;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lst[mid] > c) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      out_scores[static_cast<size_t>(q) * k + rank] = key_score(static_cast<uint32_t>(c >> 32));
+      out_ids[static_cast<size_t>(q) * k + rank] = static_cast<long long>(static_cast<int32_t>(~static_cast<uint32_t>(c)));
+    }
+  }
+  for (int r = static_cast<int>(n_valid) + tid; r < k; r += kTopkThreads) {  // fewer than k real entries: empty tail
+    out_scores[static_cast<size_t>(q) * k + r] = -INFINITY;
+    out_ids[static_cast<size_t>(q) * k + r] = -1;
+  }
+}
+
+// true when the launch was taken (sorted packed global lists that fit in shared memory)
+static bool launch_merge_sorted(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
+                                int* rc) {
+  constexpr size_t kDynMax = 200 * 1024;
+  const size_t bytes = static_cast<size_t>(src.G) * static_cast<size_t>(src.L) * 8;
+  if (!src.lists_sorted || src.packed == nullptr || !src.packed_global || src.counts != nullptr || out_scores == nullptr ||
+      out_ids == nullptr || bytes > kDynMax || src.G < 1)
+    return false;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
+    if (cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDynMax)) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+  }
+  LaunchScope _ls(kCatTopk, stream);
+  const cudaError_t e = launch_kernel(merge_sorted_kernel, dim3(nq), dim3(kTopkThreads), bytes, stream, src, k, out_scores,
+                                      reinterpret_cast<long long*>(out_ids));
+  if (e != cudaSuccess) {
+    set_error("merge_sorted_kernel: %s", cudaGetErrorString(e));
+    *rc = SGPT_ERR_CUDA;
+  } else {
+    *rc = SGPT_OK;
+  }
+  return true;
+}
+
 int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
                        const TopkExtra& extra) {
   if (k <= 0 || k > 4096) {
     set_error("top-k: k=%d outside [1, 4096]", k);
     return SGPT_ERR_INVALID;
+  }
+  if (extra.n_dst == 0 && extra.packed == nullptr && extra.tau == nullptr) {
+    int rc = SGPT_OK;
+    if (launch_merge_sorted(src, nq, k, out_scores, out_ids, stream, &rc)) return rc;
   }
   if (static_cast<long long>(src.G) * ((src.L + 31) & ~31ll) >= (1ll << 32)) {
     set_error("top-k: %d lists of %lld entries exceed the 2^32-entry selection space", src.G, src.L);

@@ -12,6 +12,9 @@ struct TopkSrc {
   const uint2* packed = nullptr;     // (score bits, local index) pairs; overrides scores/ids when set
   int packed_global = 0;             // packed.y is a signed GLOBAL id (< 0 = empty slot) instead of a local index: the
                                      // gathered per-shard lists of a cross-shard merge (exclude applies)
+  int lists_sorted = 0;              // (packed_global) every list is sorted: score descending, id ascending on ties, empty
+                                     // slots at the tail — what sgpt_search_packed / the peer push write.  Selects the
+                                     // rank-merge kernel (no selection, no sort) when the lists fit in shared memory
   // cross-GPU gather: before touching the lists, wait until wait_flag[q] >= wait_target (system-scope acquire): the
   // producers of the lists are the selection kernels of the OTHER ranks, writing through NVLink peer mappings
   const unsigned int* wait_flag = nullptr;

@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--queries", type=int, default=128)
     ap.add_argument("--k", type=int, default=1001)
     ap.add_argument("--scores", default="cos_sim,dot")
+    ap.add_argument("--pre", default="none", choices=["none", "dirty", "burn"],
+                    help="what runs before every search: nothing, a 192 MB memset (dirty L2 lines to write back), or ~3 ms "
+                         "of bf16 matmuls (the power / clock state an encode step leaves behind)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.lib()
@@ -42,22 +45,44 @@ def main():
         for s0 in range(0, n, 250_000):
             shard.add(torch.randn(min(250_000, n - s0), D, generator=g, device=dev))
         q = torch.randn(a.queries, D, generator=g, device=dev)
+        dirty = torch.empty(192 << 20, dtype=torch.uint8, device=dev) if a.pre == "dirty" else None
+        ma = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16) if a.pre == "burn" else None
+
+        def pre():
+            if dirty is not None:
+                dirty.zero_()
+            if ma is not None:
+                for _ in range(4):
+                    torch.matmul(ma, ma)
         for sf in a.scores.split(","):
             for _ in range(3):
+                pre()
                 shard.search(q, a.k, sf)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            ms = 0.0
             for _ in range(a.steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                pre()
+                e0.record()
                 shard.search(q, a.k, sf)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / a.steps
+                e1.record()
+                if a.pre != "none":
+                    torch.cuda.synchronize()
+                    ms += e0.elapsed_time(e1) / a.steps
+            if a.pre == "none":  # back-to-back searches: one pair of events around the whole loop
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(a.steps):
+                    shard.search(q, a.k, sf)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / a.steps
             ms_cat = (ctypes.c_double * len(CATS))()
             n_cat = (ctypes.c_int64 * len(CATS))()
             lib.sgpt_profile_read(None, None, None)
             lib.sgpt_profile_enable(1)
             for _ in range(a.steps):
+                pre()
                 shard.search(q, a.k, sf)
             torch.cuda.synchronize()
             lib.sgpt_profile_enable(0)
@@ -69,7 +94,7 @@ def main():
             bytes_ = n * D * 2 + (n * 4 if sf == "cos_sim" else 0)
             scan_ms = ms_cat[5] / a.steps
             print(json.dumps({
-                "docs": n, "dim": D, "queries": a.queries, "k": a.k, "score": sf, "ms_per_search": round(ms, 4),
+                "docs": n, "dim": D, "queries": a.queries, "k": a.k, "score": sf, "before_each_search": a.pre, "ms_per_search": round(ms, 4),
                 "whole_search_frac_of_hbm": round(bytes_ / (ms / 1e3) / 1e9 / hbm, 3),
                 "scan_ms": round(scan_ms, 4), "scan_launches": n_cat[5] // a.steps,
                 "scan_frac_of_hbm": round(bytes_ / (scan_ms / 1e3) / 1e9 / hbm, 3) if scan_ms > 0 else None,
