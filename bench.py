@@ -660,6 +660,24 @@ def run_b200(args, rank, world, local_rank):
     e2e_s, h2d, d2h = e2e_pass(True, KR)
     e2e_enc_s, _, _ = e2e_pass(False, KR)  # encode-only variant (extra key)
 
+    # the same search issued back to back (no encode in between): inside a step it starts in the clock / power state the
+    # encoder leaves behind (SM and L2 clocks ~1.6 of 1.96 GHz under the power cap), which slows an HBM-streaming kernel
+    # through the L2's per-clock throughput cap (profiles/r02_search_phases_clock_state_and_query_count.jsonl)
+    iso_ms = maxr(time_search(lambda: search_step(queries), 50))
+    # a DRES-sized query batch (XS:54-60 encodes ALL queries before it scores): 1024 queries per call are scanned 256 at a
+    # time by CTA pairs (cta_group::2, M = 256), i.e. 4 passes over the shard instead of 8
+    large = None
+    if world == 1:
+        try:
+            q_large = torch.randn(1024, D, generator=gq, device=dev)
+            lg_ms = time_search(lambda: shard.search(q_large, kk, "cos_sim"), 10)
+            large = {"queries": 1024, "ms_per_search": lg_ms, "queries_per_s": 1024 / (lg_ms / 1e3),
+                     "similarity_tflops": 2.0 * 1024 * NDOCS * D / (lg_ms / 1e3) / 1e12,
+                     "passes_over_the_shard": 4, "corpus_GBps": 4 * (NDOCS * D * 2 + NDOCS * 4) / (lg_ms / 1e3) / 1e9}
+            del q_large
+        except Exception as e:  # noqa: BLE001 - reported, never fatal for the main line
+            large = {"error": repr(e)[:300]}
+
     # ---- strong scaling of the exact search over ONE 10 M-doc corpus split across the ranks -----------------------------
     # (north_star: "linear top-k scaling to 8 GPUs on a 10M-doc synthetic corpus"; the main line above is weak scaling at
     # 1 M docs per GPU.)  Two legs: D = 768 (the 125M model's embedding size) and D = 4096 (config 5: sgpt-bloom-7b1).  A
@@ -718,8 +736,9 @@ def run_b200(args, rank, world, local_rank):
     att_tflops = (att_flops * B * K) / (att_ms / 1e3) / 1e12 if att_ms > 0 else None
     sim_ms, sim_n = prof_ms[5], int(prof_n[5])
     sim_bytes = NDOCS * D * 2 + NDOCS * 4 + NQ * D * 2  # corpus shard + inv norms + queries
-    # the search streams the shard ONCE per query batch, split over two launches of the same kernel (sample pass +
-    # filtered pass): bytes per search / summed device time of both launches
+    # algorithmic bytes = the shard ONCE per query batch; the two launches of the kernel read it 1 + 1/stride times (the
+    # sampled tiles are scanned again by the filtered pass: <= 1/8, 3.7 % at this shape) — that re-read is overhead, not
+    # credit: bytes per search / summed device time of both launches
     sim_gbs = sim_bytes * K / (sim_ms / 1e3) / 1e9 if sim_ms > 0 else None
     whole_search_gbs = sim_bytes * KR / (sea_ms / 1e3) / 1e9
     traffic, traffic_src = measured_traffic()
@@ -742,7 +761,12 @@ def run_b200(args, rank, world, local_rank):
         "encode_ms_per_step": enc_ms / KR, "search_ms_per_step": sea_ms / KR,
         "search": {"value": qps, "unit": "queries/s", "corpus_docs": NDOCS * world, "top_k": TOPK,
                    "pairs_per_s": qps * NDOCS * world, "exchange": transport,
-                   "whole_search_frac_of_hbm": whole_search_gbs / pk["hbm"]},
+                   "whole_search_frac_of_hbm": whole_search_gbs / pk["hbm"],
+                   "back_to_back": {"ms_per_search": iso_ms, "queries_per_s": NQ / (iso_ms / 1e3),
+                                    "whole_search_frac_of_hbm": sim_bytes / (iso_ms / 1e3) / 1e9 / pk["hbm"],
+                                    "note": "50 searches in a row, nothing else on the GPU; the step figure above is "
+                                            "measured right after the encoder (power-capped clocks)"},
+                   "large_query_batch": large},
         "encoder_model_tflops": (lin_flops + att_flops) * B * world * KR / (enc_ms / 1e3) / 1e12,
         "roofline": {"kernel": "gemm_bf16_tn_kernel (tcgen05 linear layers)", "bound": "tensor", "achieved": gemm_tflops,
                      "peak": pk["tf_sustained"], "unit": "TFLOP/s",

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SGPT_ABI_VERSION 2
+#define SGPT_ABI_VERSION 3  /* 3: sgpt_topk_merge_packed requires sorted input lists; sgpt_debug_topk_timeline added */
 
 #define SGPT_OK 0
 #define SGPT_ERR_INVALID 1     /* bad argument / unsupported shape */

@@ -95,7 +95,7 @@ _SIGNATURES = {
     "sgpt_search_gather": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, vp, vp, vp, i64, vp]),
 }
 
-ABI_VERSION = 2  # include/sgpt_b200.h SGPT_ABI_VERSION these signatures / struct layouts were written for
+ABI_VERSION = 3  # include/sgpt_b200.h SGPT_ABI_VERSION these signatures / struct layouts were written for
 IPC_HANDLE_BYTES = 64
 
 _lib: Optional[C.CDLL] = None

@@ -158,9 +158,10 @@ static int pick_bn(int M, int N) {
   return (eff(256) * 1.25 >= eff(128)) ? 256 : 128;
 }
 
-FilterGeometry filter_geometry(long long tiles) {
-  const long long sms = sm_count();
-  const long long ctas = tiles < sms ? (tiles > 0 ? tiles : 1) : sms;
+FilterGeometry filter_geometry(long long tiles, int nq) {
+  // queries above one M-tile are scanned by CTA pairs (M = 256): one group per (pair, column half)
+  const long long units = nq > kGemmBM ? sm_count() / 2 : sm_count();
+  const long long ctas = tiles < units ? (tiles > 0 ? tiles : 1) : units;
   const long long per_cta = (tiles + ctas - 1) / ctas;
   FilterGeometry g;
   g.groups = static_cast<int>(2 * ctas);
@@ -168,32 +169,43 @@ FilterGeometry filter_geometry(long long tiles) {
   return g;
 }
 
+// nq <= 128: independent CTAs (M = 128).  128 < nq <= 256: CTA pairs running tcgen05.mma.cta_group::2 with M = 256 — each CTA
+// holds 128 of the queries and HALF of every corpus tile, so a scan moves half the corpus bytes per query through each SM
+// and the kernel turns from HBM-bound into tensor-bound (2 x the queries per pass over the shard).
+template <class P>
+static int launch_filter_gemm(const void* Q, const void* C, int nq, int n, int D, const P& p, cudaStream_t stream, TileMap tm) {
+  if (nq > kGemmBM) return launch_gemm<kSimBN, EpiFilterRows, 2>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
+  return launch_gemm<kSimBN, EpiFilterRows, 1>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
+}
+
 int launch_filter_candidates(const void* Q, const void* C, const float* q_scale, const float* c_scale,
                              const float* tau, const float* tau_hi, uint2* cand, int* counts, int* counts_back,
                              long long stride_q, int L, int group0, int nq, int n, int D, int tile_mode, int tile_stride,
                              cudaStream_t stream) {
-  SGPT_REQUIRE(nq <= kGemmBM, "filter GEMM: at most %d queries per launch (got %d)", kGemmBM, nq);
+  SGPT_REQUIRE(nq <= 2 * kGemmBM, "filter GEMM: at most %d queries per launch (got %d)", 2 * kGemmBM, nq);
   TileMap tm;
   tm.mode = tile_mode;
   tm.stride = tile_stride;
-  const FilterGeometry g = filter_geometry(tm.count((n + kSimBN - 1) / kSimBN));
+  const FilterGeometry g = filter_geometry(tm.count((n + kSimBN - 1) / kSimBN), nq);
   SGPT_REQUIRE(L >= g.L && (L % 2) == 0 && (stride_q % 2) == 0, "filter GEMM: candidate lists too small (L=%d < %d)", L,
                g.L);
-  EpiFilterRows::Params p{q_scale, c_scale, tau, tau_hi, cand, counts, counts_back, stride_q, L, group0, nq, nullptr, 0, 0};
-  return launch_gemm<kSimBN, EpiFilterRows>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
+  EpiFilterRows::Params p{q_scale, c_scale, tau, tau_hi, cand, counts, counts_back, stride_q, L, group0, nq, nullptr, 0, 0,
+                          nq > kGemmBM ? 1 : 0};
+  return launch_filter_gemm(Q, C, nq, n, D, p, stream, tm);
 }
 
 int launch_sample_maxima(const void* Q, const void* C, const float* q_scale, const float* c_scale, float* pool,
                          long long stride_p, int Lp, int nq, int n, int D, int tile_stride, cudaStream_t stream) {
-  SGPT_REQUIRE(nq <= kGemmBM, "sample GEMM: at most %d queries per launch (got %d)", kGemmBM, nq);
+  SGPT_REQUIRE(nq <= 2 * kGemmBM, "sample GEMM: at most %d queries per launch (got %d)", 2 * kGemmBM, nq);
   TileMap tm;
   tm.mode = 1;
   tm.stride = tile_stride;
-  const FilterGeometry g = filter_geometry(tm.count((n + kSimBN - 1) / kSimBN));
+  const FilterGeometry g = filter_geometry(tm.count((n + kSimBN - 1) / kSimBN), nq);
   SGPT_REQUIRE(Lp >= g.L / 4 && (Lp % 8) == 0 && (stride_p % 8) == 0 && stride_p >= static_cast<long long>(g.groups) * Lp,
                "sample GEMM: maxima lists too small (Lp=%d < %d)", Lp, g.L / 4);
-  EpiFilterRows::Params p{q_scale, c_scale, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nq, pool, stride_p, Lp};
-  return launch_gemm<kSimBN, EpiFilterRows>(Q, D, C, D, nq, n, D, p, stream, kCatScores, tm);
+  EpiFilterRows::Params p{q_scale, c_scale, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nq, pool, stride_p, Lp,
+                          nq > kGemmBM ? 1 : 0};
+  return launch_filter_gemm(Q, C, nq, n, D, p, stream, tm);
 }
 
 }  // namespace sgpt

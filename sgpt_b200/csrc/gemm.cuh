@@ -334,7 +334,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    Epi::finish(st, ep, ew * 32 + lane);
+    Epi::finish(st, ep, static_cast<int>(crank) * kGemmBM + ew * 32 + lane);  // row inside the CL x 128-row tile group
     if (clock_probe) {
       atomicAdd(&g_gemm_clock[0], static_cast<unsigned long long>(clock64() - probe_c0));
       atomicAdd(&g_gemm_clock[1], static_cast<unsigned long long>(global_timer_ns() - probe_t0));
@@ -951,6 +951,7 @@ struct EpiFilterRows {
     float* pool;             // sample mode: [M][groups][Lp] block maxima (cand / counts / tau unused)
     long long stride_p;      // floats between consecutive queries' blocks of `pool`
     int Lp;                  // floats per (query, group): 32 x tiles per CTA
+    int pair;                // 1: launched as CTA pairs (cta_group::2, M = 256 queries per scan)
   };
   struct State {
     int cnt;    // front entries (sample mode: maxima written)
@@ -964,8 +965,11 @@ struct EpiFilterRows {
     float rs, tau, tau_hi;
   };
   static constexpr int kEpiWarps = 8;
+  // one group per (cluster, column half): with CTA pairs (Params::pair = 1: up to 256 queries per scan, rank r of the pair
+  // owns queries 128 r .. 128 r + 127 and all 256 documents of the tile) both CTAs of a pair write the SAME group's lists —
+  // of different queries
   static __device__ __forceinline__ int group_of(const Params& p) {
-    return p.group0 + static_cast<int>(blockIdx.x) * 2 + static_cast<int>(threadIdx.x >> 7);
+    return p.group0 + static_cast<int>(blockIdx.x >> p.pair) * 2 + static_cast<int>(threadIdx.x >> 7);
   }
   static __device__ __forceinline__ void init(State& st, const Params&, int, uint64_t*) { st.cnt = 0; st.cnt_b = 0; }
   template <int COLS, int kSlabBytes>

@@ -49,17 +49,18 @@ Plan make_plan(int nq, int64_t n, int k) {
   const int sms = sm_count();
   // the sample: every `stride`-th tile, at most one per SM (one round) and at most an eighth of the shard (it is scanned
   // twice); a sampled tile yields kSimBN / 4 maxima per query and the sample must hold 2 k of them
+  // (more than 128 queries are scanned by CTA pairs, M = 256: the same ~one tile per SM then means two per pair)
   p.stride = static_cast<int>((n_tiles + sms - 1) / sms);
   if (p.stride < 8) p.stride = 8;
   const int64_t sampled_tiles = (n_tiles + p.stride - 1) / p.stride;
-  const FilterGeometry ga = filter_geometry(sampled_tiles);  // one tile per CTA: L = kSimBN / 2
+  const FilterGeometry ga = filter_geometry(sampled_tiles, nq);  // L = kSimBN / 2 per tile a CTA (pair) visits
   p.Lp = ga.L / 4;
   p.stride_p = static_cast<int64_t>(ga.groups) * p.Lp;
   // (below two tiles per SM the dense score matrix is small and two launches beat four)
-  p.two_pass = nq <= 128 && n_tiles >= 2ll * sms && sampled_tiles * (kSimBN / 4) >= 2ll * k &&
+  p.two_pass = nq <= 256 && n_tiles >= 2ll * sms && sampled_tiles * (kSimBN / 4) >= 2ll * k &&
                p.stride_p <= kMaxTauSample && (p.Lp % 8) == 0;
   if (!p.two_pass) return p;
-  p.gb = filter_geometry(n_tiles);
+  p.gb = filter_geometry(n_tiles, nq);
   p.stride_b = static_cast<int64_t>(p.gb.groups) * p.gb.L;
   // upper threshold: ~2.5 k documents of the whole shard expected above it (relative sd 1 / sqrt(k_hi): with k_hi >= 24
   // the front lists hold k entries in all but a negligible share of the queries; the others take the back lists too)
@@ -77,14 +78,23 @@ Plan make_plan(int nq, int64_t n, int k) {
 
 }  // namespace
 
-constexpr int kQueryBlock = 128;  // queries per scan (one M-tile of the similarity GEMM)
+// queries per scan of the two-pass path: 256 = one M-tile per CTA of a pair (gemm.cu launch_filter_gemm); batches of up
+// to 128 queries run on independent CTAs.  The dense path (small shards) takes the same blocks.
+constexpr int kQueryBlock = 256;
 
-extern "C" int64_t sgpt_search_workspace_bytes(int nq, int64_t n, int k) {
-  if (nq > kQueryBlock) nq = kQueryBlock;  // larger batches are processed in blocks that reuse the workspace
+static int64_t plan_bytes(int nq, int64_t n, int k) {
   const Plan p = make_plan(nq, n, k);
   if (!p.two_pass) return static_cast<int64_t>(nq) * padded_cols(n) * 4 + 256;
   return align256(static_cast<int64_t>(nq) * p.stride_p * 4) + align256(static_cast<int64_t>(nq) * p.stride_b * 8) +
          2 * align256(static_cast<int64_t>(p.gb.groups) * nq * 4) + 2 * align256(nq * 4) + 256;
+}
+
+extern "C" int64_t sgpt_search_workspace_bytes(int nq, int64_t n, int k) {
+  if (nq <= 128) return plan_bytes(nq, n, k);
+  // larger batches are processed in blocks of kQueryBlock that reuse the workspace; the last block may hold <= 128 queries
+  // and then takes the single-CTA plan, whose lists are laid out differently
+  const int64_t a = plan_bytes(nq < kQueryBlock ? nq : kQueryBlock, n, k), b = plan_bytes(128, n, k);
+  return a > b ? a : b;
 }
 
 // One shard, all query blocks.  `fin` carries the packed destinations of the final selection (TopkExtra::dst/flag:

@@ -205,7 +205,10 @@ def _assert_same_topk(scores_dev, ids_dev, full, k, id_base=0):
                                          (1, 3000, 768, 1001, "cos_sim"), (7, 600, 64, 1001, "cos_sim"),
                                          # >= 8 x 148 corpus tiles: the two-pass threshold-filter path; 130 queries =
                                          # two query blocks; ragged last tile (n % 256 != 0)
-                                         (130, 320001, 64, 1001, "cos_sim"), (5, 310000, 128, 10, "dot")])
+                                         (130, 320001, 64, 1001, "cos_sim"), (5, 310000, 128, 10, "dot"),
+                                         # more than 128 queries: CTA pairs scan 256 queries per pass (M = 256); 300 =
+                                         # one pair block + a 44-query block on the single-CTA plan; 256 = a full pair
+                                         (300, 320001, 64, 100, "dot"), (256, 150001, 128, 1001, "cos_sim")])
 def test_search_identical_topk_ids(nq, n, D, k, fn):
     from sgpt_b200 import CorpusShard
 

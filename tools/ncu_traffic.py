@@ -22,8 +22,8 @@ CLASSES = [  # (class, regex on the demangled kernel name) — first match wins
     ("linear_gemm", r"gemm_bf16_tn_kernel"),
     ("attention", r"attention_"),
     ("layernorm", r"layernorm_"),
-    ("topk", r"topk_"),
-    ("pool", r"pool_kernel|row_stats_kernel|l2_scale_rows"),
+    ("topk", r"topk_|tau_select|merge_sorted"),
+    ("pool", r"pool_|row_stats_kernel|l2_scale_rows"),
     ("embed", r"embed_kernel"),
 ]
 
