@@ -86,7 +86,7 @@ static int64_t plan_bytes(int nq, int64_t n, int k) {
   const Plan p = make_plan(nq, n, k);
   if (!p.two_pass) return static_cast<int64_t>(nq) * padded_cols(n) * 4 + 256;
   return align256(static_cast<int64_t>(nq) * p.stride_p * 4) + align256(static_cast<int64_t>(nq) * p.stride_b * 8) +
-         2 * align256(static_cast<int64_t>(p.gb.groups) * nq * 4) + 2 * align256(nq * 4) + 256;
+         2 * align256(static_cast<int64_t>(p.gb.groups) * nq * 4) + 3 * align256(nq * 4) + 256;
 }
 
 extern "C" int64_t sgpt_search_workspace_bytes(int nq, int64_t n, int k) {
@@ -153,6 +153,8 @@ static int search_impl(const void* Q, const void* Cm, const float* q_scale, cons
   float* tau = reinterpret_cast<float*>(w);
   w += align256(nq * 4);
   float* tau_hi = reinterpret_cast<float*>(w);
+  w += align256(nq * 4);
+  int* need_generic = reinterpret_cast<int*>(w);
 
   // pass A: block maxima of the sampled tiles -> admission thresholds
   int rc = launch_sample_maxima(Q, Cm, q_scale, c_scale, pool, p.stride_p, p.Lp, nq, static_cast<int>(n), D, p.stride, stream);
@@ -174,6 +176,11 @@ static int search_impl(const void* Q, const void* Cm, const float* q_scale, cons
   src.L = p.gb.L;
   src.stride_g = p.gb.L;
   src.stride_q = p.stride_b;
+  // normal case (front parts hold k .. 4096 entries): packed, sorted, done; the generic kernel answers the other queries
+  bool front = false;
+  rc = launch_front_select(src, nq, k, out_scores, out_ids, stream, fin, need_generic, &front);
+  if (rc != SGPT_OK) return rc;
+  if (front) src.run_flag = need_generic;
   return launch_topk_select(src, nq, k, out_scores, out_ids, stream, fin);
 }
 

@@ -7,6 +7,7 @@
 //   - a filtered candidate list   packed (score, local idx) pairs with a per-query count
 //   - G gathered lists            [G, nq, L] scores + ids (cross-chunk / cross-shard merge; id < 0 = empty slot)
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/sgpt_b200.h"
 #include "common.cuh"
@@ -78,12 +79,16 @@ constexpr int kTopkThreads = 1024;
 // Phase timeline of the selection kernel (sgpt_debug_topk_timeline): thread 0 of CTA 0 stamps %globaltimer at the phase
 // boundaries of every launch; the last launch's stamps stay readable.  One store per phase: no measurable cost.
 __device__ unsigned long long g_topk_timeline[16];
+__device__ __forceinline__ unsigned long long timeline_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void timeline_mark(int slot) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_topk_timeline[slot] = t;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_topk_timeline[slot] = timeline_now();
+}
+__device__ __forceinline__ void timeline_set(int slot, unsigned long long t) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_topk_timeline[slot] = t;
 }
 
 // Sum of `v` over the 1024 threads of the CTA, returned to every thread; ONE barrier per call (scratch double-buffered by
@@ -163,6 +168,38 @@ __device__ __forceinline__ void for_each_elem(const TopkSrc& s, int nl, int q, i
   }
 }
 
+// Final outputs of a selection: skey[i] / sid[i], i < k, hold the winners in order (key 0 = empty slot).  fp32 scores + int64
+// ids and/or the packed 8-byte entries written to this rank's buffer and the peers' gather buffers (16-byte-aligned rows;
+// over NVLink for peer-mapped destinations), then one system-scope release per destination.  Called by ALL threads.
+__device__ __forceinline__ void write_topk_outputs(int q, int k, const uint32_t* skey, const long long* sid,
+                                                   float* __restrict__ out_scores, long long* __restrict__ out_ids,
+                                                   const TopkExtra& extra, int tid) {
+  if (out_scores != nullptr) {
+    for (int i = tid; i < k; i += kTopkThreads) {
+      const uint32_t key = skey[i];
+      out_scores[static_cast<size_t>(q) * k + i] = key ? key_score(key) : -INFINITY;
+      out_ids[static_cast<size_t>(q) * k + i] = key ? sid[i] : -1;
+    }
+  }
+  if (extra.n_dst > 0) {
+    for (int p = 0; p < extra.n_dst; ++p) {
+      uint2* row = extra.dst[p] + (static_cast<size_t>(extra.dst_slot) * extra.dst_nq + q) * k;
+      for (int i = tid; i < k; i += kTopkThreads) {
+        const uint32_t key = skey[i];
+        row[i] = key ? make_uint2(__float_as_uint(key_score(key)), static_cast<uint32_t>(static_cast<int32_t>(sid[i])))
+                     : make_uint2(0xff800000u, 0xffffffffu);  // (-inf, -1)
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      for (int p = 0; p < extra.n_dst; ++p)
+        if (extra.flag[p] != nullptr)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(extra.flag[p] + q) : "memory");
+    }
+  }
+}
+
 // sorted[] / sorted_id[]: KP (power of two >= k) slots in dynamic smem
 // ckeys[]: when the flat (padded) index space of the query fits `cache_keys` entries of dynamic smem behind the sort
 // buffers, every key is fetched from global memory ONCE (one warp per list, several loads in flight) and the three
@@ -189,8 +226,11 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
-  timeline_mark(0);
+  const unsigned long long t_entry = timeline_now();
   pdl_sync();  // programmatic dependent launch: see common.cuh
+  // two-pass search: the front-list kernel (front_select_kernel) has already answered this query
+  if (src.run_flag != nullptr && src.run_flag[q] == 0) return;  // (block-uniform)
+  timeline_set(0, t_entry);
   timeline_mark(1);
   if (src.wait_flag != nullptr) {
     // cross-GPU gather: the lists of this query are complete once every rank has signalled (topk.cuh TopkExtra::flag)
@@ -578,32 +618,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
     }
   }
   timeline_mark(9);
-  if (out_scores != nullptr) {
-    for (int i = tid; i < k; i += kTopkThreads) {
-      const uint32_t key = skey[i];
-      out_scores[static_cast<size_t>(q) * k + i] = key ? key_score(key) : -INFINITY;
-      out_ids[static_cast<size_t>(q) * k + i] = key ? sid[i] : -1;
-    }
-  }
-  // packed final output to this rank's buffer and/or the peers' gather buffers (16-byte stores of two entries; over
-  // NVLink for peer-mapped destinations), then one system-scope release per destination
-  if (extra.n_dst > 0) {
-    for (int p = 0; p < extra.n_dst; ++p) {
-      uint2* row = extra.dst[p] + (static_cast<size_t>(extra.dst_slot) * extra.dst_nq + q) * k;
-      for (int i = tid; i < k; i += kTopkThreads) {
-        const uint32_t key = skey[i];
-        row[i] = key ? make_uint2(__float_as_uint(key_score(key)), static_cast<uint32_t>(static_cast<int32_t>(sid[i])))
-                     : make_uint2(0xff800000u, 0xffffffffu);  // (-inf, -1)
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      for (int p = 0; p < extra.n_dst; ++p)
-        if (extra.flag[p] != nullptr)
-          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(extra.flag[p] + q) : "memory");
-    }
-  }
+  write_topk_outputs(q, k, skey, sid, out_scores, out_ids, extra, tid);
   // optional side outputs for the two-pass search: winners re-packed as the head of another candidate list, and the
   // k-th best score as that query's admission threshold
   if (extra.packed != nullptr) {
@@ -615,6 +630,187 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_select_kernel(TopkSrc sr
   if (extra.tau != nullptr && tid == 0)
     extra.tau[q] = (kk >= static_cast<uint32_t>(k)) ? key_score(prefix) : -INFINITY;  // key of the k-th best
   timeline_mark(10);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Final selection of the two-pass search for the NORMAL case: the front parts of a query's candidate lists (the scores
+// above the upper threshold, ~2.5 k per query) hold at least k and at most kFrontCap entries.  Then nothing has to be
+// selected at all: the entries are packed end to end into shared memory as 64-bit composites (order key << 32 | ~local
+// index: larger = earlier, ties by ascending document id), sorted by one bitonic network over 4096 slots — four per
+// thread: strides 1 and 2 stay inside a thread, strides 4..64 are warp shuffles, only strides >= 128 go through shared
+// memory — and the first k are the answer, ids included (no histogram, no pivot, no compaction, no second trip to global
+// memory for the ids).  Queries outside that case (front parts short: the back parts are needed; or more than kFrontCap
+// ties) set need_generic[q] and are answered by topk_select_kernel, which is launched right behind with
+// TopkSrc::run_flag = need_generic and returns at once for every other query.
+// Loads: 4 lanes per list, 16 bytes (two entries) per lane, 256 lists of the query in flight at a time.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFrontCap = 4096;
+
+__device__ __forceinline__ void cx_sorted(unsigned long long& lo, unsigned long long& hi, bool desc) {
+  const bool swap = desc ? (lo < hi) : (lo > hi);
+  if (swap) {
+    const unsigned long long t = lo;
+    lo = hi;
+    hi = t;
+  }
+}
+
+__global__ void __launch_bounds__(kTopkThreads, 1) front_select_kernel(TopkSrc src, int k, int KP,
+                                                                    float* __restrict__ out_scores,
+                                                                    long long* __restrict__ out_ids, TopkExtra extra,
+                                                                    int* __restrict__ need_generic) {
+  extern __shared__ __align__(16) uint8_t dsm_front[];  // KP >= 4 (launcher): every region below is 16-byte aligned
+  uint32_t* skey = reinterpret_cast<uint32_t*>(dsm_front);
+  long long* sid = reinterpret_cast<long long*>(dsm_front + static_cast<size_t>(KP) * 4);
+  unsigned long long* cbuf = reinterpret_cast<unsigned long long*>(dsm_front + static_cast<size_t>(KP) * 12);  // [kFrontCap]
+  __shared__ uint32_t s_coff[kMaxFlatLists + 1];  // compact offsets of the lists (exclusive prefix of their lengths)
+  __shared__ uint32_t warp_tot[32];
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const unsigned long long t_entry = timeline_now();
+  pdl_sync();
+  const unsigned long long t_dep = timeline_now();
+  const int G = src.G;  // <= kMaxFlatLists (launcher)
+  const uint32_t mylen = (tid < G) ? static_cast<uint32_t>(list_len(src, q, tid)) : 0u;
+  uint32_t incl = mylen;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+#pragma unroll 8
+  for (int w = 0; w < 32; ++w) {
+    const uint32_t v = warp_tot[w];
+    base += (w < warp) ? v : 0u;
+    total += v;
+  }
+  const bool mine = total >= static_cast<uint32_t>(k) && total <= static_cast<uint32_t>(kFrontCap);  // block-uniform
+  if (tid == 0) need_generic[q] = mine ? 0 : 1;
+  if (!mine) return;
+  timeline_set(0, t_entry);
+  timeline_set(1, t_dep);
+  timeline_set(2, t_dep);
+  if (tid < G) s_coff[tid] = base + incl - mylen;
+  if (tid == 0) s_coff[G] = total;
+  for (uint32_t i = total + tid; i < static_cast<uint32_t>(kFrontCap); i += kTopkThreads) cbuf[i] = 0ull;  // sorts last
+  __syncthreads();
+  timeline_mark(3);
+  {
+    const uint32_t sl = lane & 3u;
+    for (int g = warp * 8 + static_cast<int>(lane >> 2); g < G; g += (kTopkThreads / 32) * 8) {
+      const uint32_t c0 = s_coff[g], len = s_coff[g + 1] - c0;
+      const uint2* lst = src.packed + static_cast<long long>(g) * src.stride_g + static_cast<long long>(q) * src.stride_q;
+      for (uint32_t idx = 2u * sl; idx < len; idx += 8u) {  // (the second entry of a pair may lie beyond len: unused slot of the list)
+        const uint4 v = *reinterpret_cast<const uint4*>(lst + idx);
+        cbuf[c0 + idx] = (static_cast<unsigned long long>(score_key(__uint_as_float(v.x))) << 32) | static_cast<uint32_t>(~v.y);
+        if (idx + 1u < len)
+          cbuf[c0 + idx + 1u] = (static_cast<unsigned long long>(score_key(__uint_as_float(v.z))) << 32) | static_cast<uint32_t>(~v.w);
+      }
+    }
+  }
+  __syncthreads();
+  timeline_mark(4);
+  timeline_mark(5);
+  timeline_mark(6);
+  timeline_mark(7);
+  timeline_mark(8);
+  // ---- bitonic sort of the kFrontCap slots, descending; thread t owns slots 4 t .. 4 t + 3 ----
+  unsigned long long e[4];
+  {
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(cbuf + 4 * tid);
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(cbuf + 4 * tid + 2);
+    e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y;
+  }
+#pragma unroll 1
+  for (int size = 2; size <= kFrontCap; size <<= 1) {
+    const bool desc = ((4 * tid) & size) == 0;  // direction of this thread's run (all four slots share it for size >= 4)
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 128) {
+        __syncthreads();  // the previous exchange's readers are done
+        *reinterpret_cast<ulonglong2*>(cbuf + 4 * tid) = make_ulonglong2(e[0], e[1]);
+        *reinterpret_cast<ulonglong2*>(cbuf + 4 * tid + 2) = make_ulonglong2(e[2], e[3]);
+        __syncthreads();
+        const int pt = (4 * tid) ^ stride;
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(cbuf + pt);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(cbuf + pt + 2);
+        const unsigned long long o[4] = {a.x, a.y, b.x, b.y};
+        const bool keep_max = (((4 * tid) & stride) == 0) == desc;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e[r] = keep_max ? (e[r] > o[r] ? e[r] : o[r]) : (e[r] < o[r] ? e[r] : o[r]);
+      } else if (stride >= 4) {
+        const int lm = stride >> 2;  // partner lane = lane ^ lm
+        const bool keep_max = ((lane & lm) == 0) == desc;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t olo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(e[r]), lm);
+          const uint32_t ohi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(e[r] >> 32), lm);
+          const unsigned long long o = (static_cast<unsigned long long>(ohi) << 32) | olo;
+          e[r] = keep_max ? (e[r] > o ? e[r] : o) : (e[r] < o ? e[r] : o);
+        }
+      } else if (stride == 2) {  // (size >= 4)
+        cx_sorted(e[0], e[2], desc);
+        cx_sorted(e[1], e[3], desc);
+      } else {  // stride 1
+        if (size == 2) {  // slots 4t, 4t+1: descending pair; 4t+2, 4t+3: ascending pair
+          cx_sorted(e[0], e[1], true);
+          cx_sorted(e[2], e[3], false);
+        } else {
+          cx_sorted(e[0], e[1], desc);
+          cx_sorted(e[2], e[3], desc);
+        }
+      }
+    }
+  }
+  __syncthreads();  // cbuf readers of the last exchange are done; skey / sid are separate arrays anyway
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = 4 * tid + r;
+    if (i < KP) {
+      const uint32_t key = static_cast<uint32_t>(e[r] >> 32);
+      skey[i] = key;
+      sid[i] = key ? src.id_base + static_cast<long long>(~static_cast<uint32_t>(e[r])) : -1;
+    }
+  }
+  __syncthreads();
+  timeline_mark(9);
+  write_topk_outputs(q, k, skey, sid, out_scores, out_ids, extra, tid);
+  timeline_mark(10);
+}
+
+// Launch of the front-list kernel; *taken = false when the source does not qualify (then only the generic kernel runs).
+int launch_front_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
+                        const TopkExtra& extra, int* need_generic, bool* taken) {
+  *taken = false;
+  if (src.packed == nullptr || src.packed_global || src.counts == nullptr || src.counts_back == nullptr ||
+      src.G > kMaxFlatLists || (src.stride_g & 1) != 0 || (src.stride_q & 1) != 0 || k <= 0 || k > kFrontCap ||
+      need_generic == nullptr)
+    return SGPT_OK;
+  // OFF by default: measured SLOWER than the generic kernel on B200 (profiles/r02_search_phases_call29_*.jsonl): sorting all
+  // 4096 slots is 78 compare-exchange stages over 4 slots per thread = 30 us, against 20 us for compaction + exact k-th key +
+  // placing + sorting only the 1024 winners; the denser load (3.3 vs 5.3 us) does not pay for it.  SGPT_FRONT_SELECT=1
+  // (read per call) keeps it testable.
+  {
+    const char* e = getenv("SGPT_FRONT_SELECT");
+    if (!(e != nullptr && e[0] == '1')) return SGPT_OK;
+  }
+  int KP = 4;
+  while (KP < k) KP <<= 1;
+  const size_t dsm = static_cast<size_t>(KP) * 12 + static_cast<size_t>(kFrontCap) * 8;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
+    SGPT_CHECK_CUDA(cudaFuncSetAttribute(front_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  }
+  LaunchScope _ls(kCatTopk, stream);
+  SGPT_CHECK_CUDA(launch_kernel(front_select_kernel, dim3(nq), dim3(kTopkThreads), dsm, stream, src, k, KP, out_scores,
+                                reinterpret_cast<long long*>(out_ids), extra, need_generic));
+  *taken = true;
+  return SGPT_OK;
 }
 
 // Admission thresholds of the two-pass search (search.cu) from the sampled block maxima (gemm.cuh EpiFilterRows, sample

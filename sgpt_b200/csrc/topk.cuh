@@ -24,6 +24,9 @@ struct TopkSrc {
   // (slots L - count .. L - 1) — the candidates between the search's lower and upper admission thresholds.  The
   // selection reads them (as lists G .. 2G-1) only when the front parts together hold fewer than k entries.
   const int32_t* counts_back = nullptr;
+  // per-query switch (two-pass search): the selection kernel returns at once for queries with run_flag[q] == 0 — they were
+  // answered by the front-list kernel (launch_front_select) launched just before it
+  const int* run_flag = nullptr;
   long long id_base = 0;
   int G = 1;                         // lists per query
   int nq = 0;
@@ -53,6 +56,13 @@ struct TopkExtra {
 // out_scores / out_ids may be null when only the side outputs are wanted.
 int launch_topk_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
                        const TopkExtra& extra = TopkExtra());
+
+// Final selection of the two-pass search from the FRONT parts of two-sided lists alone (topk.cu front_select_kernel): answers
+// every query whose front parts hold between k and 4096 entries and clears need_generic[q] for it; sets need_generic[q] = 1
+// for the others, which launch_topk_select (with TopkSrc::run_flag = need_generic) then answers.  *taken = false when the
+// source does not qualify (nothing launched, need_generic untouched).
+int launch_front_select(const TopkSrc& src, int nq, int k, float* out_scores, int64_t* out_ids, cudaStream_t stream,
+                        const TopkExtra& extra, int* need_generic, bool* taken);
 
 // tau_lo[q] / tau_hi[q] = lower bounds (tight to 2^-11 relative) of the k-th / k_hi-th largest of the `total` floats at
 // pool + q * stride_q (0xffffffff = unused slot; total % 8 == 0, total <= kMaxTauSample, 1 <= k_hi <= k); -inf when fewer

@@ -432,6 +432,24 @@ def test_search_two_pass_front_and_back_lists(k_hi, monkeypatch):
     _assert_same_topk(s, i, full, k, id_base=7)
 
 
+def test_search_front_list_kernel_opt_in(monkeypatch):
+    """SGPT_FRONT_SELECT=1: the final selection of the two-pass search by the front-list kernel (pack the entries above the
+    upper threshold, sort all of them, take the first k) instead of the generic selection kernel — measured slower and off
+    by default, but it must stay exact; queries it declines (front parts short) fall through to the generic kernel."""
+    from sgpt_b200 import CorpusShard
+
+    monkeypatch.setenv("SGPT_FRONT_SELECT", "1")
+    nq, n, D, k = 37, 130001, 128, 1001
+    q, c = planted_corpus(n, D, nq, seed=78)
+    shard = CorpusShard.from_embeddings(c.cuda(), device="cuda:0", id_base=3)
+    full = _oracle_topk_on_stored(q, c, k, "cos_sim")
+    s, i = shard.search(q.cuda(), k, "cos_sim")
+    _assert_same_topk(s, i, full, k, id_base=3)
+    monkeypatch.setenv("SGPT_SEARCH_K_HI", "1")  # front parts nearly empty: every query is declined
+    s, i = shard.search(q.cuda(), k, "cos_sim")
+    _assert_same_topk(s, i, full, k, id_base=3)
+
+
 def test_search_two_pass_with_massive_ties():
     """Two-pass filter path on a corpus with only 40 distinct vectors (every score value is shared by ~7750 documents):
     the admission threshold sits inside a tie group, which must not lose candidates."""

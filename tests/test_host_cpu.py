@@ -36,6 +36,28 @@ def test_library_exports_every_declared_symbol():
     assert lib.sgpt_topk(None, 4, 1, 8, 3, 0, None, None, None, None) == 1  # lds < n
 
 
+def test_search_workspace_plan_is_consistent_across_query_blocks():
+    """Host logic of the fused search (csrc/search.cu make_plan / sgpt_search_workspace_bytes; no GPU needed — the SM count
+    falls back to 148): batches above 256 queries are processed in blocks that REUSE one workspace, whose last block may be
+    small enough for the single-CTA plan with its different list layout, so the size for nq queries must cover every block
+    size that can occur; small shards take the dense path (nq x n fp32 scores)."""
+    from sgpt_b200 import _lib
+
+    ws = _lib.lib().sgpt_search_workspace_bytes
+    n, k = 1_000_000, 1001
+    for nq in (129, 200, 256, 300, 1000, 5000):
+        need = ws(nq, n, k)
+        blocks = {min(256, nq)} | ({nq % 256} if nq > 256 and nq % 256 else set())
+        for nb in blocks:
+            assert need >= ws(nb, n, k), (nq, nb)
+    assert ws(128, n, k) >= ws(7, n, k) > 0
+    # two-pass lists are worst-case sized: ~8 bytes per (query, document)
+    assert 0.9 < ws(128, n, k) / (128 * n * 8) < 1.2
+    # below two corpus tiles per SM (75 776 documents at 148 SMs): dense scores, 4 bytes per (query, document)
+    assert ws(16, 50_000, k) == 16 * 50_000 * 4 + 256
+    assert ws(16, 80_000, k) > 16 * 80_000 * 4 + 256
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from sgpt_b200 import _lib
 
