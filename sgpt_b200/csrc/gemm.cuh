@@ -1014,6 +1014,7 @@ struct EpiFilterRows {
     const float rs = st.rs;
     const bool pooled = (p.pool != nullptr);
     const float tau = st.tau, tau_hi = st.tau_hi;
+    const bool nan_path = __any_sync(0xffffffffu, !pooled && tau <= -1.0f) != 0;  // warp-uniform
     const float csv[4] = {st.cs.x, st.cs.y, st.cs.z, st.cs.w};
     uint2* dst = p.cand + static_cast<long long>(qok ? q : 0) * p.stride_q + static_cast<long long>(group_of(p)) * p.L;
     int cnt = st.cnt, cnt_b = st.cnt_b;
@@ -1029,11 +1030,19 @@ struct EpiFilterRows {
 #pragma unroll
       for (int i = 0; i < 32; ++i) cs[i] = __shfl_sync(0xffffffffu, csv[i & 3], (c >> 2) + (i >> 2));
       tmem_ld_wait();
+      // XS:99 maps a NaN score to -1.  While tau > -1 (always, except for degenerate corpora) a NaN fails `x >= tau` exactly
+      // as its image -1 would, and in sample mode fmaxf drops it (a smaller maximum keeps tau a valid lower bound): the
+      // explicit mapping (two instructions per score) is only executed when some row of the warp could admit a -1.
       float x[32];
+      if (nan_path) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float s = __uint_as_float(v[i]) * rs * cs[i];
-        x[i] = (s != s) ? -1.f : s;  // XS:99 NaN -> -1
+        for (int i = 0; i < 32; ++i) {
+          const float s = __uint_as_float(v[i]) * rs * cs[i];
+          x[i] = (s != s) ? -1.f : s;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) * rs * cs[i];
       }
       if (pooled) {
         // sample pass: maxima of 4 consecutive documents, two 16-byte stores (cnt is a multiple of 8, the lists 32-byte

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 GPU call 28: evidence for profiles/ with the final kernels — launch list + DRAM traffic of a bench window, full ncu
+# round-2 GPU call 28 (run from call 29 / 31): evidence for profiles/ with the final kernels — launch list + DRAM traffic of a bench window, full ncu
 # captures of the top kernels (GEMM with gelu epilogue, residual GEMM, attention, LayerNorm, both search scans, selections)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
@@ -25,7 +25,7 @@ for _ in range(3):
     sh.search(q, 1001, "cos_sim")
 torch.cuda.synchronize()
 PY
-N="ncu --set full --clock-control none --import-source on"
+N="ncu --set full --clock-control none --import-source on --kernel-name-base demangled"
 timeout 600 $N -k regex:'gemm_bf16_tn_kernel.*OpTmaBiasActBF16.*1' -s 24 -c 1 -o gpurun_out/r2_28_gemm_gelu python /tmp/enc125.py > gpurun_out/r2_28_ncu_a.log 2>&1
 timeout 600 $N -k regex:'gemm_bf16_tn_kernel.*OpTmaResidAddBF16' -s 48 -c 1 -o gpurun_out/r2_28_gemm_resid python /tmp/enc125.py > gpurun_out/r2_28_ncu_b.log 2>&1
 timeout 600 $N -k regex:attention_tc -s 24 -c 1 -o gpurun_out/r2_28_attn_single python /tmp/enc125.py > gpurun_out/r2_28_ncu_c.log 2>&1
@@ -33,4 +33,4 @@ timeout 600 $N -k regex:layernorm_bf16 -s 48 -c 1 -o gpurun_out/r2_28_layernorm 
 # the two launches of the similarity GEMM of one search: sample pass (even index), filter pass (odd index)
 timeout 600 $N -k regex:'gemm_bf16_tn_kernel.*EpiFilterRows' -s 4 -c 2 -o gpurun_out/r2_28_simscan python /tmp/enc125.py > gpurun_out/r2_28_ncu_e.log 2>&1
 timeout 600 $N -k regex:'topk_select|tau_select' -s 4 -c 2 -o gpurun_out/r2_28_select python /tmp/enc125.py > gpurun_out/r2_28_ncu_f.log 2>&1
-ls -la gpurun_out/*.ncu-rep | head; tail -2 gpurun_out/r2_28_ncu_e.log
+ls -la gpurun_out/*.ncu-rep | head -12; tail -2 gpurun_out/r2_28_ncu_e.log
