@@ -958,8 +958,10 @@ static bool launch_merge_sorted(const TopkSrc& src, int nq, int k, float* out_sc
                                 int* rc) {
   constexpr size_t kDynMax = 200 * 1024;
   const size_t bytes = static_cast<size_t>(src.G) * static_cast<size_t>(src.L) * 8;
+  // Measured on B200 (profiles/r02_bench_line_final_{2,8}gpu.json): 2 lists 0.016 ms against 0.032 ms for selecting again,
+  // 8 lists 0.047 against 0.031 ms — every entry pays one binary search per OTHER list — so only few lists are rank-merged.
   if (!src.lists_sorted || src.packed == nullptr || !src.packed_global || src.counts != nullptr || out_scores == nullptr ||
-      out_ids == nullptr || bytes > kDynMax || src.G < 1)
+      out_ids == nullptr || bytes > kDynMax || src.G < 1 || src.G > 3)
     return false;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
