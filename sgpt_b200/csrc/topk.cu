@@ -1,11 +1,19 @@
-// S2/S3: exact row-wise top-k selection (torch.topk at XS:102-108; heapq.nlargest merge at XS:121-132).
+// S2/S3: exact row-wise top-k selection (torch.topk at XS:102-108; heapq.nlargest merge at XS:121-132) and the kernels
+// around it.
 //
-// One CTA (1024 threads) per query.  MSD radix select on an order-preserving 32-bit image of the fp32 score
-// (11 + 11 + 10 bits, warp-aggregated shared-memory histograms), then a gather of the k winners and an in-smem
-// bitonic sort (score descending, id ascending).  The same kernel serves three sources through `TopkSrc`:
-//   - a dense score row           scores[q, 0..n)                       (ids = id_base + column)
-//   - a filtered candidate list   packed (score, local idx) pairs with a per-query count
-//   - G gathered lists            [G, nq, L] scores + ids (cross-chunk / cross-shard merge; id < 0 = empty slot)
+//   topk_select_kernel    one CTA (1024 threads) per query; keys = an order-preserving 32-bit image of the fp32 score, cached
+//                         in shared memory.  Fast path: sample pivot -> one compaction pass -> exact k-th key by a radix-4
+//                         bitwise search on register-resident keys; fallback: MSD radix select (11 + 11 + 10 bits,
+//                         warp-aggregated histograms).  Then the k winners are placed, their ids fetched, and sorted
+//                         (score descending, id ascending).  Sources through `TopkSrc`:
+//                           - a dense score row           scores[q, 0..n)                    (ids = id_base + column)
+//                           - filtered candidate lists    packed (score, local idx) pairs with per-(list, query) counts,
+//                                                         optionally two-sided (front / back parts, topk.cuh)
+//                           - G gathered lists            [G, nq, L] scores + ids or packed entries (cross-chunk /
+//                                                         cross-shard merge; id < 0 = empty slot; optional peer-signal wait)
+//   tau_select_kernel     the two admission thresholds of the two-pass search from its sampled block maxima
+//   merge_sorted_kernel   S3 for few already-sorted packed lists: positions by binary search, no selection, no sort
+//   front_select_kernel   opt-in experiment: sort all entries above the upper threshold instead of selecting (slower)
 #include <math.h>
 #include <stdlib.h>
 
