@@ -4,6 +4,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/sgpt_b200.h"
 #include "gemm_api.h"
 #include "host_utils.h"
@@ -110,6 +112,14 @@ static int pick_band(int M, int N, int K) {
   return (w_bytes >= (64ll << 20) && m_groups >= 16) ? 8 : 0;
 }
 
+// The 16-warp early-release epilogue (gemm.cuh EpiTma16) for CTA pairs on 256-wide tiles: ON unless SGPT_GEMM_EPI16=0 (read
+// per call: the GPU tests compare both forms in one process).  Same box, alternating runs of bench.py: 38.70 k embeddings/s
+// with 8 epilogue warps, 39.73 / 39.76 k with 16 (GEMM time per step 5.50 -> 5.22 / 5.35 ms).
+static bool epi16_enabled() {
+  const char* e = getenv("SGPT_GEMM_EPI16");
+  return !(e != nullptr && e[0] == '0');
+}
+
 template <class Epi>
 static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                          const typename Epi::Params& p, int bn, cudaStream_t stream, int ksplit = 1) {
@@ -117,6 +127,10 @@ static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw,
   TileMap tm;
   tm.ksplit = ksplit;
   tm.band = pick_band(M, N, K);
+  using Epi16 = typename Epi16Of<Epi>::type;
+  if constexpr (!std::is_same<Epi16, Epi>::value) {
+    if (bn == 256 && pair && epi16_enabled()) return launch_gemm<256, Epi16, 2>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm);
+  }
   if (bn == 256) {
     if (M >= 4 * kGemmBM && cl4_enabled() && ksplit == 1)
       return launch_gemm<256, Epi, 4>(x, ldx, w, ldw, M, N, K, p, stream);

@@ -63,6 +63,13 @@ struct StateHasKs { static constexpr bool value = false; };
 template <class State>
 struct StateHasKs<State, decltype((void)State::ks)> { static constexpr bool value = true; };
 
+// Epilogues with a kEarlyRelease member split their tile work into load() — the warp's accumulator columns into registers
+// — and store(); the kernel hands the TMEM accumulator stage back to the MMA issuer between the two.
+template <class Epi, class = void>
+struct EpiEarlyRelease { static constexpr bool value = false; };
+template <class Epi>
+struct EpiEarlyRelease<Epi, decltype((void)Epi::kEarlyRelease)> { static constexpr bool value = true; };
+
 // Epilogues may state a total staging size (kStagingBytes member); 0 / absent = the default rule of GemmCfg.
 template <class Epi, class = void>
 struct EpiStaging { static constexpr int value = 0; };
@@ -325,12 +332,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + half * kColsPerWarp;
-      Epi::template tile<kColsPerWarp, kSlabBytes>(st, ep, m0, n0, lane, trow, stage_slab, M, N);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
-        else mbar_arrive(&tmem_empty_bar[acc]);
+      if constexpr (EpiEarlyRelease<Epi>::value) {
+        // the accumulator stage goes back to the MMA issuer as soon as this warp's columns are in registers: the stage is
+        // held for one TMEM load, not for the arithmetic, the shared-memory stores, the proxy fence and the TMA hand-over
+        Epi::template load<kColsPerWarp, kSlabBytes>(st, trow);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
+          else mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        Epi::template store<kColsPerWarp, kSlabBytes>(st, ep, m0, n0, lane, stage_slab, M, N);
+      } else {
+        Epi::template tile<kColsPerWarp, kSlabBytes>(st, ep, m0, n0, lane, trow, stage_slab, M, N);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
+          else mbar_arrive(&tmem_empty_bar[acc]);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -442,6 +462,93 @@ struct EpiTma {
     }
   }
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Default for CTA pairs on 256-wide tiles since the end of round 2 (SGPT_GEMM_EPI16=0 restores 8 warps): 16 epilogue warps — four per TMEM lane quarter, 64 accumulator
+// columns (= one 128-byte bf16 box) each — that release the accumulator stage EARLY (kernel: load -> arrive -> store).
+// Why: with 8 warps a warp walks through four boxes per tile in series (smem box free -> tcgen05.ld -> arithmetic -> 8 x
+// st.shared -> fence.proxy.async -> TMA) and keeps the TMEM stage until the last one; at K = 768 that chain is about as
+// long as the 6144-clock mainloop of the next tile, so the MMA issuer waits for a free accumulator (ncu: tensor pipe 41-55 %
+// active, issue slots 15-35 % busy).  Here the stage is held for ONE TMEM load.  640 threads -> at most 96 registers per
+// thread: the 64 accumulator values stay in registers and the box is computed and stored in two halves of four chunks.
+// ---------------------------------------------------------------------------------------------------------------
+template <class Op>
+struct EpiTma16 {
+  using Params = typename Op::Params;
+  struct State {
+    uint32_t it;
+    uint32_t ks;
+    typename Op::Row row;
+    uint32_t v[64];  // this warp's accumulator columns of the current tile (thread = row)
+  };
+  static constexpr int kEpiWarps = 16;
+  static constexpr bool kEarlyRelease = true;
+  static constexpr int kCols = 128 / Op::kElemBytes;  // columns per 128-byte row segment: 64 (bf16) or 32 (fp32)
+  static __device__ __forceinline__ void init(State& st, const Params&, int, uint64_t*) { st.it = 0; st.ks = 0; }
+  template <int BN, int kSlabBytes>
+  static __device__ __forceinline__ void pre_tile(State& st, const Params& p, int m0, int, int lane, float*, int M, int) {
+    if (m0 < M) st.row = Op::row_init(p, m0 + lane, M);
+  }
+  static __device__ __forceinline__ void finish(State&, const Params&, int lane_row) {
+    if ((lane_row & 31) == 0) bulk_wait_group<0>();
+  }
+  template <int BN, int kSlabBytes>
+  static __device__ __forceinline__ void load(State& st, uint32_t trow) {
+    static_assert(BN == 64, "EpiTma16: 64 accumulator columns per warp (256-wide tiles)");
+    tmem_ld_32x32(trow, *reinterpret_cast<uint32_t(*)[32]>(&st.v[0]));
+    tmem_ld_32x32(trow + 32, *reinterpret_cast<uint32_t(*)[32]>(&st.v[32]));
+    tmem_ld_wait();
+  }
+  template <int BN, int kSlabBytes>
+  static __device__ __forceinline__ void store(State& st, const Params& p, int m0, int n0, int lane, float* slab, int M,
+                                               int N) {
+    static_assert(kSlabBytes == 4096, "EpiTma16: one 4 KB box per warp");
+    if (m0 >= M) return;  // whole 32-row slab out of range (warp-uniform)
+    const uint32_t box = smem_u32(slab);
+    const uint32_t row_addr = box + lane * 128u;
+    const typename Op::Row rc = st.row;
+#pragma unroll
+    for (int c = 0; c < BN; c += kCols) {  // one box (bf16 outputs) or two (fp32)
+      const int n = n0 + c;
+      if (n >= N) break;  // warp-uniform
+      if (st.it >= 1) {   // the TMA store of this warp's previous box must have finished READING the box
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t o[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int jj = 4 * h + j;
+          if constexpr (OpSplitK<Op>::value)
+            Op::chunk(p, rc, &st.v[c + jj * (kCols / 8)], n + jj * (kCols / 8), N, m0 + lane, o[j], st.ks == 0);
+          else
+            Op::chunk(p, rc, &st.v[c + jj * (kCols / 8)], n + jj * (kCols / 8), N, m0 + lane, o[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int jj = 4 * h + j;
+          sts_v4(row_addr + ((jj ^ (lane & 7)) << 4), o[j][0], o[j][1], o[j][2], o[j][3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        Op::issue(p, reinterpret_cast<const void*>(__cvta_shared_to_generic(box)), n, m0);
+        bulk_commit_group();
+      }
+      ++st.it;
+    }
+  }
+};
+
+// The 16-warp form of an epilogue, for the three ops it has been validated and measured with (bit-identical outputs,
+// tests/test_gpu_raster.py; whole-model parity; +2.7 % embeddings/s on SGPT-125M, profiles/r02_gemm_epilogue_16_warps_ab.jsonl):
+// bias (+ gelu_new) -> bf16 and the bf16 residual reduce-add.  Every other epilogue (GPT-J rotary, fp32 residual, the
+// LayerNorm-fold family, the search filter) maps to itself.  (The ops are declared below.)
+template <class Epi>
+struct Epi16Of { using type = Epi; };
 
 // bias index helper: columns beyond N are clipped by the tensor map, their bias is read from the last valid entry
 __device__ __forceinline__ float bias_at(const float* bias, int col, int N) {
@@ -1089,6 +1196,11 @@ struct EpiFilterRows {
 };
 using EpiFilterCandidates = EpiFilterRows;
 
+
+template <bool kGelu>
+struct Epi16Of<EpiTma<OpTmaBiasActBF16<kGelu>, 0>> { using type = EpiTma16<OpTmaBiasActBF16<kGelu>>; };
+template <>
+struct Epi16Of<EpiTma<OpTmaResidAddBF16, 0>> { using type = EpiTma16<OpTmaResidAddBF16>; };
 
 template <bool kGelu>
 using EpiBiasActBF16 = EpiTma<OpTmaBiasActBF16<kGelu>>;

@@ -12,15 +12,17 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def band_env():
-    old = os.environ.get("SGPT_GEMM_BAND")
+    old = {k: os.environ.get(k) for k in ("SGPT_GEMM_BAND", "SGPT_GEMM_EPI16")}
     yield
-    if old is None:
-        os.environ.pop("SGPT_GEMM_BAND", None)
-    else:
-        os.environ["SGPT_GEMM_BAND"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
-@pytest.mark.parametrize("M,K,N,epi", [(2700, 256, 1304, "bf16"), (5000, 512, 768, "gelu"), (1290, 1024, 520, "resid")])
+@pytest.mark.parametrize("M,K,N,epi", [(2700, 256, 1304, "bf16"), (5000, 512, 768, "gelu"), (1290, 1024, 520, "resid"),
+                                       (40000, 768, 2304, "bf16")])
 def test_linear_is_independent_of_the_tile_order(M, K, N, epi, band_env):
     from sgpt_b200 import _lib as L
 
@@ -40,6 +42,7 @@ def test_linear_is_independent_of_the_tile_order(M, K, N, epi, band_env):
     xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
     code = {"bf16": L.EPI_BF16, "gelu": L.EPI_GELU_BF16, "resid": L.EPI_RESID_BF16}[epi]
     results = {}
+    os.environ["SGPT_GEMM_EPI16"] = "0"  # the 8-warp epilogue is the reference form; the 16-warp form is compared below
     for setting in ("0", "3", "8"):
         os.environ["SGPT_GEMM_BAND"] = setting
         out = r0.clone().cuda() if epi == "resid" else torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
@@ -50,3 +53,14 @@ def test_linear_is_independent_of_the_tile_order(M, K, N, epi, band_env):
     assert torch.equal(results["0"], results["3"]) and torch.equal(results["0"], results["8"])
     err = (results["8"].double() - want).abs()
     assert bool((err <= 0.02 + 0.01 * want.abs()).all()), float(err.max())
+    # the 16-warp early-release epilogue (the default; SGPT_GEMM_EPI16=1 here, gemm.cuh EpiTma16) runs the same per-element
+    # arithmetic: bit-identical outputs, also across several tiles per CTA (the accumulator stage is released before the
+    # stores of the previous tile have left the warp)
+    os.environ["SGPT_GEMM_BAND"] = "0"
+    os.environ["SGPT_GEMM_EPI16"] = "1"
+    for _ in range(2):
+        out = r0.clone().cuda() if epi == "resid" else torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+        L.check(lib.sgpt_linear(xd.data_ptr(), K, wd.data_ptr(), K, bd.data_ptr(), out.data_ptr(), N,
+                                out.data_ptr() if epi == "resid" else None, M, N, K, code, L.current_stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), results["0"])
