@@ -129,7 +129,9 @@ static int launch_linear(const void* x, int64_t ldx, const void* w, int64_t ldw,
   tm.band = pick_band(M, N, K);
   using Epi16 = typename Epi16Of<Epi>::type;
   if constexpr (!std::is_same<Epi16, Epi>::value) {
-    if (bn == 256 && pair && epi16_enabled()) return launch_gemm<256, Epi16, 2>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm);
+    // (the opt-in 4-CTA-cluster experiment keeps its own 8-warp form)
+    if (bn == 256 && pair && epi16_enabled() && !cl4_enabled())
+      return launch_gemm<256, Epi16, 2>(x, ldx, w, ldw, M, N, K, p, stream, kCatGemm, tm);
   }
   if (bn == 256) {
     if (M >= 4 * kGemmBM && cl4_enabled() && ksplit == 1)
